@@ -1,0 +1,109 @@
+"""Device-resident batched API: torch tensors are the buffers, the C-ABI does the work.
+
+No host copies happen here; inputs and outputs stay in HBM (this is what ``bench.py``'s ``value`` times).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import FarnebackParams, LKParams, GFTTParams
+
+# reference call-site parameters
+FARNEBACK_DEFAULTS = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2,
+                          flags=0)  # DenseOF.py:127-128
+LK_GRID_DEFAULTS = dict(winSize=(45, 45), maxLevel=2, criteria=(3, 10, 0.03))  # pathfinder_viewer.py:154-158
+LK_TRACK_DEFAULTS = dict(winSize=(15, 15), maxLevel=2, criteria=(3, 10, 0.03))  # SparseOF.py:6-8
+GFTT_DEFAULTS = dict(maxCorners=20, qualityLevel=0.3, minDistance=10, blockSize=7)  # SparseOF.py:10-13
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_u8_frames(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.uint8 and t.dim() == 3
+            and t.is_contiguous()):
+        raise _lib.error(-215, f"{name} must be a contiguous CUDA uint8 tensor (N,H,W)")
+
+
+def bgr2gray(bgr, out=None):
+    """uint8 (N,H,W,3) or (H,W,3) CUDA tensor -> uint8 (N,H,W) / (H,W).  Bit-exact with cv2.cvtColor(BGR2GRAY)."""
+    squeeze = bgr.dim() == 3
+    b = bgr.unsqueeze(0) if squeeze else bgr
+    if not (b.is_cuda and b.dtype == torch.uint8 and b.dim() == 4 and b.shape[-1] == 3 and b.is_contiguous()):
+        raise _lib.error(-215, "bgr must be a contiguous CUDA uint8 tensor (N,H,W,3)")
+    n, h, w, _ = b.shape
+    if out is None:
+        out = torch.empty((n, h, w), dtype=torch.uint8, device=b.device)
+    with torch.cuda.device(b.device):
+        _lib.check(_lib.lib().b2of_bgr2gray_u8_dev(_p(b), h, w, w * 3, h * w * 3, _p(out), w, h * w, n, _stream()))
+    return out[0] if squeeze else out
+
+
+def pyrdown(img, out=None):
+    """uint8 (N,H,W) -> uint8 (N,(H+1)//2,(W+1)//2).  Bit-exact with cv2.pyrDown."""
+    _check_u8_frames(img, "img")
+    n, h, w = img.shape
+    dh, dw = (h + 1) // 2, (w + 1) // 2
+    if out is None:
+        out = torch.empty((n, dh, dw), dtype=torch.uint8, device=img.device)
+    with torch.cuda.device(img.device):
+        _lib.check(_lib.lib().b2of_pyrdown_u8_dev(_p(img), h, w, w, h * w, _p(out), dw, dh * dw, n, _stream()))
+    return out
+
+
+class FarnebackEngine:
+    """Batched dense flow on device-resident frames.
+
+    ``chunk_pairs`` pairs are in flight per pass; the scratch (level images, polynomial expansions, flow
+    ping/pong) is allocated once for that many.
+    """
+
+    def __init__(self, rows, cols, chunk_pairs=8, device=None, **params):
+        p = dict(FARNEBACK_DEFAULTS)
+        p.update(params)
+        self.rows, self.cols = int(rows), int(cols)
+        self.params = FarnebackParams(float(p["pyr_scale"]), int(p["levels"]), int(p["winsize"]),
+                                      int(p["iterations"]), int(p["poly_n"]), float(p["poly_sigma"]), int(p["flags"]))
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.chunk_pairs = int(chunk_pairs)
+        l = _lib.lib()
+        with torch.cuda.device(self.device):
+            need = max(l.b2of_farneback_workspace_bytes(self.rows, self.cols, C.byref(self.params), self.chunk_pairs, 0),
+                       l.b2of_farneback_workspace_bytes(self.rows, self.cols, C.byref(self.params), self.chunk_pairs, 1))
+        if need == 0:
+            _lib.check(-215)
+        self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+
+    def flow_sequence(self, frames, out=None):
+        """uint8 (F,H,W) consecutive frames -> float32 (F-1,H,W,2); per-frame work is done once per frame."""
+        _check_u8_frames(frames, "frames")
+        f, h, w = frames.shape
+        assert (h, w) == (self.rows, self.cols)
+        if out is None:
+            out = torch.empty((max(f - 1, 0), h, w, 2), dtype=torch.float32, device=frames.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().b2of_farneback_sequence_dev(_p(frames), w, h * w, f, h, w, C.byref(self.params),
+                                                              _p(out), _p(self.workspace), self.workspace.numel(),
+                                                              _stream()))
+        return out
+
+    def flow_pairs(self, prev, next, out=None):
+        """uint8 (B,H,W) prev and next stacks (independent pairs) -> float32 (B,H,W,2)."""
+        _check_u8_frames(prev, "prev")
+        _check_u8_frames(next, "next")
+        assert prev.shape == next.shape
+        b, h, w = prev.shape
+        assert (h, w) == (self.rows, self.cols)
+        if out is None:
+            out = torch.empty((b, h, w, 2), dtype=torch.float32, device=prev.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().b2of_farneback_pairs_dev(_p(prev), _p(next), w, h * w, b, h, w,
+                                                           C.byref(self.params), _p(out), _p(self.workspace),
+                                                           self.workspace.numel(), _stream()))
+        return out

@@ -1,0 +1,81 @@
+// Shared host/device helpers for libb2of (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+#include <string>
+
+#include "../../include/b2of.h"
+
+namespace b2of {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<unsigned long long> g_launches;
+
+inline int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  set_error("%s", buf);
+  return code;
+}
+
+#define B2OF_CUDA(expr)                                                                          \
+  do {                                                                                           \
+    cudaError_t e__ = (expr);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      return b2of::fail(B2OF_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+// cv2-style assertion: same text shape the reference's user would have seen from cv2.error
+#define B2OF_ASSERT(cond, fn)                                                                    \
+  do {                                                                                           \
+    if (!(cond)) return b2of::fail(B2OF_E_BADARG, "(-215:Assertion failed) %s in function '%s'", #cond, fn); \
+  } while (0)
+
+#define B2OF_LAUNCH_CHECK()                                                                      \
+  do {                                                                                           \
+    b2of::g_launches.fetch_add(1, std::memory_order_relaxed);                                    \
+    cudaError_t e__ = cudaGetLastError();                                                        \
+    if (e__ != cudaSuccess)                                                                      \
+      return b2of::fail(B2OF_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+__host__ __device__ inline int reflect101(int i, int n) {
+  // BORDER_REFLECT_101, valid for any offset
+  if (n == 1) return 0;
+  int period = 2 * (n - 1);
+  i %= period;
+  if (i < 0) i += period;
+  return i >= n ? period - i : i;
+}
+
+__host__ __device__ inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// round-half-to-even, cv::cvRound for doubles
+inline int cv_round(double v) { return (int)nearbyint(v); }
+
+// linear bump allocator over a caller-provided workspace
+struct Arena {
+  char* base;
+  size_t cap;
+  size_t off;
+  Arena(void* p, size_t n) : base((char*)p), cap(n), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = align_up(off, 256);
+    T* r = (T*)(base ? base + off : nullptr);
+    off += count * sizeof(T);
+    return r;
+  }
+  bool ok() const { return off <= cap; }
+};
+
+}  // namespace b2of

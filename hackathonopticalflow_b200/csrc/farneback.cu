@@ -1,0 +1,782 @@
+// K3-K6: dense Farneback flow, replaces cv2.calcOpticalFlowFarneback as called at DenseOF.py:147-156
+// (wrapper DenseOF.py:127-157, call site :520).  Arithmetic spec: SURVEY.md App. A.3 (opencv optflowgf.cpp,
+// GaussianBlur, resize -- third-party, restated in oracle/farneback.py).
+//
+// Data layout in HBM (all float32, per pyramid level k of size w_k x h_k, pitch_k = w_k rounded up to 32):
+//   I_k   [frame][h_k][pitch_k]            blurred + resampled level image            (K3)
+//   R_k   [frame][5][h_k][pitch_k]         polynomial expansion, PLANAR channels      (K4)
+//   F_k   [pair][h_k][pitch_k] float2      flow ping/pong buffers                     (K5)
+// M (the 5-channel matrix field) never leaves the SM: UpdateMatrices, the (2m+1)^2 window sum and the 2x2
+// solve are one kernel per (level, iteration); the x(1/pyr_scale) bilinear flow upsample is folded into
+// the first iteration of each level.
+#include <math.h>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b2of {
+
+constexpr int FB_MIN_SIZE = 32;
+constexpr int FB_MAX_POLY_N = 16;
+
+struct PolyConst {
+  float g[FB_MAX_POLY_N + 1], xg[FB_MAX_POLY_N + 1], xxg[FB_MAX_POLY_N + 1];
+  float ig11, ig03, ig33, ig55;
+};
+
+struct FbLevel {
+  int k, w, h, pitch, ksz;
+  double scale, sigma;
+  // device tables (owned by the plan)
+  float* taps;            // ksz blur taps
+  int *sx0, *sx1, *sy0, *sy1;  // resize source indices
+  float *fx, *fy;         // resize fractions
+  // flow upsample tables from the next-coarser level (valid when k < top level)
+  int *ux0, *ux1, *uy0, *uy1;
+  float *ufx, *ufy;
+};
+
+struct FbPlan {
+  int rows, cols;
+  b2of_farneback_params p;
+  std::vector<FbLevel> lv;  // coarsest first
+  PolyConst pc;
+  float* gauss_taps;  // winsize/2+1 taps for the FARNEBACK_GAUSSIAN window (device)
+  void* table_block;
+  size_t S;  // sum of h*pitch over levels (floats per plane per frame)
+};
+
+// ----------------------------------------------------------------------------------------------
+// host-side plan: level sizes, Gaussian taps, resize tables -- computed exactly as cv2 does
+// ----------------------------------------------------------------------------------------------
+static void gaussian_kernel(int n, double sigma, std::vector<float>& out) {
+  out.resize(n);
+  static const float small3[] = {0.25f, 0.5f, 0.25f};
+  static const float small5[] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
+  static const float small7[] = {0.03125f, 0.109375f, 0.21875f, 0.28125f, 0.21875f, 0.109375f, 0.03125f};
+  if (sigma <= 0 && (n == 1 || n == 3 || n == 5 || n == 7)) {
+    const float* t = n == 3 ? small3 : n == 5 ? small5 : small7;
+    if (n == 1) { out[0] = 1.f; return; }
+    for (int i = 0; i < n; ++i) out[i] = t[i];
+    return;
+  }
+  double s = sigma > 0 ? sigma : ((n - 1) * 0.5 - 1) * 0.3 + 0.8;
+  std::vector<double> k(n);
+  double sum = 0;
+  for (int i = 0; i < n; ++i) {
+    double x = i - (n - 1) * 0.5;
+    k[i] = exp(-(x * x) / (2.0 * s * s));
+    sum += k[i];
+  }
+  for (int i = 0; i < n; ++i) out[i] = (float)(k[i] / sum);
+}
+
+static void linear_tables(int dst_n, int src_n, std::vector<int>& s0, std::vector<int>& s1, std::vector<float>& f) {
+  s0.resize(dst_n); s1.resize(dst_n); f.resize(dst_n);
+  double scale = (double)src_n / dst_n;
+  for (int i = 0; i < dst_n; ++i) {
+    float ff = (float)((i + 0.5) * scale - 0.5);
+    int s = (int)floorf(ff);
+    ff -= s;
+    if (s < 0) { s = 0; ff = 0; }
+    if (s >= src_n - 1) { s = src_n - 1; ff = 0; }
+    s0[i] = s;
+    s1[i] = s + 1 < src_n ? s + 1 : src_n - 1;
+    f[i] = ff;
+  }
+}
+
+static void invert6(double G[6][6], double inv[6][6]) {
+  double a[6][12];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) { a[i][j] = G[i][j]; a[i][j + 6] = i == j; }
+  for (int c = 0; c < 6; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < 6; ++r) if (fabs(a[r][c]) > fabs(a[piv][c])) piv = r;
+    for (int j = 0; j < 12; ++j) { double t = a[c][j]; a[c][j] = a[piv][j]; a[piv][j] = t; }
+    double d = a[c][c];
+    for (int j = 0; j < 12; ++j) a[c][j] /= d;
+    for (int r = 0; r < 6; ++r) if (r != c) {
+      double m = a[r][c];
+      if (m != 0) for (int j = 0; j < 12; ++j) a[r][j] -= m * a[c][j];
+    }
+  }
+  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) inv[i][j] = a[i][j + 6];
+}
+
+static void poly_constants(int n, double sigma, PolyConst& pc) {
+  if (sigma < 1.1920929e-07) sigma = n * 0.3;
+  std::vector<float> g(2 * n + 1);
+  double s = 0;
+  for (int x = -n; x <= n; ++x) { g[x + n] = (float)exp(-x * x / (2 * sigma * sigma)); s += g[x + n]; }
+  s = 1. / s;
+  for (int x = -n; x <= n; ++x) g[x + n] = (float)(g[x + n] * s);
+  double G[6][6] = {{0}};
+  for (int y = -n; y <= n; ++y)
+    for (int x = -n; x <= n; ++x) {
+      double gg = (double)g[y + n] * g[x + n];
+      G[0][0] += gg;
+      G[1][1] += gg * x * x;
+      G[3][3] += gg * x * x * x * x;
+      G[5][5] += gg * x * x * y * y;
+    }
+  G[2][2] = G[0][3] = G[0][4] = G[3][0] = G[4][0] = G[1][1];
+  G[4][4] = G[3][3];
+  G[3][4] = G[4][3] = G[5][5];
+  double inv[6][6];
+  invert6(G, inv);
+  memset(&pc, 0, sizeof pc);
+  for (int k = 0; k <= n; ++k) {
+    pc.g[k] = g[n + k];
+    pc.xg[k] = (float)(k * g[n + k]);
+    pc.xxg[k] = (float)(k * k * g[n + k]);
+  }
+  pc.ig11 = (float)inv[1][1];
+  pc.ig03 = (float)inv[0][3];
+  pc.ig33 = (float)inv[3][3];
+  pc.ig55 = (float)inv[5][5];
+}
+
+struct PlanKey {
+  int dev, rows, cols, levels, winsize, poly_n, flags;
+  double pyr_scale, poly_sigma;
+  bool operator<(const PlanKey& o) const {
+    return memcmp(this, &o, sizeof(PlanKey)) < 0;
+  }
+};
+static std::mutex g_plan_mu;
+static std::map<PlanKey, FbPlan*> g_plans;
+
+static int build_plan(int rows, int cols, const b2of_farneback_params& p, FbPlan** out) {
+  FbPlan* pl = new FbPlan();
+  pl->rows = rows; pl->cols = cols; pl->p = p;
+  int k = 0;
+  double scale = 1;
+  for (; k < p.levels; ++k) {
+    scale *= p.pyr_scale;
+    if (cols * scale < FB_MIN_SIZE || rows * scale < FB_MIN_SIZE) break;
+  }
+  int top = k;
+  std::vector<std::vector<float>> fl;
+  std::vector<std::vector<int>> il;
+  for (int lvl = top; lvl >= 0; --lvl) {
+    FbLevel L{};
+    L.k = lvl;
+    double sc = 1;
+    for (int i = 0; i < lvl; ++i) sc *= p.pyr_scale;
+    L.scale = sc;
+    L.sigma = (1. / sc - 1) * 0.5;
+    int ks = cv_round(L.sigma * 5) | 1;
+    L.ksz = ks > 3 ? ks : 3;
+    L.w = cv_round(cols * sc);
+    L.h = cv_round(rows * sc);
+    L.pitch = (int)align_up(L.w, 32);
+    pl->lv.push_back(L);
+  }
+  // pack all tables into one device block
+  std::vector<char> host;
+  auto put = [&](const void* src, size_t bytes) {
+    size_t off = align_up(host.size(), 16);
+    host.resize(off + bytes);
+    memcpy(host.data() + off, src, bytes);
+    return off;
+  };
+  struct Offs { size_t taps, sx0, sx1, sy0, sy1, fx, fy, ux0, ux1, uy0, uy1, ufx, ufy; };
+  std::vector<Offs> offs(pl->lv.size());
+  pl->S = 0;
+  for (size_t i = 0; i < pl->lv.size(); ++i) {
+    FbLevel& L = pl->lv[i];
+    pl->S += (size_t)L.h * L.pitch;
+    std::vector<float> taps;
+    gaussian_kernel(L.ksz, L.sigma, taps);
+    offs[i].taps = put(taps.data(), taps.size() * 4);
+    std::vector<int> s0, s1;
+    std::vector<float> f;
+    linear_tables(L.w, cols, s0, s1, f);
+    offs[i].sx0 = put(s0.data(), s0.size() * 4); offs[i].sx1 = put(s1.data(), s1.size() * 4); offs[i].fx = put(f.data(), f.size() * 4);
+    linear_tables(L.h, rows, s0, s1, f);
+    offs[i].sy0 = put(s0.data(), s0.size() * 4); offs[i].sy1 = put(s1.data(), s1.size() * 4); offs[i].fy = put(f.data(), f.size() * 4);
+    if (i > 0) {
+      const FbLevel& C = pl->lv[i - 1];
+      linear_tables(L.w, C.w, s0, s1, f);
+      offs[i].ux0 = put(s0.data(), s0.size() * 4); offs[i].ux1 = put(s1.data(), s1.size() * 4); offs[i].ufx = put(f.data(), f.size() * 4);
+      linear_tables(L.h, C.h, s0, s1, f);
+      offs[i].uy0 = put(s0.data(), s0.size() * 4); offs[i].uy1 = put(s1.data(), s1.size() * 4); offs[i].ufy = put(f.data(), f.size() * 4);
+    }
+  }
+  // FARNEBACK_GAUSSIAN window taps (float32, as cv2)
+  int m = p.winsize / 2;
+  std::vector<float> gk(m + 1);
+  {
+    double sigma = m * 0.3;
+    float s = 1.f;
+    gk[0] = 1.f;
+    for (int i = 1; i <= m; ++i) {
+      float t = (float)exp(-i * i / (2 * sigma * sigma));
+      gk[i] = t;
+      s += t * 2;
+    }
+    s = 1.f / s;
+    for (int i = 0; i <= m; ++i) gk[i] = gk[i] * s;
+  }
+  size_t gk_off = put(gk.data(), gk.size() * 4);
+  cudaError_t e = cudaMalloc(&pl->table_block, host.size());
+  if (e != cudaSuccess) { delete pl; return fail(B2OF_E_NOMEM, "cudaMalloc(plan tables) failed: %s", cudaGetErrorString(e)); }
+  e = cudaMemcpy(pl->table_block, host.data(), host.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(pl->table_block); delete pl; return fail(B2OF_E_CUDA, "plan table upload failed: %s", cudaGetErrorString(e)); }
+  char* base = (char*)pl->table_block;
+  for (size_t i = 0; i < pl->lv.size(); ++i) {
+    FbLevel& L = pl->lv[i];
+    L.taps = (float*)(base + offs[i].taps);
+    L.sx0 = (int*)(base + offs[i].sx0); L.sx1 = (int*)(base + offs[i].sx1); L.fx = (float*)(base + offs[i].fx);
+    L.sy0 = (int*)(base + offs[i].sy0); L.sy1 = (int*)(base + offs[i].sy1); L.fy = (float*)(base + offs[i].fy);
+    if (i > 0) {
+      L.ux0 = (int*)(base + offs[i].ux0); L.ux1 = (int*)(base + offs[i].ux1); L.ufx = (float*)(base + offs[i].ufx);
+      L.uy0 = (int*)(base + offs[i].uy0); L.uy1 = (int*)(base + offs[i].uy1); L.ufy = (float*)(base + offs[i].ufy);
+    }
+  }
+  pl->gauss_taps = (float*)(base + gk_off);
+  poly_constants(p.poly_n, p.poly_sigma, pl->pc);
+  *out = pl;
+  return B2OF_OK;
+}
+
+static int get_plan(int rows, int cols, const b2of_farneback_params& p, FbPlan** out) {
+  PlanKey key;
+  memset(&key, 0, sizeof key);
+  cudaGetDevice(&key.dev);
+  key.rows = rows; key.cols = cols; key.levels = p.levels; key.winsize = p.winsize; key.poly_n = p.poly_n;
+  key.flags = p.flags & B2OF_OPTFLOW_FARNEBACK_GAUSSIAN;
+  key.pyr_scale = p.pyr_scale; key.poly_sigma = p.poly_sigma;
+  std::lock_guard<std::mutex> lock(g_plan_mu);
+  auto it = g_plans.find(key);
+  if (it != g_plans.end()) { *out = it->second; return B2OF_OK; }
+  FbPlan* pl = nullptr;
+  int rc = build_plan(rows, cols, p, &pl);
+  if (rc) return rc;
+  g_plans[key] = pl;
+  *out = pl;
+  return B2OF_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// K3: level image = resize_linear(GaussianBlur(float(frame)))  -- two separable passes, each fusing the
+// 1-D blur (REFLECT_101) with the 1-D linear resample.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) fb_level_hpass(const uint8_t* __restrict__ frames, size_t step,
+                                                       size_t frame_stride, int W, int H, float* __restrict__ T,
+                                                       int wk, int pitch, size_t t_frame_stride,
+                                                       const float* __restrict__ taps, int ksz,
+                                                       const int* __restrict__ sx0, const int* __restrict__ sx1,
+                                                       const float* __restrict__ fxs) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y;
+  if (x >= wk) return;
+  const uint8_t* row = frames + blockIdx.z * frame_stride + (size_t)y * step;
+  int r = ksz >> 1;
+  int a = sx0[x], b = sx1[x];
+  float f = fxs[x];
+  float va = 0.f, vb = 0.f;
+  bool interior = a - r >= 0 && b + r < W;
+  if (interior) {
+    for (int t = 0; t < ksz; ++t) {
+      float kt = __ldg(taps + t);
+      va = fmaf(kt, (float)row[a + t - r], va);
+      vb = fmaf(kt, (float)row[b + t - r], vb);
+    }
+  } else {
+    for (int t = 0; t < ksz; ++t) {
+      float kt = __ldg(taps + t);
+      va = fmaf(kt, (float)row[reflect101(a + t - r, W)], va);
+      vb = fmaf(kt, (float)row[reflect101(b + t - r, W)], vb);
+    }
+  }
+  T[blockIdx.z * t_frame_stride + (size_t)y * pitch + x] = va * (1.f - f) + vb * f;
+}
+
+__global__ void __launch_bounds__(128) fb_level_vpass(const float* __restrict__ T, int H, int pitch,
+                                                       size_t t_frame_stride, float* __restrict__ I, int wk, int hk,
+                                                       size_t i_frame_stride, const float* __restrict__ taps, int ksz,
+                                                       const int* __restrict__ sy0, const int* __restrict__ sy1,
+                                                       const float* __restrict__ fys) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y;
+  if (x >= wk) return;
+  const float* tb = T + blockIdx.z * t_frame_stride + x;
+  int r = ksz >> 1;
+  int a = sy0[y], b = sy1[y];
+  float f = fys[y];
+  float va = 0.f, vb = 0.f;
+  for (int t = 0; t < ksz; ++t) {
+    float kt = __ldg(taps + t);
+    va = fmaf(kt, tb[(size_t)reflect101(a + t - r, H) * pitch], va);
+    vb = fmaf(kt, tb[(size_t)reflect101(b + t - r, H) * pitch], vb);
+  }
+  I[blockIdx.z * i_frame_stride + (size_t)y * pitch + x] = va * (1.f - f) + vb * f;
+}
+
+// ----------------------------------------------------------------------------------------------
+// K4: polynomial expansion. 64x32 output tile per CTA; the (32+2n)x(64+2n) input tile and the three
+// vertically filtered rows live in shared memory; REPLICATE borders; planar 5-channel output.
+// ----------------------------------------------------------------------------------------------
+constexpr int PE_TW = 64, PE_TH = 32;
+
+__global__ void __launch_bounds__(256) fb_polyexp(const float* __restrict__ I, int w, int h, int pitch,
+                                                   size_t i_frame_stride, float* __restrict__ R,
+                                                   size_t plane_stride, size_t r_frame_stride, PolyConst pc, int n) {
+  extern __shared__ float smem[];
+  const int sw = PE_TW + 2 * n;  // tile width with halo
+  const int sh = PE_TH + 2 * n;
+  float* s_in = smem;                    // [sh][sw]
+  float* s_r0 = s_in + sh * sw;          // [PE_TH][sw]
+  float* s_r1 = s_r0 + PE_TH * sw;
+  float* s_r2 = s_r1 + PE_TH * sw;
+  const int x0 = blockIdx.x * PE_TW, y0 = blockIdx.y * PE_TH;
+  const float* ib = I + blockIdx.z * i_frame_stride;
+  const int t = threadIdx.x;
+  for (int i = t; i < sh * sw; i += 256) {
+    int r = i / sw, c = i % sw;
+    int gy = clampi(y0 + r - n, 0, h - 1), gx = clampi(x0 + c - n, 0, w - 1);
+    s_in[i] = ib[(size_t)gy * pitch + gx];
+  }
+  __syncthreads();
+  // vertical pass
+  for (int i = t; i < PE_TH * sw; i += 256) {
+    int r = i / sw, c = i % sw;
+    const float* col = s_in + (r + n) * sw + c;
+    float c0 = col[0];
+    float r0 = c0 * pc.g[0], r1 = 0.f, r2 = 0.f;
+    for (int k = 1; k <= n; ++k) {
+      float a = col[-k * sw], b = col[k * sw];
+      float sum = a + b;
+      r0 = fmaf(pc.g[k], sum, r0);
+      r1 = fmaf(pc.xg[k], b - a, r1);
+      r2 = fmaf(pc.xxg[k], sum, r2);
+    }
+    s_r0[i] = r0; s_r1[i] = r1; s_r2[i] = r2;
+  }
+  __syncthreads();
+  // horizontal pass: 64x32 outputs, 8 per thread (same column group, rows ty, ty+8, ...)
+  const int tx = t & 63, ty = t >> 6;
+  float* rb = R + blockIdx.z * r_frame_stride;
+  for (int r = ty; r < PE_TH; r += 4) {
+    int gx = x0 + tx, gy = y0 + r;
+    if (gx >= w || gy >= h) continue;
+    const float* p0 = s_r0 + r * sw + tx + n;
+    const float* p1 = s_r1 + r * sw + tx + n;
+    const float* p2 = s_r2 + r * sw + tx + n;
+    float b1 = p0[0] * pc.g[0], b3 = p1[0] * pc.g[0], b5 = p2[0] * pc.g[0];
+    float b2 = 0.f, b4 = 0.f, b6 = 0.f;
+    for (int k = 1; k <= n; ++k) {
+      float tg = p0[k] + p0[-k];
+      b1 = fmaf(tg, pc.g[k], b1);
+      b4 = fmaf(tg, pc.xxg[k], b4);
+      b2 = fmaf(p0[k] - p0[-k], pc.xg[k], b2);
+      b3 = fmaf(p1[k] + p1[-k], pc.g[k], b3);
+      b6 = fmaf(p1[k] - p1[-k], pc.xg[k], b6);
+      b5 = fmaf(p2[k] + p2[-k], pc.g[k], b5);
+    }
+    size_t o = (size_t)gy * pitch + gx;
+    rb[o] = b3 * pc.ig11;
+    rb[o + plane_stride] = b2 * pc.ig11;
+    rb[o + 2 * plane_stride] = b1 * pc.ig03 + b5 * pc.ig33;
+    rb[o + 3 * plane_stride] = b1 * pc.ig03 + b4 * pc.ig33;
+    rb[o + 4 * plane_stride] = b6 * pc.ig55;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K5/K6: one fused kernel per (level, iteration):
+//   flow_in (zero | previous iteration | bilinear x(1/pyr_scale) upsample of the coarser level)
+//   -> UpdateMatrices on a (T+2m)^2 halo tile (bilinear warp of R1, border attenuation)   [smem M, 5 ch]
+//   -> separable (2m+1)^2 window sum, BORDER_REPLICATE (box, or Gaussian taps with flag 256)
+//   -> per-pixel 2x2 solve -> flow_out
+// ----------------------------------------------------------------------------------------------
+constexpr int IT_T = 32;       // output tile edge
+constexpr int IT_THREADS = 256;
+
+struct IterArgs {
+  const float* R;          // level base, [frame][5][h][pitch]
+  size_t r_frame_stride, plane_stride;
+  int pitch, w, h;
+  int pair_frame_step;     // 1: sequence (pair p = frames p, p+1); 2: independent pairs (2p, 2p+1)
+  int mode;                // 0 zero flow, 1 flow_in at this level, 2 upsample coarse flow
+  const float2* flow_in;   // mode 1: [pair][h][pitch]; mode 2: coarse [pair][ch][cpitch]
+  size_t flow_in_pair_stride;
+  int in_pitch;            // in float2
+  int cw, ch;
+  const int *ux0, *ux1, *uy0, *uy1;
+  const float *ufx, *ufy;
+  float up_mult;
+  float2* flow_out;
+  size_t flow_out_pair_stride;
+  int out_pitch;           // in float2
+  int m;                   // winsize / 2
+  float inv_area;          // 1 / winsize^2 (box)
+  const float* gtaps;      // Gaussian window taps or nullptr
+};
+
+__device__ __forceinline__ float2 fetch_flow(const IterArgs& a, const float2* fin, int x, int y) {
+  if (a.mode == 0) return make_float2(0.f, 0.f);
+  if (a.mode == 1) return fin[(size_t)y * a.in_pitch + x];
+  int xa = a.ux0[x], xb = a.ux1[x], ya = a.uy0[y], yb = a.uy1[y];
+  float fx = a.ufx[x], fy = a.ufy[y];
+  float2 p00 = fin[(size_t)ya * a.in_pitch + xa], p01 = fin[(size_t)ya * a.in_pitch + xb];
+  float2 p10 = fin[(size_t)yb * a.in_pitch + xa], p11 = fin[(size_t)yb * a.in_pitch + xb];
+  float tx0 = p00.x * (1.f - fx) + p01.x * fx, ty0 = p00.y * (1.f - fx) + p01.y * fx;
+  float tx1 = p10.x * (1.f - fx) + p11.x * fx, ty1 = p10.y * (1.f - fx) + p11.y * fx;
+  return make_float2((tx0 * (1.f - fy) + tx1 * fy) * a.up_mult, (ty0 * (1.f - fy) + ty1 * fy) * a.up_mult);
+}
+
+__device__ __forceinline__ float border_w(int i, int n) {
+  // product of the 5-px attenuation table from both ends (UpdateMatrices)
+  const float tab[5] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f};
+  float s = 1.f;
+  if (i < 5) s *= tab[i];
+  if (i >= n - 5) s *= tab[n - 1 - i];
+  return s;
+}
+
+template <bool GAUSS>
+__global__ void __launch_bounds__(IT_THREADS) fb_iter(IterArgs a) {
+  extern __shared__ float smem[];
+  const int m = a.m;
+  const int E = IT_T + 2 * m;       // halo tile edge
+  const int ES = E | 1;             // odd row stride: conflict-free column walks
+  float* sM = smem;                 // [5][E][ES]
+  float* sH = sM + 5 * E * ES;      // [5][E][IT_T+1]   horizontal sums
+  const int HS = IT_T + 1;
+  const int pair = blockIdx.z;
+  const int x0 = blockIdx.x * IT_T, y0 = blockIdx.y * IT_T;
+  const int w = a.w, h = a.h, pitch = a.pitch;
+  const float* R0 = a.R + (size_t)pair * a.pair_frame_step * a.r_frame_stride;
+  const float* R1 = R0 + a.r_frame_stride;
+  const size_t ps = a.plane_stride;
+  const float2* fin = a.flow_in ? a.flow_in + (size_t)pair * a.flow_in_pair_stride : nullptr;
+  const int t = threadIdx.x;
+
+  // ---- step A: M on the halo tile (positions clamped to the image = BORDER_REPLICATE of M) ----
+  for (int i = t; i < E * E; i += IT_THREADS) {
+    int iy = i / E, ix = i - iy * E;
+    int x = clampi(x0 - m + ix, 0, w - 1), y = clampi(y0 - m + iy, 0, h - 1);
+    float2 d = fetch_flow(a, fin, x, y);
+    float fx = (float)x + d.x, fy = (float)y + d.y;
+    float flx = floorf(fx), fly = floorf(fy);
+    int x1 = (int)flx, y1 = (int)fly;
+    fx -= flx; fy -= fly;
+    size_t o = (size_t)y * pitch + x;
+    float q0 = R0[o], q1 = R0[o + ps], q2 = R0[o + 2 * ps], q3 = R0[o + 3 * ps], q4 = R0[o + 4 * ps];
+    float r2, r3, r4, r5, r6;
+    if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+      float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+      const float* p = R1 + (size_t)y1 * pitch + x1;
+      r2 = a00 * p[0] + a01 * p[1] + a10 * p[pitch] + a11 * p[pitch + 1]; p += ps;
+      r3 = a00 * p[0] + a01 * p[1] + a10 * p[pitch] + a11 * p[pitch + 1]; p += ps;
+      r4 = a00 * p[0] + a01 * p[1] + a10 * p[pitch] + a11 * p[pitch + 1]; p += ps;
+      r5 = a00 * p[0] + a01 * p[1] + a10 * p[pitch] + a11 * p[pitch + 1]; p += ps;
+      r6 = a00 * p[0] + a01 * p[1] + a10 * p[pitch] + a11 * p[pitch + 1];
+      r4 = (q2 + r4) * 0.5f;
+      r5 = (q3 + r5) * 0.5f;
+      r6 = (q4 + r6) * 0.25f;
+    } else {
+      r2 = r3 = 0.f;
+      r4 = q2; r5 = q3; r6 = q4 * 0.5f;
+    }
+    r2 = (q0 - r2) * 0.5f;
+    r3 = (q1 - r3) * 0.5f;
+    r2 += r4 * d.y + r6 * d.x;
+    r3 += r6 * d.y + r5 * d.x;
+    if (x < 5 || x >= w - 5 || y < 5 || y >= h - 5) {
+      float s = border_w(x, w) * border_w(y, h);
+      r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
+    }
+    int so = iy * ES + ix;
+    sM[so] = r4 * r4 + r6 * r6;
+    sM[so + E * ES] = (r4 + r5) * r6;
+    sM[so + 2 * E * ES] = r5 * r5 + r6 * r6;
+    sM[so + 3 * E * ES] = r4 * r2 + r6 * r3;
+    sM[so + 4 * E * ES] = r6 * r2 + r5 * r3;
+  }
+  __syncthreads();
+
+  // ---- step B: horizontal window sums, one (channel, row) per work item ----
+  for (int i = t; i < 5 * E; i += IT_THREADS) {
+    const float* row = sM + i * ES;   // (c*E + iy) * ES
+    float* out = sH + i * HS;
+    if (GAUSS) {
+      for (int x = 0; x < IT_T; ++x) {
+        float s = row[x + m] * a.gtaps[0];
+        for (int k = 1; k <= m; ++k) s = fmaf(row[x + m - k] + row[x + m + k], a.gtaps[k], s);
+        out[x] = s;
+      }
+    } else {
+      float s = 0.f;
+      for (int k = 0; k < 2 * m; ++k) s += row[k];
+      for (int x = 0; x < IT_T; ++x) {
+        s += row[x + 2 * m];
+        out[x] = s;
+        s -= row[x];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- step C: vertical window sums + 2x2 solve; thread = (column, 4-row segment) ----
+  {
+    const int x = t & 31, seg = t >> 5;   // 8 segments of 4 rows
+    const int gx = x0 + x;
+    float acc[5];
+    float2* fo = a.flow_out + (size_t)pair * a.flow_out_pair_stride;
+    if (GAUSS) {
+      for (int r = 0; r < 4; ++r) {
+        int y = seg * 4 + r;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          const float* col = sH + (c * E + y + m) * HS + x;
+          float s = col[0] * a.gtaps[0];
+          for (int k = 1; k <= m; ++k) s = fmaf(col[-k * HS] + col[k * HS], a.gtaps[k], s);
+          acc[c] = s;
+        }
+        int gy = y0 + y;
+        if (gx < w && gy < h) {
+          float g11 = acc[0], g12 = acc[1], g22 = acc[2], h1 = acc[3], h2 = acc[4];
+          float idet = 1.f / (g11 * g22 - g12 * g12 + 1e-3f);
+          fo[(size_t)gy * a.out_pitch + gx] = make_float2((g11 * h2 - g12 * h1) * idet, (g22 * h1 - g12 * h2) * idet);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        const float* col = sH + (c * E + seg * 4) * HS + x;
+        float s = 0.f;
+        for (int k = 0; k < 2 * m; ++k) s += col[k * HS];
+        acc[c] = s;
+      }
+      for (int r = 0; r < 4; ++r) {
+        int y = seg * 4 + r;
+        float v[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          const float* col = sH + (c * E + y) * HS + x;
+          acc[c] += col[2 * m * HS];
+          v[c] = acc[c] * a.inv_area;
+          acc[c] -= col[0];
+        }
+        int gy = y0 + y;
+        if (gx < w && gy < h) {
+          float g11 = v[0], g12 = v[1], g22 = v[2], h1 = v[3], h2 = v[4];
+          float idet = 1.f / (g11 * g22 - g12 * g12 + 1e-3f);
+          fo[(size_t)gy * a.out_pitch + gx] = make_float2((g11 * h2 - g12 * h1) * idet, (g22 * h1 - g12 * h2) * idet);
+        }
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host driver
+// ----------------------------------------------------------------------------------------------
+struct FbWorkspace {
+  float* T;       // [frames][rows][pitch0]
+  float* I;       // [frames][S]
+  float* R;       // per level: [frames][5][h][pitch]; level bases via offsets
+  float2* FA;     // per level ping: [pairs][h][pitch]
+  float2* FB;     // per level pong
+  size_t bytes;
+};
+
+static size_t fb_layout(const FbPlan* pl, int pairs, int frames, void* base, size_t cap, FbWorkspace* ws) {
+  Arena ar(base, cap);
+  size_t pitch0 = align_up(pl->cols, 32);
+  ws->T = ar.take<float>((size_t)frames * pl->rows * pitch0);
+  ws->I = ar.take<float>((size_t)frames * pl->S);
+  ws->R = ar.take<float>((size_t)frames * 5 * pl->S);
+  ws->FA = ar.take<float2>((size_t)pairs * pl->S);
+  ws->FB = ar.take<float2>((size_t)pairs * pl->S);
+  ws->bytes = align_up(ar.off, 256);
+  return ws->bytes;
+}
+
+static int check_params(int rows, int cols, const b2of_farneback_params* p) {
+  const char* fn = "calcOpticalFlowFarneback";
+  B2OF_ASSERT(p != nullptr, fn);
+  B2OF_ASSERT(rows > 0 && cols > 0, fn);
+  B2OF_ASSERT(p->pyr_scale > 0 && p->pyr_scale < 1, fn);
+  B2OF_ASSERT(p->levels >= 0, fn);
+  B2OF_ASSERT(p->winsize >= 1, fn);
+  B2OF_ASSERT(p->iterations >= 0, fn);
+  B2OF_ASSERT(p->poly_n >= 1, fn);
+  if (p->poly_n > FB_MAX_POLY_N) return fail(B2OF_E_UNSUPPORTED, "poly_n > %d is not supported", FB_MAX_POLY_N);
+  if (p->flags & B2OF_OPTFLOW_USE_INITIAL_FLOW)
+    return fail(B2OF_E_UNSUPPORTED, "OPTFLOW_USE_INITIAL_FLOW is not supported yet (not used by the reference)");
+  if (p->winsize / 2 > 45) return fail(B2OF_E_UNSUPPORTED, "winsize > 91 is not supported");
+  return B2OF_OK;
+}
+
+size_t farneback_workspace_bytes(int rows, int cols, const b2of_farneback_params* p, int chunk_pairs, int shared) {
+  if (check_params(rows, cols, p)) return 0;
+  FbPlan* pl;
+  if (get_plan(rows, cols, *p, &pl)) return 0;
+  FbWorkspace ws;
+  int frames = shared ? chunk_pairs + 1 : 2 * chunk_pairs;
+  return fb_layout(pl, chunk_pairs, frames, nullptr, 0, &ws);
+}
+
+// per-frame work: level images + polynomial expansion for `frames` frames; frame i lands in workspace
+// slot slot0 + i*slot_step (independent pairs interleave prev/next frames: slot_step 2)
+static int fb_frames(const FbPlan* pl, const FbWorkspace& ws, const uint8_t* frames_dev, size_t step,
+                     size_t frame_stride, int frames, int slot0, int slot_step, int total_slots, cudaStream_t st) {
+  const int W = pl->cols, H = pl->rows;
+  size_t pitch0 = align_up(W, 32);
+  size_t lvl_off = 0;
+  for (size_t li = 0; li < pl->lv.size(); ++li) {
+    const FbLevel& L = pl->lv[li];
+    size_t plane = (size_t)L.h * L.pitch;
+    float* Tb = ws.T + (size_t)slot0 * H * pitch0;
+    float* Ib = ws.I + (size_t)total_slots * lvl_off + (size_t)slot0 * plane;
+    float* Rb = ws.R + (size_t)total_slots * 5 * lvl_off + (size_t)slot0 * 5 * plane;
+    size_t t_stride = (size_t)H * pitch0 * slot_step, i_stride = plane * slot_step, r_stride = 5 * plane * slot_step;
+    dim3 g1(cdiv(L.w, 128), H, frames);
+    fb_level_hpass<<<g1, 128, 0, st>>>(frames_dev, step, frame_stride, W, H, Tb, L.w, L.pitch, t_stride, L.taps, L.ksz,
+                                       L.sx0, L.sx1, L.fx);
+    B2OF_LAUNCH_CHECK();
+    dim3 g2(cdiv(L.w, 128), L.h, frames);
+    fb_level_vpass<<<g2, 128, 0, st>>>(Tb, H, L.pitch, t_stride, Ib, L.w, L.h, i_stride, L.taps, L.ksz, L.sy0, L.sy1,
+                                       L.fy);
+    B2OF_LAUNCH_CHECK();
+    int n = pl->p.poly_n;
+    size_t smem = ((size_t)(PE_TH + 2 * n) * (PE_TW + 2 * n) + 3 * (size_t)PE_TH * (PE_TW + 2 * n)) * sizeof(float);
+    dim3 g3(cdiv(L.w, PE_TW), cdiv(L.h, PE_TH), frames);
+    fb_polyexp<<<g3, 256, smem, st>>>(Ib, L.w, L.h, L.pitch, i_stride, Rb, plane, r_stride, pl->pc, n);
+    B2OF_LAUNCH_CHECK();
+    lvl_off += plane;
+  }
+  return B2OF_OK;
+}
+
+static std::once_flag g_attr_once;
+static void set_func_attrs() {
+  cudaFuncSetAttribute(fb_iter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(fb_iter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(fb_polyexp, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+// iterations for `pairs` pairs whose frames sit in workspace slots (pair p -> slots p*fstep, p*fstep+1)
+static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fstep, int total_slots, float* flow_out,
+                    cudaStream_t st) {
+  const b2of_farneback_params& p = pl->p;
+  const int m = p.winsize / 2;
+  const bool gauss = (p.flags & B2OF_OPTFLOW_FARNEBACK_GAUSSIAN) != 0;
+  const int E = IT_T + 2 * m;
+  size_t smem = ((size_t)5 * E * (E | 1) + (size_t)5 * E * (IT_T + 1)) * sizeof(float);
+  if (smem > 227 * 1024) return fail(B2OF_E_UNSUPPORTED, "winsize %d needs %zu B of shared memory", p.winsize, smem);
+  size_t lvl_off = 0;
+  const float2* coarse = nullptr;
+  int cpitch = 0, cw = 0, ch = 0;
+  size_t cstride = 0;
+  for (size_t li = 0; li < pl->lv.size(); ++li) {
+    const FbLevel& L = pl->lv[li];
+    const bool last_level = li + 1 == pl->lv.size();
+    size_t plane = (size_t)L.h * L.pitch;
+    float2* A = ws.FA + (size_t)pairs * lvl_off;
+    float2* B = ws.FB + (size_t)pairs * lvl_off;
+    IterArgs a{};
+    a.R = ws.R + (size_t)total_slots * 5 * lvl_off;
+    a.r_frame_stride = 5 * plane;
+    a.plane_stride = plane;
+    a.pitch = L.pitch; a.w = L.w; a.h = L.h;
+    a.pair_frame_step = fstep;
+    a.m = m;
+    a.inv_area = (float)(1.0 / ((double)p.winsize * p.winsize));
+    a.gtaps = gauss ? pl->gauss_taps : nullptr;
+    a.ux0 = L.ux0; a.ux1 = L.ux1; a.uy0 = L.uy0; a.uy1 = L.uy1; a.ufx = L.ufx; a.ufy = L.ufy;
+    a.up_mult = (float)(1.0 / p.pyr_scale);
+    const float2* cur = nullptr;  // flow at this level after the previous iteration
+    int cur_pitch = 0;
+    size_t cur_stride = 0;
+    dim3 grid(cdiv(L.w, IT_T), cdiv(L.h, IT_T), pairs);
+    int iters = p.iterations;
+    if (iters == 0) {
+      // cv2 with iterations == 0 returns the (upsampled) initial flow of the finest level untouched;
+      // run one pass of the upsample through a degenerate path is not worth a kernel: treat as unsupported
+      return fail(B2OF_E_UNSUPPORTED, "iterations == 0 is not supported");
+    }
+    for (int it = 0; it < iters; ++it) {
+      if (it == 0) {
+        if (coarse) {
+          a.mode = 2; a.flow_in = coarse; a.flow_in_pair_stride = cstride; a.in_pitch = cpitch; a.cw = cw; a.ch = ch;
+        } else {
+          a.mode = 0; a.flow_in = nullptr;
+        }
+      } else {
+        a.mode = 1; a.flow_in = cur; a.flow_in_pair_stride = cur_stride; a.in_pitch = cur_pitch;
+      }
+      bool final_out = last_level && it == iters - 1;
+      float2* dst;
+      int dpitch;
+      size_t dstride;
+      if (final_out) {
+        dst = (float2*)flow_out; dpitch = L.w; dstride = (size_t)L.w * L.h;
+      } else {
+        dst = (it & 1) ? B : A; dpitch = L.pitch; dstride = plane;
+      }
+      a.flow_out = dst; a.out_pitch = dpitch; a.flow_out_pair_stride = dstride;
+      if (gauss) fb_iter<true><<<grid, IT_THREADS, smem, st>>>(a);
+      else fb_iter<false><<<grid, IT_THREADS, smem, st>>>(a);
+      B2OF_LAUNCH_CHECK();
+      cur = dst; cur_pitch = dpitch; cur_stride = dstride;
+    }
+    coarse = cur; cpitch = cur_pitch; cstride = cur_stride; cw = L.w; ch = L.h;
+    lvl_off += plane;
+  }
+  return B2OF_OK;
+}
+
+int farneback_dev(const uint8_t* prev, const uint8_t* next, size_t step, size_t frame_stride, int n_pairs, int shared,
+                  int rows, int cols, const b2of_farneback_params* p, float* flow, void* workspace,
+                  size_t workspace_bytes, cudaStream_t st) {
+  int rc = check_params(rows, cols, p);
+  if (rc) return rc;
+  const char* fn = "calcOpticalFlowFarneback";
+  B2OF_ASSERT(prev != nullptr && next != nullptr && flow != nullptr, fn);
+  B2OF_ASSERT(step >= (size_t)cols, fn);
+  if (n_pairs <= 0) return B2OF_OK;
+  FbPlan* pl;
+  rc = get_plan(rows, cols, *p, &pl);
+  if (rc) return rc;
+  std::call_once(g_attr_once, set_func_attrs);
+  // largest chunk the workspace can hold
+  FbWorkspace ws;
+  int chunk = n_pairs;
+  while (chunk >= 1) {
+    int frames = shared ? chunk + 1 : 2 * chunk;
+    if (fb_layout(pl, chunk, frames, nullptr, 0, &ws) <= workspace_bytes) break;
+    chunk = chunk > 1 ? (chunk + 1) / 2 : 0;
+  }
+  if (chunk < 1)
+    return fail(B2OF_E_NOMEM, "farneback workspace too small: %zu B given, %zu B needed for one pair", workspace_bytes,
+                fb_layout(pl, 1, 2, nullptr, 0, &ws));
+  size_t flow_pair = (size_t)rows * cols * 2;
+  for (int p0 = 0; p0 < n_pairs; p0 += chunk) {
+    int np = n_pairs - p0 < chunk ? n_pairs - p0 : chunk;
+    int frames = shared ? np + 1 : 2 * np;
+    fb_layout(pl, np, frames, workspace, workspace_bytes, &ws);
+    if (shared) {
+      rc = fb_frames(pl, ws, prev + (size_t)p0 * frame_stride, step, frame_stride, frames, 0, 1, frames, st);
+      if (rc) return rc;
+    } else {
+      // independent pairs: prev[i] -> slot 2i, next[i] -> slot 2i+1
+      rc = fb_frames(pl, ws, prev + (size_t)p0 * frame_stride, step, frame_stride, np, 0, 2, frames, st);
+      if (rc) return rc;
+      rc = fb_frames(pl, ws, next + (size_t)p0 * frame_stride, step, frame_stride, np, 1, 2, frames, st);
+      if (rc) return rc;
+    }
+    rc = fb_pairs(pl, ws, np, shared ? 1 : 2, frames, flow + (size_t)p0 * flow_pair, st);
+    if (rc) return rc;
+  }
+  return B2OF_OK;
+}
+
+}  // namespace b2of

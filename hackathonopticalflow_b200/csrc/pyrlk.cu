@@ -1,0 +1,374 @@
+// K10-K11: pyramidal Lucas-Kanade, replaces cv2.calcOpticalFlowPyrLK as called at pathfinder_viewer.py:156-158 /
+// DenseOF.py:183-185 (45x45 grid form, prev = current frame, next = previous frame) and SparseOF.py:35-36
+// (15x15 track form).  Arithmetic spec: SURVEY.md App. A.4 (opencv lkpyramid.cpp -- third-party, restated in
+// oracle/pyrlk.py): u8 pyrDown chain, int16 Scharr derivatives, 14-bit fixed-point bilinear patches, float32
+// 2x2 normal equations, <= maxCount Newton steps.
+//
+// One warp per feature, all pyramid levels inside one launch; the template patch (Iw, Ixw, Iyw as int16)
+// lives in shared memory, window sums are exact integers reduced with warp shuffles.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace b2of {
+
+int pyrdown_dev(const uint8_t*, int, int, size_t, size_t, uint8_t*, size_t, size_t, int, cudaStream_t);
+
+constexpr int LK_MAX_LEVELS = 12;
+constexpr int LK_WARPS = 4;
+
+struct LkLevels {
+  int n;  // number of levels (effective maxLevel + 1)
+  int w[LK_MAX_LEVELS], h[LK_MAX_LEVELS];
+  size_t step[LK_MAX_LEVELS];
+  size_t off[LK_MAX_LEVELS];         // byte offset of level l inside one image's pyramid block
+  size_t doff[LK_MAX_LEVELS];        // short2 offset of level l inside one image's derivative block
+  size_t pyr_bytes, deriv_elems;     // per image
+};
+
+static int lk_plan(int rows, int cols, const b2of_lk_params* p, LkLevels* L) {
+  memset(L, 0, sizeof *L);
+  int w = cols, h = rows, n = 0;
+  size_t off = 0, doff = 0;
+  for (int level = 0; level <= p->max_level && level < LK_MAX_LEVELS; ++level) {
+    L->w[n] = w; L->h[n] = h;
+    L->step[n] = align_up(w, 16);
+    L->off[n] = off; L->doff[n] = doff;
+    off += align_up(L->step[n] * h, 256);
+    doff += align_up((size_t)w * h, 64);
+    ++n;
+    w = (w + 1) / 2; h = (h + 1) / 2;
+    if (w <= p->win_w || h <= p->win_h) break;
+  }
+  L->n = n;
+  L->pyr_bytes = off;
+  L->deriv_elems = doff;
+  return B2OF_OK;
+}
+
+// ---- K10: Scharr 3x3 -> (Ix, Iy) int16, REFLECT_101 (calcScharrDeriv) ----
+__global__ void __launch_bounds__(256) lk_scharr(const uint8_t* __restrict__ img, size_t step, size_t img_bstride,
+                                                  int w, int h, short2* __restrict__ d, size_t d_bstride) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  const uint8_t* b = img + blockIdx.z * img_bstride;
+  int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+  const uint8_t* r0 = b + (size_t)reflect101(y - 1, h) * step;
+  const uint8_t* r1 = b + (size_t)y * step;
+  const uint8_t* r2 = b + (size_t)reflect101(y + 1, h) * step;
+  int t0m = (r0[xm] + r2[xm]) * 3 + r1[xm] * 10, t0p = (r0[xp] + r2[xp]) * 3 + r1[xp] * 10;
+  int t1m = r2[xm] - r0[xm], t1c = r2[x] - r0[x], t1p = r2[xp] - r0[xp];
+  d[blockIdx.z * d_bstride + (size_t)y * w + x] = make_short2((short)(t0p - t0m), (short)((t1m + t1p) * 3 + t1c * 10));
+}
+
+struct LkArgs {
+  const uint8_t* pyr_i;   // [batch] pyramid blocks of the first image
+  const uint8_t* pyr_j;   // [batch] pyramid blocks of the second image
+  const short2* deriv;    // [batch] derivative blocks of the first image
+  LkLevels L;
+  const float* prev_pts; size_t pts_bstride;  // in points
+  float* next_pts; uint8_t* status; float* err;
+  int n_pts;
+  int ww, wh;
+  int max_count; float eps2d_hi, eps2d_lo;  // eps^2 as a double split (hi + lo)
+  int flags; float min_eig_thr;
+};
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    int lo = __shfl_xor_sync(0xffffffffu, (int)(v & 0xffffffffll), o);
+    int hi = __shfl_xor_sync(0xffffffffu, (int)(v >> 32), o);
+    v += ((long long)hi << 32) | (unsigned int)lo;
+  }
+  return v;
+}
+
+__device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
+  // cvRound((1-a)(1-b)*2^14) ...: float products rounded half-to-even
+  w00 = __float2int_rn(__fmul_rn(__fmul_rn(1.f - a, 1.f - b), 16384.f));
+  w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, 1.f - b), 16384.f));
+  w10 = __float2int_rn(__fmul_rn(__fmul_rn(1.f - a, b), 16384.f));
+  w11 = 16384 - w00 - w01 - w10;
+}
+
+__device__ __forceinline__ int img_px(const uint8_t* img, size_t step, int w, int h, int x, int y, bool inside) {
+  if (!inside) { x = reflect101(x, w); y = reflect101(y, h); }
+  return img[(size_t)y * step + x];
+}
+
+// sum over the window of (bilinear(J) >> 9 - Iw) * {Ixw, Iyw}  (or |diff| when ABS)
+template <bool ABS>
+__device__ __forceinline__ void lk_window_pass(const uint8_t* J, size_t step, int w, int h, int ix, int iy, int w00,
+                                               int w01, int w10, int w11, const short* sI, const short2* sD, int ww,
+                                               int wh, int lane, long long& o1, long long& o2) {
+  const bool inside = ix >= 0 && iy >= 0 && ix + ww < w && iy + wh < h;
+  const int n = ww * wh;
+  long long s1 = 0, s2 = 0;
+  int a1 = 0, a2 = 0, cnt = 0;
+  int x = lane % ww, y = lane / ww;
+  for (int p = lane; p < n; p += 32) {
+    int gx = ix + x, gy = iy + y;
+    int v;
+    if (inside) {
+      const uint8_t* q = J + (size_t)gy * step + gx;
+      v = q[0] * w00 + q[1] * w01 + q[step] * w10 + q[step + 1] * w11;
+    } else {
+      v = img_px(J, step, w, h, gx, gy, false) * w00 + img_px(J, step, w, h, gx + 1, gy, false) * w01 +
+          img_px(J, step, w, h, gx, gy + 1, false) * w10 + img_px(J, step, w, h, gx + 1, gy + 1, false) * w11;
+    }
+    int diff = ((v + 256) >> 9) - (int)sI[p];
+    if (ABS) {
+      a1 += diff < 0 ? -diff : diff;
+    } else {
+      short2 d = sD[p];
+      a1 += diff * (int)d.x;
+      a2 += diff * (int)d.y;
+    }
+    if (++cnt == 32) { s1 += a1; s2 += a2; a1 = a2 = 0; cnt = 0; }
+    x += 32;
+    while (x >= ww) { x -= ww; ++y; }
+  }
+  s1 += a1; s2 += a2;
+  o1 = warp_sum_ll(s1);
+  o2 = ABS ? 0 : warp_sum_ll(s2);
+}
+
+__global__ void __launch_bounds__(LK_WARPS * 32) lk_track(LkArgs a) {
+  extern __shared__ __align__(16) unsigned char lk_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pt = blockIdx.x * LK_WARPS + warp;
+  const int b = blockIdx.y;
+  if (pt >= a.n_pts) return;
+  const int ww = a.ww, wh = a.wh, n = ww * wh;
+  const size_t per_warp = align_up16((size_t)n * 6);
+  short* sI = (short*)(lk_smem + warp * per_warp);
+  short2* sD = (short2*)(sI + ((n + 1) & ~1));
+  const uint8_t* PI = a.pyr_i + (size_t)b * a.L.pyr_bytes;
+  const uint8_t* PJ = a.pyr_j + (size_t)b * a.L.pyr_bytes;
+  const short2* DV = a.deriv + (size_t)b * a.L.deriv_elems;
+  const size_t pidx = (size_t)b * a.pts_bstride + pt;
+  const size_t oidx = (size_t)b * a.n_pts + pt;
+  const float ppx = a.prev_pts[2 * pidx], ppy = a.prev_pts[2 * pidx + 1];
+  const float hx = (ww - 1) * 0.5f, hy = (wh - 1) * 0.5f;
+  const float FLT_SCALE = 1.f / (1 << 20);
+  const double eps2 = (double)a.eps2d_hi + (double)a.eps2d_lo;
+  float nx = 0.f, ny = 0.f;  // nextPts[i]
+  if (a.flags & B2OF_OPTFLOW_USE_INITIAL_FLOW) { nx = a.next_pts[2 * oidx]; ny = a.next_pts[2 * oidx + 1]; }
+  int status = 1;
+  float err = 0.f;
+  const int max_level = a.L.n - 1;
+  for (int level = max_level; level >= 0; --level) {
+    const int W = a.L.w[level], H = a.L.h[level];
+    const size_t step = a.L.step[level];
+    const uint8_t* I = PI + a.L.off[level];
+    const uint8_t* J = PJ + a.L.off[level];
+    const short2* D = DV + a.L.doff[level];
+    const float sc = 1.f / (float)(1 << level);
+    float px = ppx * sc, py = ppy * sc;
+    float qx, qy;  // nextPt
+    if (level == max_level) {
+      if (a.flags & B2OF_OPTFLOW_USE_INITIAL_FLOW) { qx = nx * sc; qy = ny * sc; }
+      else { qx = px; qy = py; }
+    } else {
+      qx = nx * 2.f; qy = ny * 2.f;
+    }
+    nx = qx; ny = qy;
+    px -= hx; py -= hy;
+    int ipx = (int)floorf(px), ipy = (int)floorf(py);
+    if (ipx < -ww || ipx >= W || ipy < -wh || ipy >= H) {
+      if (level == 0) { status = 0; err = 0.f; }
+      continue;
+    }
+    int w00, w01, w10, w11;
+    lk_weights(px - ipx, py - ipy, w00, w01, w10, w11);
+    // ---- template patch + normal matrix ----
+    long long sA11 = 0, sA12 = 0, sA22 = 0;
+    {
+      const bool inside = ipx >= 0 && ipy >= 0 && ipx + ww < W && ipy + wh < H;
+      int c11 = 0, c12 = 0, c22 = 0, cnt = 0;
+      int x = lane % ww, y = lane / ww;
+      __syncwarp();
+      for (int p = lane; p < n; p += 32) {
+        int gx = ipx + x, gy = ipy + y;
+        int iv, dxv, dyv;
+        if (inside) {
+          const uint8_t* q = I + (size_t)gy * step + gx;
+          iv = q[0] * w00 + q[1] * w01 + q[step] * w10 + q[step + 1] * w11;
+          const short2* dq = D + (size_t)gy * W + gx;
+          short2 d00 = dq[0], d01 = dq[1], d10 = dq[W], d11 = dq[W + 1];
+          dxv = d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11;
+          dyv = d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11;
+        } else {
+          iv = img_px(I, step, W, H, gx, gy, false) * w00 + img_px(I, step, W, H, gx + 1, gy, false) * w01 +
+               img_px(I, step, W, H, gx, gy + 1, false) * w10 + img_px(I, step, W, H, gx + 1, gy + 1, false) * w11;
+          dxv = dyv = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            int xx = gx + (k & 1), yy = gy + (k >> 1);
+            int wk = k == 0 ? w00 : k == 1 ? w01 : k == 2 ? w10 : w11;
+            if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
+              short2 d = D[(size_t)yy * W + xx];
+              dxv += d.x * wk; dyv += d.y * wk;
+            }
+          }
+        }
+        int ival = (iv + 256) >> 9;
+        int ixv = (dxv + 8192) >> 14, iyv = (dyv + 8192) >> 14;
+        sI[p] = (short)ival;
+        sD[p] = make_short2((short)ixv, (short)iyv);
+        c11 += ixv * ixv; c12 += ixv * iyv; c22 += iyv * iyv;
+        if (++cnt == 32) { sA11 += c11; sA12 += c12; sA22 += c22; c11 = c12 = c22 = 0; cnt = 0; }
+        x += 32;
+        while (x >= ww) { x -= ww; ++y; }
+      }
+      sA11 += c11; sA12 += c12; sA22 += c22;
+      sA11 = warp_sum_ll(sA11); sA12 = warp_sum_ll(sA12); sA22 = warp_sum_ll(sA22);
+      __syncwarp();
+    }
+    float A11 = __fmul_rn((float)sA11, FLT_SCALE), A12 = __fmul_rn((float)sA12, FLT_SCALE),
+          A22 = __fmul_rn((float)sA22, FLT_SCALE);
+    float Dt = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+    float dd = __fsub_rn(A11, A22);
+    float min_eig = __fdiv_rn(
+        __fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(__fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12)))),
+        (float)(2 * ww * wh));
+    if (a.flags & B2OF_OPTFLOW_LK_GET_MIN_EIGENVALS) err = min_eig;
+    if (min_eig < a.min_eig_thr || Dt < 1.1920929e-07f) {
+      if (level == 0) status = 0;
+      continue;
+    }
+    Dt = __fdiv_rn(1.f, Dt);
+    qx -= hx; qy -= hy;
+    float pdx = 0.f, pdy = 0.f;
+    for (int j = 0; j < a.max_count; ++j) {
+      int ix = (int)floorf(qx), iy = (int)floorf(qy);
+      if (ix < -ww || ix >= W || iy < -wh || iy >= H) {
+        if (level == 0) status = 0;
+        break;
+      }
+      lk_weights(qx - ix, qy - iy, w00, w01, w10, w11);
+      long long s1, s2;
+      lk_window_pass<false>(J, step, W, H, ix, iy, w00, w01, w10, w11, sI, sD, ww, wh, lane, s1, s2);
+      float b1 = __fmul_rn((float)s1, FLT_SCALE), b2 = __fmul_rn((float)s2, FLT_SCALE);
+      float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), Dt);
+      float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), Dt);
+      qx += dx; qy += dy;
+      nx = qx + hx; ny = qy + hy;
+      if ((double)dx * dx + (double)dy * dy <= eps2) break;
+      if (j > 0 && fabsf(dx + pdx) < 0.01f && fabsf(dy + pdy) < 0.01f) {
+        nx -= dx * 0.5f; ny -= dy * 0.5f;
+        break;
+      }
+      pdx = dx; pdy = dy;
+    }
+    if (status && level == 0 && !(a.flags & B2OF_OPTFLOW_LK_GET_MIN_EIGENVALS)) {
+      float ex = nx - hx, ey = ny - hy;
+      int ix = (int)floorf(ex), iy = (int)floorf(ey);
+      if (ix < -ww || ix >= W || iy < -wh || iy >= H) {
+        status = 0;
+      } else {
+        lk_weights(ex - ix, ey - iy, w00, w01, w10, w11);
+        long long s1, s2;
+        lk_window_pass<true>(J, step, W, H, ix, iy, w00, w01, w10, w11, sI, sD, ww, wh, lane, s1, s2);
+        err = __fmul_rn((float)s1, 1.f / (float)(32 * ww * wh));
+      }
+    }
+  }
+  if (lane == 0) {
+    a.next_pts[2 * oidx] = nx;
+    a.next_pts[2 * oidx + 1] = ny;
+    a.status[oidx] = (uint8_t)status;
+    a.err[oidx] = err;
+  }
+}
+
+static int lk_check(int rows, int cols, const b2of_lk_params* p) {
+  const char* fn = "calcOpticalFlowPyrLK";
+  B2OF_ASSERT(p != nullptr, fn);
+  B2OF_ASSERT(rows > 0 && cols > 0, fn);
+  B2OF_ASSERT(p->max_level >= 0 && p->win_w > 2 && p->win_h > 2, fn);
+  size_t per_warp = align_up((size_t)p->win_w * p->win_h * 6, 16) + 16;
+  if (per_warp * LK_WARPS > 200 * 1024)
+    return fail(B2OF_E_UNSUPPORTED, "winSize %dx%d needs more shared memory than one SM has", p->win_w, p->win_h);
+  return B2OF_OK;
+}
+
+size_t pyrlk_workspace_bytes(int rows, int cols, const b2of_lk_params* p, int batch) {
+  if (lk_check(rows, cols, p)) return 0;
+  LkLevels L;
+  lk_plan(rows, cols, p, &L);
+  if (batch < 1) batch = 1;
+  return (size_t)batch * (2 * L.pyr_bytes + L.deriv_elems * sizeof(short2)) + 1024;
+}
+
+int pyrlk_dev(const uint8_t* prev, const uint8_t* next, size_t step, size_t frame_stride, int batch, int rows, int cols,
+              const float* prev_pts, size_t pts_bstride, int n_pts, float* next_pts, uint8_t* status, float* err,
+              const b2of_lk_params* p, void* ws, size_t ws_bytes, cudaStream_t st) {
+  int rc = lk_check(rows, cols, p);
+  if (rc) return rc;
+  const char* fn = "calcOpticalFlowPyrLK";
+  B2OF_ASSERT(prev != nullptr && next != nullptr && step >= (size_t)cols, fn);
+  B2OF_ASSERT(n_pts >= 0 && batch >= 0, fn);
+  if (n_pts == 0 || batch == 0) return B2OF_OK;
+  B2OF_ASSERT(prev_pts != nullptr && next_pts != nullptr && status != nullptr && err != nullptr, fn);
+  LkArgs a{};
+  lk_plan(rows, cols, p, &a.L);
+  size_t need = (size_t)batch * (2 * a.L.pyr_bytes + a.L.deriv_elems * sizeof(short2));
+  if (ws == nullptr || ws_bytes < need)
+    return fail(B2OF_E_NOMEM, "pyrlk workspace too small: %zu B given, %zu B needed", ws_bytes, need);
+  uint8_t* pi = (uint8_t*)ws;
+  uint8_t* pj = pi + (size_t)batch * a.L.pyr_bytes;
+  short2* dv = (short2*)(pj + (size_t)batch * a.L.pyr_bytes);
+  // level 0: copy into the padded-step pyramid block, then the pyrDown chain
+  for (int which = 0; which < 2; ++which) {
+    uint8_t* dst = which ? pj : pi;
+    const uint8_t* src = which ? next : prev;
+    if (batch == 1 || frame_stride != 0) {
+      for (int b = 0; b < batch; ++b)
+        B2OF_CUDA(cudaMemcpy2DAsync(dst + (size_t)b * a.L.pyr_bytes, a.L.step[0], src + (size_t)b * frame_stride, step,
+                                    cols, rows, cudaMemcpyDeviceToDevice, st));
+    } else {
+      return fail(B2OF_E_BADARG, "frame_stride == 0 with batch > 1");
+    }
+    for (int l = 1; l < a.L.n; ++l) {
+      rc = pyrdown_dev(dst + a.L.off[l - 1], a.L.h[l - 1], a.L.w[l - 1], a.L.step[l - 1], a.L.pyr_bytes,
+                       dst + a.L.off[l], a.L.step[l], a.L.pyr_bytes, batch, st);
+      if (rc) return rc;
+    }
+  }
+  for (int l = 0; l < a.L.n; ++l) {
+    dim3 grid(cdiv(a.L.w[l], 256), a.L.h[l], batch);
+    lk_scharr<<<grid, 256, 0, st>>>(pi + a.L.off[l], a.L.step[l], a.L.pyr_bytes, a.L.w[l], a.L.h[l], dv + a.L.doff[l],
+                                    a.L.deriv_elems);
+    B2OF_LAUNCH_CHECK();
+  }
+  a.pyr_i = pi; a.pyr_j = pj; a.deriv = dv;
+  a.prev_pts = prev_pts; a.pts_bstride = pts_bstride;
+  a.next_pts = next_pts; a.status = status; a.err = err;
+  a.n_pts = n_pts;
+  a.ww = p->win_w; a.wh = p->win_h;
+  int mc = 30;
+  double eps = 0.001;
+  if (p->crit_type & B2OF_TERM_COUNT) mc = p->crit_max_count < 0 ? 0 : (p->crit_max_count > 100 ? 100 : p->crit_max_count);
+  if (p->crit_type & B2OF_TERM_EPS) eps = p->crit_eps < 0 ? 0. : (p->crit_eps > 10. ? 10. : p->crit_eps);
+  double eps2 = eps * eps;
+  a.max_count = mc;
+  a.eps2d_hi = (float)eps2;
+  a.eps2d_lo = (float)(eps2 - (double)a.eps2d_hi);
+  a.flags = p->flags;
+  a.min_eig_thr = (float)p->min_eig_threshold;
+  size_t per_warp = align_up((size_t)p->win_w * p->win_h * 6, 16);
+  size_t smem = per_warp * LK_WARPS;
+  static std::atomic<size_t> max_set{0};
+  if (smem > 48 * 1024 && smem > max_set.load()) {
+    B2OF_CUDA(cudaFuncSetAttribute(lk_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    max_set.store(smem);
+  }
+  dim3 grid(cdiv(n_pts, LK_WARPS), batch);
+  lk_track<<<grid, LK_WARPS * 32, smem, st>>>(a);
+  B2OF_LAUNCH_CHECK();
+  return B2OF_OK;
+}
+
+}  // namespace b2of

@@ -1,0 +1,175 @@
+/*
+ * b2of.h -- C-ABI of libb2of.so, the B200 (sm_100a) optical-flow engine.
+ *
+ * This is the drop-in boundary for the per-frame-pair hot path of
+ * spirinis/HackathonOpticalFlow.  The reference defines no plugin API of its own:
+ * the path sits behind four `cv2` Python calls, so every entry point below names
+ * the reference call site (file:line) whose arithmetic it replaces.  Shorthands:
+ *   viewer.py   = /root/reference/pathfinder_viewer.py
+ *   DenseOF.py  = /root/reference/<dev dir>/DenseOF.py
+ *   SparseOF.py = /root/reference/<dev dir>/SparseOF.py
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / numpy / cv types.
+ *   - `*_dev` pointers are CUDA device pointers on the current device; `stream`
+ *     is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - `*_host` entry points take ordinary host memory, do their own H2D/D2H on an
+ *     internal stream and return after the result is in the caller's buffer --
+ *     exactly the contract of the cv2 call they replace.
+ *   - return value: 0 on success, negative B2OF_E_* on failure; the message is
+ *     available from b2of_last_error() (thread-local).  Argument failures mirror
+ *     the cv2 assertion the reference would have hit (cv2.error -215).
+ *   - images are 8-bit single channel, row-major, `step` bytes between rows.
+ *   - dense flow is float32 (rows, cols, 2) interleaved (dx, dy), C-contiguous.
+ *   - there is NO CPU fallback anywhere behind this header.
+ */
+#ifndef B2OF_H
+#define B2OF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2OF_VERSION 100
+
+#define B2OF_OK 0
+#define B2OF_E_BADARG (-215) /* cv2's StsAssert code: same meaning */
+#define B2OF_E_CUDA (-1)
+#define B2OF_E_NOMEM (-4)
+#define B2OF_E_UNSUPPORTED (-213) /* cv2's StsNotImplemented */
+
+/* cv2 flag values (cv2.OPTFLOW_*), kept numerically identical */
+#define B2OF_OPTFLOW_USE_INITIAL_FLOW 4
+#define B2OF_OPTFLOW_LK_GET_MIN_EIGENVALS 8
+#define B2OF_OPTFLOW_FARNEBACK_GAUSSIAN 256
+#define B2OF_TERM_COUNT 1
+#define B2OF_TERM_EPS 2
+
+int b2of_version(void);
+const char* b2of_last_error(void);
+/* number of kernel launches issued by this library in this process (all threads) */
+unsigned long long b2of_launch_count(void);
+
+/* ---- K1: cv2.cvtColor(img, cv2.COLOR_BGR2GRAY) --------------------------------
+ * replaces viewer.py:244, :280; DenseOF.py:481, :510; SparseOF.py:28.
+ * `batch` images, `src_batch_stride`/`dst_batch_stride` bytes apart. Bit-exact. */
+int b2of_bgr2gray_u8_dev(const uint8_t* bgr_dev, int rows, int cols, size_t src_step, size_t src_batch_stride,
+                         uint8_t* gray_dev, size_t dst_step, size_t dst_batch_stride, int batch, void* stream);
+int b2of_bgr2gray_u8_host(const uint8_t* bgr, int rows, int cols, size_t src_step, uint8_t* gray, size_t dst_step);
+
+/* ---- K2: cv2.pyrDown on 8-bit gray (the chain buildOpticalFlowPyramid runs inside
+ * cv2.calcOpticalFlowPyrLK; viewer.py:156-158, SparseOF.py:35-36). Bit-exact.
+ * dst is ((rows+1)/2, (cols+1)/2). */
+int b2of_pyrdown_u8_dev(const uint8_t* src_dev, int rows, int cols, size_t src_step, size_t src_batch_stride,
+                        uint8_t* dst_dev, size_t dst_step, size_t dst_batch_stride, int batch, void* stream);
+int b2of_pyrdown_u8_host(const uint8_t* src, int rows, int cols, size_t src_step, uint8_t* dst, size_t dst_step);
+
+/* ---- K3-K6: cv2.calcOpticalFlowFarneback ---------------------------------------
+ * replaces DenseOF.py:147-156 (wrapper calculate_optical_flow DenseOF.py:127-157,
+ * call site :520; reference parameters 0.5, 3, 15, 3, 5, 1.2, 0). */
+typedef struct b2of_farneback_params {
+  double pyr_scale;
+  int levels;
+  int winsize;
+  int iterations;
+  int poly_n;
+  double poly_sigma;
+  int flags;
+} b2of_farneback_params;
+
+/* bytes of device scratch needed to process `chunk_pairs` pairs at once.
+ * shared_frames != 0: the pairs are consecutive frames of one sequence, per-frame
+ * work (level images, polynomial expansion) is done once per frame. */
+size_t b2of_farneback_workspace_bytes(int rows, int cols, const b2of_farneback_params* p, int chunk_pairs,
+                                      int shared_frames);
+
+/* n_pairs independent pairs: pair i is (prev_dev + i*frame_stride, next_dev + i*frame_stride);
+ * flow_dev + i*rows*cols*2 receives its flow.  The workspace decides how many pairs
+ * run per pass (>= 1 pair's worth is required). */
+int b2of_farneback_pairs_dev(const uint8_t* prev_dev, const uint8_t* next_dev, size_t step, size_t frame_stride,
+                             int n_pairs, int rows, int cols, const b2of_farneback_params* p, float* flow_dev,
+                             void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* n_frames consecutive frames -> n_frames-1 flows (frame i -> frame i+1). */
+int b2of_farneback_sequence_dev(const uint8_t* frames_dev, size_t step, size_t frame_stride, int n_frames, int rows,
+                                int cols, const b2of_farneback_params* p, float* flow_dev, void* workspace_dev,
+                                size_t workspace_bytes, void* stream);
+
+/* the cv2 call itself: host prev/next in, host flow out (flow must not be NULL; the
+ * Python shim allocates it when the caller passed None, as cv2 does). */
+int b2of_farneback_host(const uint8_t* prev, const uint8_t* next, size_t step, int rows, int cols,
+                        const b2of_farneback_params* p, float* flow);
+/* pipelined host form: n_pairs pairs from host memory, copies overlapped with compute */
+int b2of_farneback_pairs_host(const uint8_t* prev, const uint8_t* next, size_t step, size_t frame_stride, int n_pairs,
+                              int rows, int cols, const b2of_farneback_params* p, float* flow);
+
+/* ---- K10-K11: cv2.calcOpticalFlowPyrLK ------------------------------------------
+ * replaces viewer.py:156-158 / DenseOF.py:183-185 (45x45 grid form, prev = current
+ * frame) and SparseOF.py:35-36 (15x15 track form, forward + backward). */
+typedef struct b2of_lk_params {
+  int win_w, win_h;
+  int max_level;
+  int crit_type; /* B2OF_TERM_* bits */
+  int crit_max_count;
+  double crit_eps;
+  int flags;
+  double min_eig_threshold;
+} b2of_lk_params;
+
+size_t b2of_pyrlk_workspace_bytes(int rows, int cols, const b2of_lk_params* p, int batch);
+/* batch image pairs, each tracking the same number of points.
+ * prev_pts/next_pts: float32 (batch, n_pts, 2); status uint8 (batch, n_pts); err float32 (batch, n_pts).
+ * next_pts is read only when flags has USE_INITIAL_FLOW. pts_batch_stride (in points) may be 0
+ * to track one shared point set (the viewer's grid) in every pair. */
+int b2of_pyrlk_dev(const uint8_t* prev_dev, const uint8_t* next_dev, size_t step, size_t frame_stride, int batch,
+                   int rows, int cols, const float* prev_pts_dev, size_t pts_batch_stride, int n_pts,
+                   float* next_pts_dev, uint8_t* status_dev, float* err_dev, const b2of_lk_params* p,
+                   void* workspace_dev, size_t workspace_bytes, void* stream);
+int b2of_pyrlk_host(const uint8_t* prev, const uint8_t* next, size_t step, int rows, int cols, const float* prev_pts,
+                    int n_pts, float* next_pts, uint8_t* status, float* err, const b2of_lk_params* p);
+
+/* ---- K7-K9: cv2.goodFeaturesToTrack ---------------------------------------------
+ * replaces SparseOF.py:69 (feature_params SparseOF.py:10-13, mask SparseOF.py:61-66). */
+typedef struct b2of_gftt_params {
+  int max_corners;
+  double quality_level;
+  double min_distance;
+  int block_size;
+  int gradient_size; /* 3 only */
+  int use_harris;
+  double k;
+} b2of_gftt_params;
+
+size_t b2of_gftt_workspace_bytes(int rows, int cols, const b2of_gftt_params* p, int batch);
+/* corners_dev: float32 (batch, corners_cap, 2) (x,y); n_corners_dev: int32 (batch). mask may be NULL. */
+int b2of_gftt_dev(const uint8_t* img_dev, const uint8_t* mask_dev, size_t step, size_t frame_stride, int batch,
+                  int rows, int cols, const b2of_gftt_params* p, float* corners_dev, int corners_cap,
+                  int* n_corners_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+int b2of_gftt_host(const uint8_t* img, const uint8_t* mask, size_t step, size_t mask_step, int rows, int cols,
+                   const b2of_gftt_params* p, float* corners, int corners_cap, int* n_corners);
+
+/* ---- K12: the reference's own downstream logic, per frame, on the device ----------
+ * vector filter viewer.py:159-178 and danger intensity viewer.py:210-217.
+ * For each of `batch` frames: inputs prev points (shared grid if pts_batch_stride==0)
+ * and LK next points; outputs, compacted in input order:
+ *   kept_pts int32 (batch, n_pts, 2), kept_flow int32 (batch, n_pts, 2),
+ *   danger_v uint8 (batch, n_pts), mask uint8 (batch, n_pts), n_kept int32 (batch),
+ *   stats float32 (batch, 8): mean|flow|, max|flow|, mean dx, mean dy,
+ *                             median modulus, p99 modulus, n_kept, sum danger V. */
+#define B2OF_STATS_WIDTH 8
+int b2of_pathfinder_filter_dev(const float* pts_dev, size_t pts_batch_stride, const float* next_pts_dev, int n_pts,
+                               int batch, int width, int height, int32_t* kept_pts_dev, int32_t* kept_flow_dev,
+                               uint8_t* danger_v_dev, uint8_t* mask_dev, int32_t* n_kept_dev, float* stats_dev,
+                               void* stream);
+
+/* dense-flow statistics (what draw_flow / draw_hsv consume, DenseOF.py:44-50, :113-121):
+ * per pair float32[8]: mean|flow|, max|flow|, mean dx, mean dy, 0, 0, 0, 0 */
+int b2of_flow_stats_dev(const float* flow_dev, int n_pairs, int rows, int cols, float* stats_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2OF_H */
