@@ -11,7 +11,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libb2of.so")
-SOURCES = ["api.cu", "gray_pyr.cu", "farneback.cu", "stubs_tmp.cu"]
+SOURCES = ["api.cu", "gray_pyr.cu", "farneback.cu", "pyrlk.cu", "gftt.cu", "pathfinder.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -107,3 +107,103 @@ class FarnebackEngine:
                                                            C.byref(self.params), _p(out), _p(self.workspace),
                                                            self.workspace.numel(), _stream()))
         return out
+
+
+def _lk_params(winSize, maxLevel, criteria, flags, minEigThreshold):
+    return LKParams(int(winSize[0]), int(winSize[1]), int(maxLevel), int(criteria[0]), int(criteria[1]),
+                    float(criteria[2]), int(flags), float(minEigThreshold))
+
+
+def pyrlk(prev, next, prev_pts, next_pts=None, winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01), flags=0,
+          minEigThreshold=1e-4, workspace=None):
+    """Batched cv2.calcOpticalFlowPyrLK on device tensors.
+
+    prev/next: uint8 (B,H,W); prev_pts: float32 (N,2) shared by every pair, or (B,N,2).
+    Returns next_pts float32 (B,N,2), status uint8 (B,N), err float32 (B,N).
+    """
+    _check_u8_frames(prev, "prev")
+    _check_u8_frames(next, "next")
+    assert prev.shape == next.shape
+    b, h, w = prev.shape
+    shared = prev_pts.dim() == 2
+    n = prev_pts.shape[-2]
+    if not (prev_pts.is_cuda and prev_pts.dtype == torch.float32 and prev_pts.is_contiguous()
+            and prev_pts.shape[-1] == 2 and (shared or prev_pts.shape[0] == b)):
+        raise _lib.error(-215, "(npoints = prevPtsMat.checkVector(2, CV_32F, true)) >= 0")
+    p = _lk_params(winSize, maxLevel, criteria, flags, minEigThreshold)
+    l = _lib.lib()
+    if next_pts is None:
+        if flags & 4:
+            raise _lib.error(-215, "nextPtsMat.checkVector(2, CV_32F, true) == npoints")
+        next_pts = torch.empty((b, n, 2), dtype=torch.float32, device=prev.device)
+    status = torch.empty((b, n), dtype=torch.uint8, device=prev.device)
+    err = torch.empty((b, n), dtype=torch.float32, device=prev.device)
+    with torch.cuda.device(prev.device):
+        need = l.b2of_pyrlk_workspace_bytes(h, w, C.byref(p), b)
+        if need == 0:
+            _lib.check(-215)
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty(need, dtype=torch.uint8, device=prev.device)
+        _lib.check(l.b2of_pyrlk_dev(_p(prev), _p(next), w, h * w, b, h, w, _p(prev_pts), 0 if shared else n, n,
+                                    _p(next_pts), _p(status), _p(err), C.byref(p), _p(workspace), workspace.numel(),
+                                    _stream()))
+    return next_pts, status, err
+
+
+def gftt(img, mask=None, maxCorners=20, qualityLevel=0.3, minDistance=10, blockSize=7, useHarrisDetector=False,
+         k=0.04, cap=None, workspace=None):
+    """Batched cv2.goodFeaturesToTrack: uint8 (B,H,W) [+ mask (B,H,W)] -> corners float32 (B,cap,2), count int32 (B)."""
+    _check_u8_frames(img, "img")
+    if mask is not None:
+        _check_u8_frames(mask, "mask")
+        assert mask.shape == img.shape
+    b, h, w = img.shape
+    p = GFTTParams(int(maxCorners), float(qualityLevel), float(minDistance), int(blockSize), 3,
+                   int(bool(useHarrisDetector)), float(k))
+    if cap is None:
+        cap = int(maxCorners) if maxCorners > 0 else 4096
+    corners = torch.zeros((b, cap, 2), dtype=torch.float32, device=img.device)
+    count = torch.zeros((b,), dtype=torch.int32, device=img.device)
+    l = _lib.lib()
+    with torch.cuda.device(img.device):
+        need = l.b2of_gftt_workspace_bytes(h, w, C.byref(p), b)
+        if need == 0:
+            _lib.check(-215)
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty(need, dtype=torch.uint8, device=img.device)
+        _lib.check(l.b2of_gftt_dev(_p(img), _p(mask), w, h * w, b, h, w, C.byref(p), _p(corners), cap, _p(count),
+                                   _p(workspace), workspace.numel(), _stream()))
+    return corners, count
+
+
+def pathfinder_filter(pts, next_pts, width, height):
+    """The viewer's vector filter + danger intensity (pathfinder_viewer.py:159-178, :210-217) per frame.
+
+    pts float32 (N,2) shared grid or (B,N,2); next_pts float32 (B,N,2).
+    Returns dict(kept_pts int32 (B,N,2), kept_flow int32 (B,N,2), danger_v uint8 (B,N), mask uint8 (B,N),
+                 n_kept int32 (B), stats float32 (B,8)); rows [0, n_kept[b]) of the kept_* arrays are valid.
+    """
+    b, n, _ = next_pts.shape
+    shared = pts.dim() == 2
+    dev = next_pts.device
+    out = dict(kept_pts=torch.zeros((b, n, 2), dtype=torch.int32, device=dev),
+               kept_flow=torch.zeros((b, n, 2), dtype=torch.int32, device=dev),
+               danger_v=torch.zeros((b, n), dtype=torch.uint8, device=dev),
+               mask=torch.zeros((b, n), dtype=torch.uint8, device=dev),
+               n_kept=torch.zeros((b,), dtype=torch.int32, device=dev),
+               stats=torch.zeros((b, 8), dtype=torch.float32, device=dev))
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b2of_pathfinder_filter_dev(_p(pts), 0 if shared else n, _p(next_pts), n, b, int(width),
+                                                         int(height), _p(out["kept_pts"]), _p(out["kept_flow"]),
+                                                         _p(out["danger_v"]), _p(out["mask"]), _p(out["n_kept"]),
+                                                         _p(out["stats"]), _stream()))
+    return out
+
+
+def flow_stats(flow):
+    """float32 (B,H,W,2) -> float32 (B,8): mean|flow|, max|flow|, mean dx, mean dy, 0, 0, 0, 0 (deterministic)."""
+    b, h, w, _ = flow.shape
+    stats = torch.empty((b, 8), dtype=torch.float32, device=flow.device)
+    with torch.cuda.device(flow.device):
+        _lib.check(_lib.lib().b2of_flow_stats_dev(_p(flow), b, h, w, _p(stats), _stream()))
+    return stats

@@ -1,0 +1,292 @@
+// K7-K9: Shi-Tomasi corners, replaces cv2.goodFeaturesToTrack as called at SparseOF.py:69 (feature_params
+// SparseOF.py:10-13, disc mask SparseOF.py:61-66).  Arithmetic spec: SURVEY.md App. A.5 (opencv corner.cpp +
+// featureselect.cpp -- third-party, restated in oracle/gftt.py).
+//   K7 gftt_mineig      : Sobel 3x3 -> products -> blockSize^2 box (REFLECT_101) -> min eigenvalue, + masked max
+//   K8 gftt_nms_compact : quality threshold + 3x3 non-max suppression + mask, warp-aggregated compaction
+//   K9 gftt_select      : sort (value desc, address desc) + greedy min-distance pass (sequential semantics)
+#include <math.h>
+
+#include "common.cuh"
+
+namespace b2of {
+
+constexpr int GF_T = 32;  // output tile edge
+
+__device__ __forceinline__ unsigned int f2ord(float f) {
+  unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned int k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void __launch_bounds__(256) gftt_mineig(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask,
+                                                    size_t step, size_t frame_stride, int w, int h, int bs,
+                                                    float scale, int harris, float hk, float* __restrict__ eig,
+                                                    unsigned int* __restrict__ max_key) {
+  extern __shared__ __align__(16) unsigned char gsm[];
+  const int r = bs / 2;
+  const int E = GF_T + bs - 1;  // halo tile edge (anchor at bs/2, window [-r, bs-1-r])
+  float* sC = (float*)gsm;                       // [3][E][E]
+  double* sH = (double*)(sC + ((3 * E * E + 1) & ~1));  // [3][E][GF_T]
+  const int x0 = blockIdx.x * GF_T, y0 = blockIdx.y * GF_T;
+  const uint8_t* ib = img + blockIdx.z * frame_stride;
+  const int t = threadIdx.x;
+  for (int i = t; i < E * E; i += 256) {
+    int iy = i / E, ix = i - iy * E;
+    int x = reflect101(x0 - r + ix, w), y = reflect101(y0 - r + iy, h);
+    int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+    const uint8_t* r0 = ib + (size_t)reflect101(y - 1, h) * step;
+    const uint8_t* r1 = ib + (size_t)y * step;
+    const uint8_t* r2 = ib + (size_t)reflect101(y + 1, h) * step;
+    int dx = (r0[xp] + 2 * r1[xp] + r2[xp]) - (r0[xm] + 2 * r1[xm] + r2[xm]);
+    int dy = (r2[xm] + 2 * r2[x] + r2[xp]) - (r0[xm] + 2 * r0[x] + r0[xp]);
+    float fx = (float)dx * scale, fy = (float)dy * scale;
+    sC[i] = fx * fx;
+    sC[E * E + i] = fx * fy;
+    sC[2 * E * E + i] = fy * fy;
+  }
+  __syncthreads();
+  for (int i = t; i < 3 * E * GF_T; i += 256) {
+    int c = i / (E * GF_T), rem = i - c * E * GF_T;
+    int iy = rem / GF_T, x = rem - iy * GF_T;
+    const float* row = sC + c * E * E + iy * E + x;
+    double s = 0;
+    for (int k = 0; k < bs; ++k) s += (double)row[k];
+    sH[i] = s;
+  }
+  __syncthreads();
+  unsigned int local_max = 0;  // ordered key; 0 is below every real float
+  const uint8_t* mb = mask ? mask + blockIdx.z * frame_stride : nullptr;
+  for (int i = t; i < GF_T * GF_T; i += 256) {
+    int y = i / GF_T, x = i - y * GF_T;
+    int gx = x0 + x, gy = y0 + y;
+    if (gx >= w || gy >= h) continue;
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int k = 0; k < bs; ++k) {
+      s0 += sH[(y + k) * GF_T + x];
+      s1 += sH[E * GF_T + (y + k) * GF_T + x];
+      s2 += sH[2 * E * GF_T + (y + k) * GF_T + x];
+    }
+    float c0 = (float)s0, c1 = (float)s1, c2 = (float)s2, v;
+    if (harris) {
+      v = __fsub_rn(__fsub_rn(__fmul_rn(c0, c2), __fmul_rn(c1, c1)), __fmul_rn(__fmul_rn(hk, __fadd_rn(c0, c2)), __fadd_rn(c0, c2)));
+    } else {
+      float a = c0 * 0.5f, b = c1, c = c2 * 0.5f;
+      float d = __fsub_rn(a, c);
+      v = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b))));
+    }
+    eig[blockIdx.z * (size_t)w * h + (size_t)gy * w + gx] = v;
+    if (!mb || mb[(size_t)gy * step + gx]) {
+      unsigned int k = f2ord(v);
+      local_max = k > local_max ? k : local_max;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned int other = __shfl_xor_sync(0xffffffffu, local_max, o);
+    local_max = other > local_max ? other : local_max;
+  }
+  if ((t & 31) == 0 && local_max) atomicMax(max_key + blockIdx.z, local_max);
+}
+
+__global__ void __launch_bounds__(256) gftt_nms_compact(const float* __restrict__ eig,
+                                                         const uint8_t* __restrict__ mask, size_t step,
+                                                         size_t frame_stride, int w, int h, double quality,
+                                                         const unsigned int* __restrict__ max_key,
+                                                         unsigned long long* __restrict__ cand, int cand_cap,
+                                                         int* __restrict__ cand_count) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int b = blockIdx.z;
+  const float* e = eig + (size_t)b * w * h;
+  bool is_cand = false;
+  float v = 0.f;
+  if (x >= 1 && x < w - 1 && y >= 1 && y < h - 1) {
+    unsigned int mk = max_key[b];
+    float max_val = mk ? ord2f(mk) : 0.f;
+    float thr = (float)((double)max_val * quality);
+    v = e[(size_t)y * w + x];
+    if (v > thr && v != 0.f && (!mask || mask[b * frame_stride + (size_t)y * step + x])) {
+      is_cand = true;
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx)
+          if (e[(size_t)(y + dy) * w + x + dx] > v) is_cand = false;
+    }
+  }
+  unsigned int ballot = __ballot_sync(0xffffffffu, is_cand);
+  if (ballot) {
+    int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(cand_count + b, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (is_cand) {
+      int slot = base + __popc(ballot & ((1u << lane) - 1));
+      if (slot < cand_cap)
+        cand[(size_t)b * cand_cap + slot] = ((unsigned long long)f2ord(v) << 32) | (unsigned int)(y * w + x);
+    }
+  }
+}
+
+// One CTA per image: bitonic sort (descending 64-bit keys = value desc, then address desc) of the candidate
+// list padded to a power of two, then the greedy min-distance pass with warp 0 (lane k scans bucket k of the
+// 3x3 neighbourhood; candidates are visited strictly in sorted order, as featureselect.cpp does).
+__global__ void __launch_bounds__(1024) gftt_select(unsigned long long* __restrict__ cand, int cand_cap,
+                                                     const int* __restrict__ cand_count, int w, int h,
+                                                     int max_corners, float min_dist, int* __restrict__ cell_head,
+                                                     int* __restrict__ next_in_cell, float* __restrict__ corners,
+                                                     int corners_cap, int* __restrict__ n_corners) {
+  const int b = blockIdx.x;
+  unsigned long long* keys = cand + (size_t)b * cand_cap;
+  int n = cand_count[b];
+  if (n > cand_cap) n = cand_cap;
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  if (np2 > cand_cap) np2 = cand_cap;  // cand_cap is a power of two
+  for (int i = n + threadIdx.x; i < np2; i += blockDim.x) keys[i] = 0ull;
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+        int l = i ^ j;
+        if (l > i) {
+          unsigned long long a = keys[i], c = keys[l];
+          bool desc = (i & k) == 0;
+          if (desc ? a < c : a > c) { keys[i] = c; keys[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  float* out = corners + (size_t)b * corners_cap * 2;
+  if (min_dist < 1.f) {
+    int total = (max_corners > 0 && n > max_corners) ? max_corners : n;
+    for (int i = threadIdx.x; i < total && i < corners_cap; i += blockDim.x) {
+      unsigned int idx = (unsigned int)(keys[i] & 0xffffffffull);
+      out[2 * i] = (float)(idx % w);
+      out[2 * i + 1] = (float)(idx / w);
+    }
+    if (threadIdx.x == 0) n_corners[b] = total;
+    return;
+  }
+  const int cell = __float2int_rn(min_dist);
+  const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
+  int* head = cell_head + (size_t)b * gw * gh;
+  int* nxt = next_in_cell + (size_t)b * cand_cap;
+  for (int i = threadIdx.x; i < gw * gh; i += blockDim.x) head[i] = -1;
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  const float md2 = min_dist * min_dist;
+  int accepted = 0;
+  for (int i = 0; i < n; ++i) {
+    unsigned int idx = (unsigned int)(keys[i] & 0xffffffffull);
+    int x = idx % w, y = idx / w;
+    int cx = x / cell, cy = y / cell;
+    bool bad = false;
+    if (lane < 9) {
+      int xx = cx + lane % 3 - 1, yy = cy + lane / 3 - 1;
+      if (xx >= 0 && xx < gw && yy >= 0 && yy < gh) {
+        for (int q = head[yy * gw + xx]; q >= 0; q = nxt[q]) {
+          unsigned int qi = (unsigned int)(keys[q] & 0xffffffffull);
+          float dx = (float)(x - (int)(qi % w)), dy = (float)(y - (int)(qi / w));
+          if (dx * dx + dy * dy < md2) { bad = true; break; }
+        }
+      }
+    }
+    if (__any_sync(0xffffffffu, bad)) continue;
+    if (lane == 0) {
+      nxt[i] = head[cy * gw + cx];
+      head[cy * gw + cx] = i;
+      if (accepted < corners_cap) { out[2 * accepted] = (float)x; out[2 * accepted + 1] = (float)y; }
+    }
+    __syncwarp();
+    ++accepted;
+    if (max_corners > 0 && accepted == max_corners) break;
+  }
+  if (lane == 0) n_corners[b] = accepted;
+}
+
+static int gftt_check(int rows, int cols, const b2of_gftt_params* p) {
+  const char* fn = "goodFeaturesToTrack";
+  B2OF_ASSERT(p != nullptr, fn);
+  B2OF_ASSERT(rows > 0 && cols > 0, fn);
+  B2OF_ASSERT(p->quality_level > 0 && p->min_distance >= 0 && p->max_corners >= 0, fn);
+  B2OF_ASSERT(p->block_size >= 1, fn);
+  if (p->gradient_size != 3) return fail(B2OF_E_UNSUPPORTED, "gradientSize != 3 is not supported");
+  if (p->block_size > 31) return fail(B2OF_E_UNSUPPORTED, "blockSize > 31 is not supported");
+  return B2OF_OK;
+}
+
+struct GfLayout {
+  float* eig; unsigned long long* cand; int* next_in_cell; int* cell_head; unsigned int* max_key; int* cand_count;
+  int cand_cap; size_t cells; size_t bytes;
+};
+
+static void gf_layout(int rows, int cols, const b2of_gftt_params* p, int batch, void* base, size_t cap, GfLayout* L) {
+  Arena ar(base, cap);
+  size_t n = (size_t)rows * cols;
+  int cc = 1024;
+  while ((size_t)cc < n / 2 + 1) cc <<= 1;
+  L->cand_cap = cc;
+  int cell = p->min_distance >= 1 ? cv_round(p->min_distance) : 1;
+  if (cell < 1) cell = 1;
+  L->cells = (size_t)cdiv(cols, cell) * cdiv(rows, cell);
+  L->eig = ar.take<float>(n * batch);
+  L->cand = ar.take<unsigned long long>((size_t)cc * batch);
+  L->next_in_cell = ar.take<int>((size_t)cc * batch);
+  L->cell_head = ar.take<int>(p->min_distance >= 1 ? L->cells * batch : 1);
+  L->max_key = ar.take<unsigned int>(batch);
+  L->cand_count = ar.take<int>(batch);
+  L->bytes = align_up(ar.off, 256);
+}
+
+size_t gftt_workspace_bytes(int rows, int cols, const b2of_gftt_params* p, int batch) {
+  if (gftt_check(rows, cols, p)) return 0;
+  if (batch < 1) batch = 1;
+  GfLayout L;
+  gf_layout(rows, cols, p, batch, nullptr, 0, &L);
+  return L.bytes;
+}
+
+int gftt_dev(const uint8_t* img, const uint8_t* mask, size_t step, size_t frame_stride, int batch, int rows, int cols,
+             const b2of_gftt_params* p, float* corners, int cap, int* n_corners, void* ws, size_t ws_bytes,
+             cudaStream_t st) {
+  int rc = gftt_check(rows, cols, p);
+  if (rc) return rc;
+  const char* fn = "goodFeaturesToTrack";
+  B2OF_ASSERT(img != nullptr && n_corners != nullptr && step >= (size_t)cols, fn);
+  B2OF_ASSERT(cap >= 0 && (corners != nullptr || cap == 0), fn);
+  if (batch <= 0) return B2OF_OK;
+  GfLayout L;
+  gf_layout(rows, cols, p, batch, ws, ws_bytes, &L);
+  if (ws == nullptr || ws_bytes < L.bytes)
+    return fail(B2OF_E_NOMEM, "gftt workspace too small: %zu B given, %zu B needed", ws_bytes, L.bytes);
+  B2OF_CUDA(cudaMemsetAsync(L.max_key, 0, sizeof(unsigned int) * batch, st));
+  B2OF_CUDA(cudaMemsetAsync(L.cand_count, 0, sizeof(int) * batch, st));
+  const int bs = p->block_size;
+  const int E = GF_T + bs - 1;
+  size_t smem = (size_t)((3 * E * E + 1) & ~1) * sizeof(float) + (size_t)3 * E * GF_T * sizeof(double);
+  static std::atomic<size_t> max_set{0};
+  if (smem > 48 * 1024 && smem > max_set.load()) {
+    B2OF_CUDA(cudaFuncSetAttribute(gftt_mineig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    max_set.store(smem);
+  }
+  float scale = (float)(1.0 / ((double)(1 << (p->gradient_size - 1)) * bs * 255.0));
+  dim3 g1(cdiv(cols, GF_T), cdiv(rows, GF_T), batch);
+  gftt_mineig<<<g1, 256, smem, st>>>(img, mask, step, frame_stride, cols, rows, bs, scale, p->use_harris, (float)p->k,
+                                     L.eig, L.max_key);
+  B2OF_LAUNCH_CHECK();
+  dim3 g2(cdiv(cols, 32), cdiv(rows, 8), batch);
+  gftt_nms_compact<<<g2, 256, 0, st>>>(L.eig, mask, step, frame_stride, cols, rows, p->quality_level, L.max_key, L.cand,
+                                       L.cand_cap, L.cand_count);
+  B2OF_LAUNCH_CHECK();
+  gftt_select<<<batch, 1024, 0, st>>>(L.cand, L.cand_cap, L.cand_count, cols, rows, p->max_corners,
+                                      (float)p->min_distance, L.cell_head, L.next_in_cell, corners, cap, n_corners);
+  B2OF_LAUNCH_CHECK();
+  return B2OF_OK;
+}
+
+}  // namespace b2of

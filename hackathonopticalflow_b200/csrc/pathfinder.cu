@@ -1,0 +1,237 @@
+// K12: the reference's own downstream logic on the device, one CTA per frame.
+//   vector filter      pathfinder_viewer.py:159-178 (get_flow_lk after the LK call)
+//   danger intensity   pathfinder_viewer.py:210-217 (draw_sparse_lamps before drawing)
+// numpy semantics kept: float32 throughout, np.median (mean of the two middle values), np.percentile(.,99)
+// (linear interpolation), np.int32() truncation toward zero, float64 sqrt for the integer flow modulus.
+// Plus flow_stats: per-pair statistics of a dense flow field (what draw_flow / draw_hsv consume).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace b2of {
+
+constexpr int PF_THREADS = 1024;
+constexpr int PF_MAX_PTS = 32768;  // 128 KB of float keys in shared memory
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (int i = 0; i < PF_THREADS / 32; ++i) s += red[i];  // fixed order: deterministic
+  return s;
+}
+
+__global__ void __launch_bounds__(PF_THREADS) pathfinder_filter(const float* __restrict__ pts, size_t pts_bstride,
+                                                                 const float* __restrict__ next_pts, int n,
+                                                                 int width, int height, int32_t* __restrict__ kept_pts,
+                                                                 int32_t* __restrict__ kept_flow,
+                                                                 uint8_t* __restrict__ danger_v,
+                                                                 uint8_t* __restrict__ mask_out,
+                                                                 int32_t* __restrict__ n_kept,
+                                                                 float* __restrict__ stats, int np2) {
+  extern __shared__ float s_key[];  // np2 sorted moduli
+  __shared__ float red[PF_THREADS / 32];
+  __shared__ int warp_off[PF_THREADS / 32 + 1];
+  __shared__ int s_base;
+  const int b = blockIdx.x, t = threadIdx.x;
+  const float* P = pts + (size_t)b * pts_bstride * 2;
+  const float* Q = next_pts + (size_t)b * n * 2;
+  const float hw = (float)(width / 2), hh = (float)(height / 2);
+  float sum_mag = 0.f, max_mag = 0.f, sum_dx = 0.f, sum_dy = 0.f;
+  for (int i = t; i < np2; i += PF_THREADS) {
+    float key = INFINITY;
+    if (i < n) {
+      float x = P[2 * i], y = P[2 * i + 1];
+      float fx = Q[2 * i] - x, fy = Q[2 * i + 1] - y;
+      float mod = sqrtf(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)));
+      float ddx = hw - x, ddy = hh - y;
+      float mm = sqrtf(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)));
+      key = __fmul_rn(__fdiv_rn(mod, 5.f + sqrtf(mm)), 30.f);
+      sum_mag += mod; max_mag = fmaxf(max_mag, mod); sum_dx += fx; sum_dy += fy;
+    }
+    s_key[i] = key;
+  }
+  __syncthreads();
+  // bitonic sort ascending (NaN-free input assumed; +inf padding sorts last)
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = t; i < np2; i += PF_THREADS) {
+        int l = i ^ j;
+        if (l > i) {
+          float a = s_key[i], c = s_key[l];
+          bool asc = (i & k) == 0;
+          if (asc ? a > c : a < c) { s_key[i] = c; s_key[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // np.median / np.percentile(., 99) in float32
+  float med, p99;
+  {
+    if (n & 1) med = s_key[n / 2];
+    else med = __fdiv_rn(__fadd_rn(s_key[n / 2 - 1], s_key[n / 2]), 2.f);
+    double vi = 0.99 * (double)(n - 1);
+    int lo = (int)floor(vi);
+    int hi = lo + 1 < n ? lo + 1 : n - 1;
+    float tt = (float)(vi - (double)lo);
+    float a = s_key[lo], c = s_key[hi];
+    float diff = c - a;
+    p99 = tt >= 0.5f ? c - diff * (1.f - tt) : a + diff * tt;
+  }
+  // second pass: mask + ordered compaction
+  int kept_total = 0;
+  float sum_v = 0.f;
+  if (t == 0) s_base = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += PF_THREADS) {
+    int i = i0 + t;
+    bool keep = false;
+    int px = 0, py = 0, qx = 0, qy = 0;
+    if (i < n) {
+      float x = P[2 * i], y = P[2 * i + 1];
+      float fx = Q[2 * i] - x, fy = Q[2 * i + 1] - y;
+      float ang = atan2f(fy, fx);
+      float mod = sqrtf(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)));
+      float ddx = hw - x, ddy = hh - y;
+      float mm = sqrtf(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)));
+      float m2 = __fmul_rn(__fdiv_rn(mod, 5.f + sqrtf(mm)), 30.f);
+      float gx = __fmul_rn(m2, cosf(ang)), gy = __fmul_rn(m2, sinf(ang));
+      qx = (int)(__fadd_rn(__fadd_rn(x, gx), 0.5f));
+      qy = (int)(__fadd_rn(__fadd_rn(y, gy), 0.5f));
+      px = (int)(x + 0.5f);
+      py = (int)(y + 0.5f);
+      keep = (med < m2) && (m2 < p99);
+      mask_out[(size_t)b * n + i] = keep ? 1 : 0;
+    }
+    unsigned int ballot = __ballot_sync(0xffffffffu, keep);
+    int lane = t & 31, wid = t >> 5;
+    if (lane == 0) warp_off[wid] = __popc(ballot);
+    __syncthreads();
+    if (t == 0) {
+      int acc = s_base;
+      for (int wi = 0; wi < PF_THREADS / 32; ++wi) { int c = warp_off[wi]; warp_off[wi] = acc; acc += c; }
+      warp_off[PF_THREADS / 32] = acc;
+    }
+    __syncthreads();
+    if (keep) {
+      int slot = warp_off[wid] + __popc(ballot & ((1u << lane) - 1));
+      size_t o = ((size_t)b * n + slot) * 2;
+      int fxi = qx - px, fyi = qy - py;
+      kept_pts[o] = px; kept_pts[o + 1] = py;
+      kept_flow[o] = fxi; kept_flow[o + 1] = fyi;
+      double m = sqrt((double)(fxi * fxi + fyi * fyi));
+      double v = fmin(50.0 + m * 2.0, 255.0);
+      uint8_t vb = (uint8_t)v;
+      danger_v[(size_t)b * n + slot] = vb;
+      sum_v += (float)vb;
+    }
+    __syncthreads();
+    if (t == 0) s_base = warp_off[PF_THREADS / 32];
+    __syncthreads();
+  }
+  kept_total = s_base;
+  float tot_mag = block_sum(sum_mag, red);
+  float tot_dx = block_sum(sum_dx, red);
+  float tot_dy = block_sum(sum_dy, red);
+  float tot_v = block_sum(sum_v, red);
+  // block max
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) max_mag = fmaxf(max_mag, __shfl_xor_sync(0xffffffffu, max_mag, o));
+  __syncthreads();
+  if ((t & 31) == 0) red[t >> 5] = max_mag;
+  __syncthreads();
+  if (t == 0) {
+    float mx = 0.f;
+    for (int i = 0; i < PF_THREADS / 32; ++i) mx = fmaxf(mx, red[i]);
+    n_kept[b] = kept_total;
+    float* s = stats + (size_t)b * B2OF_STATS_WIDTH;
+    s[0] = tot_mag / (float)n; s[1] = mx; s[2] = tot_dx / (float)n; s[3] = tot_dy / (float)n;
+    s[4] = med; s[5] = p99; s[6] = (float)kept_total; s[7] = tot_v;
+  }
+}
+
+int pathfinder_filter_dev(const float* pts, size_t pts_bstride, const float* next_pts, int n_pts, int batch, int width,
+                          int height, int32_t* kept_pts, int32_t* kept_flow, uint8_t* danger_v, uint8_t* mask,
+                          int32_t* n_kept, float* stats, cudaStream_t st) {
+  const char* fn = "pathfinder_filter";
+  B2OF_ASSERT(n_pts >= 1 && batch >= 0 && width > 0 && height > 0, fn);
+  B2OF_ASSERT(pts && next_pts && kept_pts && kept_flow && danger_v && mask && n_kept && stats, fn);
+  if (n_pts > PF_MAX_PTS) return fail(B2OF_E_UNSUPPORTED, "more than %d points per frame", PF_MAX_PTS);
+  if (batch == 0) return B2OF_OK;
+  int np2 = 1;
+  while (np2 < n_pts) np2 <<= 1;
+  size_t smem = (size_t)np2 * sizeof(float);
+  static std::atomic<size_t> max_set{0};
+  if (smem > 48 * 1024 && smem > max_set.load()) {
+    B2OF_CUDA(cudaFuncSetAttribute(pathfinder_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    max_set.store(smem);
+  }
+  pathfinder_filter<<<batch, PF_THREADS, smem, st>>>(pts, pts_bstride, next_pts, n_pts, width, height, kept_pts,
+                                                     kept_flow, danger_v, mask, n_kept, stats, np2);
+  B2OF_LAUNCH_CHECK();
+  return B2OF_OK;
+}
+
+// ---- dense flow statistics: deterministic fixed-point accumulation, then finalize in place ----
+// scratch layout inside the 8-float stats row: [0:2) u64 sum|f| (Q20), [2:4) i64 sum dx, [4:6) i64 sum dy, [6] max bits
+__global__ void __launch_bounds__(256) flow_stats_accum(const float2* __restrict__ flow, size_t n_px,
+                                                         float* __restrict__ stats) {
+  const int b = blockIdx.y;
+  const float2* f = flow + (size_t)b * n_px;
+  float sm = 0.f, sx = 0.f, sy = 0.f, mx = 0.f;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n_px; i += (size_t)gridDim.x * 256) {
+    float2 v = f[i];
+    float m = sqrtf(v.x * v.x + v.y * v.y);
+    sm += m; sx += v.x; sy += v.y; mx = fmaxf(mx, m);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sm += __shfl_xor_sync(0xffffffffu, sm, o);
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);
+    sy += __shfl_xor_sync(0xffffffffu, sy, o);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    unsigned long long* acc = (unsigned long long*)(stats + (size_t)b * B2OF_STATS_WIDTH);
+    const double Q = 1048576.0;
+    atomicAdd(acc + 0, (unsigned long long)llrint((double)sm * Q));
+    atomicAdd(acc + 1, (unsigned long long)llrint((double)sx * Q));  // two's complement wrap = signed add
+    atomicAdd(acc + 2, (unsigned long long)llrint((double)sy * Q));
+    atomicMax((unsigned int*)(acc + 3), __float_as_uint(mx));        // mx >= 0: bit order == value order
+  }
+}
+
+__global__ void flow_stats_final(float* __restrict__ stats, size_t n_px, int n_pairs) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_pairs) return;
+  float* s = stats + (size_t)b * B2OF_STATS_WIDTH;
+  unsigned long long* acc = (unsigned long long*)s;
+  const double Q = 1048576.0;
+  double sm = (double)acc[0] / Q, sx = (double)(long long)acc[1] / Q, sy = (double)(long long)acc[2] / Q;
+  float mx = __uint_as_float(*(unsigned int*)(acc + 3));
+  s[0] = (float)(sm / (double)n_px); s[1] = mx; s[2] = (float)(sx / (double)n_px); s[3] = (float)(sy / (double)n_px);
+  s[4] = s[5] = s[6] = s[7] = 0.f;
+}
+
+int flow_stats_dev(const float* flow, int n_pairs, int rows, int cols, float* stats, cudaStream_t st) {
+  const char* fn = "flow_stats";
+  B2OF_ASSERT(n_pairs >= 0 && rows > 0 && cols > 0, fn);
+  if (n_pairs == 0) return B2OF_OK;
+  B2OF_ASSERT(flow != nullptr && stats != nullptr, fn);
+  B2OF_ASSERT(((uintptr_t)stats & 7) == 0, fn);
+  size_t n_px = (size_t)rows * cols;
+  B2OF_CUDA(cudaMemsetAsync(stats, 0, (size_t)n_pairs * B2OF_STATS_WIDTH * sizeof(float), st));
+  int bx = (int)((n_px + 256 * 8 - 1) / (256 * 8));
+  if (bx > 296) bx = 296;
+  flow_stats_accum<<<dim3(bx, n_pairs), 256, 0, st>>>((const float2*)flow, n_px, stats);
+  B2OF_LAUNCH_CHECK();
+  flow_stats_final<<<cdiv(n_pairs, 128), 128, 0, st>>>(stats, n_px, n_pairs);
+  B2OF_LAUNCH_CHECK();
+  return B2OF_OK;
+}
+
+}  // namespace b2of

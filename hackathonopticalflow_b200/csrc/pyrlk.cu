@@ -7,6 +7,7 @@
 // One warp per feature, all pyramid levels inside one launch; the template patch (Iw, Ixw, Iyw as int16)
 // lives in shared memory, window sums are exact integers reduced with warp shuffles.
 #include <math.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_track(LkArgs a) {
   const int b = blockIdx.y;
   if (pt >= a.n_pts) return;
   const int ww = a.ww, wh = a.wh, n = ww * wh;
-  const size_t per_warp = align_up16((size_t)n * 6);
+  const size_t per_warp = (((size_t)n * 6) + 15) & ~(size_t)15;
   short* sI = (short*)(lk_smem + warp * per_warp);
   short2* sD = (short2*)(sI + ((n + 1) & ~1));
   const uint8_t* PI = a.pyr_i + (size_t)b * a.L.pyr_bytes;

@@ -1,0 +1,71 @@
+"""Host-side mirror of the reference's downstream interface, running on the device.
+
+Same names and argument meaning as the reference's functions, minus the drawing (out of scope):
+
+* ``grid_points``      -- the measurement grid, pathfinder_viewer.py:255-267 (DenseOF.py:166-180)
+* ``get_flow_lk``      -- pathfinder_viewer.py:144-193: LK from the current frame back to the previous one
+                          (note the argument order at :156), modulus normalisation, median/p99 filter, int rounding
+* ``draw_sparse_lamps``-- pathfinder_viewer.py:196-223: returns the danger intensity V per kept point
+                          (what :210-217 writes) instead of a drawn image
+"""
+import numpy as np
+import torch
+
+from . import batch
+
+
+def grid_points(width, height, step=30):
+    """float32 (N,2), x-major: all y for the first x, then the next x (pathfinder_viewer.py:255-267)."""
+    def axis(dim):
+        indent = dim % step / 2 if dim // step % 2 == 1 else (dim % step + step) / 2
+        return np.arange(indent, dim, step).astype(int)
+    xs, ys = axis(width), axis(height)
+    pts = np.empty((len(xs), len(ys), 2), np.float32)
+    pts[..., 0] = xs[:, None]
+    pts[..., 1] = ys[None, :]
+    return pts.reshape(-1, 2)
+
+
+def get_flow_lk(img1, img2, points_, device="cuda"):
+    """img1: previous gray, img2: current gray, points_: float32 (N,2) (all numpy, as the reference passes them).
+
+    Returns (flow int32 (M,2), points int32 (M,2)) -- the reference's second and third return values.
+    """
+    height, width = img1.shape
+    prev = torch.from_numpy(np.ascontiguousarray(img1)).to(device)[None]
+    cur = torch.from_numpy(np.ascontiguousarray(img2)).to(device)[None]
+    pts = torch.from_numpy(np.ascontiguousarray(points_, dtype=np.float32)).to(device)
+    nxt, _status, _err = batch.pyrlk(cur, prev, pts, **batch.LK_GRID_DEFAULTS)
+    out = batch.pathfinder_filter(pts, nxt, width, height)
+    m = int(out["n_kept"][0])
+    return out["kept_flow"][0, :m].cpu().numpy(), out["kept_pts"][0, :m].cpu().numpy()
+
+
+def draw_sparse_lamps(flow_, points_):
+    """Danger intensity per kept point: uint8 V = min(50 + 2*|flow|, 255) (pathfinder_viewer.py:210-217)."""
+    f = torch.from_numpy(np.ascontiguousarray(flow_)).to(torch.float64)
+    m = torch.sqrt(f[:, 0] * f[:, 0] + f[:, 1] * f[:, 1])
+    return torch.clamp(50 + m * 2, max=255).to(torch.uint8).numpy()
+
+
+class PathfinderPipeline:
+    """Full per-frame pipeline on device-resident BGR frames (config 5): gray -> grid LK (current -> previous)
+    -> vector filter + danger points [+ dense Farneback flow and its statistics]."""
+
+    def __init__(self, height, width, step=30, dense=False, chunk_pairs=4, device=None):
+        self.h, self.w = int(height), int(width)
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.points = torch.from_numpy(grid_points(self.w, self.h, step)).to(self.device)
+        self.dense = batch.FarnebackEngine(self.h, self.w, chunk_pairs=chunk_pairs, device=self.device) if dense else None
+
+    def run(self, bgr_frames):
+        """uint8 (F,H,W,3) -> dict with per-pair outputs for the F-1 consecutive pairs."""
+        gray = batch.bgr2gray(bgr_frames)
+        prev, cur = gray[:-1], gray[1:]
+        nxt, status, err = batch.pyrlk(cur, prev, self.points, **batch.LK_GRID_DEFAULTS)
+        out = batch.pathfinder_filter(self.points, nxt, self.w, self.h)
+        out.update(gray=gray, next_pts=nxt, status=status, err=err)
+        if self.dense is not None:
+            out["flow"] = self.dense.flow_sequence(gray)
+            out["flow_stats"] = batch.flow_stats(out["flow"])
+        return out
