@@ -49,6 +49,11 @@ SIGNATURES = {
     "b2of_version": (_i, []),
     "b2of_last_error": (C.c_char_p, []),
     "b2of_launch_count": (C.c_ulonglong, []),
+    "b2of_profile_enable": (None, [_i]),
+    "b2of_profile_reset": (None, []),
+    "b2of_profile_tag_count": (_i, []),
+    "b2of_profile_tag_name": (C.c_char_p, [_i]),
+    "b2of_profile_read": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong), C.POINTER(C.c_double)]),
     "b2of_bgr2gray_u8_dev": (_i, [_vp, _i, _i, _sz, _sz, _vp, _sz, _sz, _i, _vp]),
     "b2of_bgr2gray_u8_host": (_i, [_vp, _i, _i, _sz, _vp, _sz]),
     "b2of_pyrdown_u8_dev": (_i, [_vp, _i, _i, _sz, _sz, _vp, _sz, _sz, _i, _vp]),
@@ -113,3 +118,21 @@ def check(rc):
     if rc != 0:
         msg = lib().b2of_last_error().decode("utf-8", "replace")
         raise error(rc, msg)
+
+
+def profile(enable=None, reset=False):
+    """Per-kernel device timing.  ``profile(True)`` / ``profile(False)`` switch it; ``profile()`` returns
+    {kernel family: {"ms": total device ms, "launches": n, "bytes": algorithmic bytes}} since the last reset."""
+    l = lib()
+    if enable is not None:
+        l.b2of_profile_enable(1 if enable else 0)
+    out = {}
+    if enable is None:
+        for tag in range(l.b2of_profile_tag_count()):
+            ms, n, by = C.c_double(0), C.c_ulonglong(0), C.c_double(0)
+            check(l.b2of_profile_read(tag, C.byref(ms), C.byref(n), C.byref(by)))
+            if n.value:
+                out[l.b2of_profile_tag_name(tag).decode()] = {"ms": ms.value, "launches": n.value, "bytes": by.value}
+    if reset:
+        l.b2of_profile_reset()
+    return out

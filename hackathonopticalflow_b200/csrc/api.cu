@@ -2,6 +2,7 @@
 // cv2-call contract (host arrays in, host arrays out).
 #include <mutex>
 #include <string.h>
+#include <vector>
 
 #include "common.cuh"
 
@@ -15,6 +16,35 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(t_err, sizeof t_err, fmt, ap);
   va_end(ap);
+}
+
+// ---- per-kernel timing ----
+std::atomic<int> g_prof_on{0};
+namespace {
+struct ProfRec { int tag; cudaEvent_t e0, e1; double bytes; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+const char* const kProfNames[PT_COUNT] = {"bgr2gray", "pyrdown", "fb_level_hpass", "fb_level_vpass", "fb_polyexp",
+                                          "fb_iter_finest", "fb_iter_coarse", "lk_scharr", "lk_track", "gftt_mineig",
+                                          "gftt_nms_compact", "gftt_select", "pathfinder_filter", "flow_stats"};
+cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+void prof_mark(int tag, cudaStream_t st, bool end, double bytes) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  if (!end) {
+    ProfRec r{tag, prof_event(), prof_event(), bytes};
+    cudaEventRecord(r.e0, st);
+    g_prof_recs.push_back(r);
+  } else {
+    for (size_t i = g_prof_recs.size(); i-- > 0;)
+      if (g_prof_recs[i].tag == tag) { cudaEventRecord(g_prof_recs[i].e1, st); break; }
+  }
 }
 
 // implemented in the per-subsystem translation units
@@ -101,6 +131,32 @@ extern "C" {
 int b2of_version(void) { return B2OF_VERSION; }
 const char* b2of_last_error(void) { return t_err; }
 unsigned long long b2of_launch_count(void) { return g_launches.load(); }
+
+// ---- per-kernel timing (CUDA events on the launching stream) ----
+void b2of_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
+int b2of_profile_tag_count(void) { return PT_COUNT; }
+const char* b2of_profile_tag_name(int tag) { return tag >= 0 && tag < PT_COUNT ? kProfNames[tag] : ""; }
+void b2of_profile_reset(void) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  for (auto& r : g_prof_recs) { g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1); }
+  g_prof_recs.clear();
+}
+int b2of_profile_read(int tag, double* ms_total, unsigned long long* launches, double* bytes_total) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  double ms = 0, bytes = 0;
+  unsigned long long n = 0;
+  for (auto& r : g_prof_recs) {
+    if (r.tag != tag) continue;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) return fail(B2OF_E_CUDA, "profile event sync failed");
+    float t = 0;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) return fail(B2OF_E_CUDA, "profile elapsed failed");
+    ms += t; bytes += r.bytes; ++n;
+  }
+  if (ms_total) *ms_total = ms;
+  if (launches) *launches = n;
+  if (bytes_total) *bytes_total = bytes;
+  return B2OF_OK;
+}
 
 // ---- K1 ----
 int b2of_bgr2gray_u8_dev(const uint8_t* bgr, int rows, int cols, size_t src_step, size_t src_bstride, uint8_t* gray,

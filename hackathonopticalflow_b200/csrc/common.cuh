@@ -62,6 +62,21 @@ __host__ __device__ inline int clampi(int v, int lo, int hi) { return v < lo ? l
 // round-half-to-even, cv::cvRound for doubles
 inline int cv_round(double v) { return (int)nearbyint(v); }
 
+// ---- optional per-kernel timing (CUDA events on the launching stream); off by default ----
+enum ProfTag {
+  PT_GRAY = 0, PT_PYRDOWN, PT_FB_LEVEL_H, PT_FB_LEVEL_V, PT_FB_POLYEXP, PT_FB_ITER_FINEST, PT_FB_ITER_COARSE,
+  PT_LK_SCHARR, PT_LK_TRACK, PT_GFTT_MINEIG, PT_GFTT_NMS, PT_GFTT_SELECT, PT_FILTER, PT_STATS, PT_COUNT
+};
+extern std::atomic<int> g_prof_on;
+void prof_mark(int tag, cudaStream_t st, bool end, double bytes);
+struct ProfScope {
+  int tag; cudaStream_t st; bool on;
+  ProfScope(int t, cudaStream_t s, double bytes = 0) : tag(t), st(s), on(g_prof_on.load(std::memory_order_relaxed) != 0) {
+    if (on) prof_mark(tag, st, false, bytes);
+  }
+  ~ProfScope() { if (on) prof_mark(tag, st, true, 0); }
+};
+
 // linear bump allocator over a caller-provided workspace
 struct Arena {
   char* base;

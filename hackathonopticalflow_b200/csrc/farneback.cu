@@ -639,17 +639,26 @@ static int fb_frames(const FbPlan* pl, const FbWorkspace& ws, const uint8_t* fra
     float* Rb = ws.R + (size_t)total_slots * 5 * lvl_off + (size_t)slot0 * 5 * plane;
     size_t t_stride = (size_t)H * pitch0 * slot_step, i_stride = plane * slot_step, r_stride = 5 * plane * slot_step;
     dim3 g1(cdiv(L.w, 128), H, frames);
+    {
+      ProfScope ps(PT_FB_LEVEL_H, st, (double)frames * ((double)W * H + 4.0 * H * L.w));
     fb_level_hpass<<<g1, 128, 0, st>>>(frames_dev, step, frame_stride, W, H, Tb, L.w, L.pitch, t_stride, L.taps, L.ksz,
                                        L.sx0, L.sx1, L.fx);
+    }
     B2OF_LAUNCH_CHECK();
     dim3 g2(cdiv(L.w, 128), L.h, frames);
-    fb_level_vpass<<<g2, 128, 0, st>>>(Tb, H, L.pitch, t_stride, Ib, L.w, L.h, i_stride, L.taps, L.ksz, L.sy0, L.sy1,
-                                       L.fy);
+    {
+      ProfScope ps(PT_FB_LEVEL_V, st, (double)frames * (4.0 * H * L.w + 4.0 * L.h * L.w));
+      fb_level_vpass<<<g2, 128, 0, st>>>(Tb, H, L.pitch, t_stride, Ib, L.w, L.h, i_stride, L.taps, L.ksz, L.sy0,
+                                         L.sy1, L.fy);
+    }
     B2OF_LAUNCH_CHECK();
     int n = pl->p.poly_n;
     size_t smem = ((size_t)(PE_TH + 2 * n) * (PE_TW + 2 * n) + 3 * (size_t)PE_TH * (PE_TW + 2 * n)) * sizeof(float);
     dim3 g3(cdiv(L.w, PE_TW), cdiv(L.h, PE_TH), frames);
-    fb_polyexp<<<g3, 256, smem, st>>>(Ib, L.w, L.h, L.pitch, i_stride, Rb, plane, r_stride, pl->pc, n);
+    {
+      ProfScope ps(PT_FB_POLYEXP, st, (double)frames * 24.0 * L.w * L.h);
+      fb_polyexp<<<g3, 256, smem, st>>>(Ib, L.w, L.h, L.pitch, i_stride, Rb, plane, r_stride, pl->pc, n);
+    }
     B2OF_LAUNCH_CHECK();
     lvl_off += plane;
   }
@@ -723,8 +732,15 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
         dst = (it & 1) ? B : A; dpitch = L.pitch; dstride = plane;
       }
       a.flow_out = dst; a.out_pitch = dpitch; a.flow_out_pair_stride = dstride;
-      if (gauss) fb_iter<true><<<grid, IT_THREADS, smem, st>>>(a);
-      else fb_iter<false><<<grid, IT_THREADS, smem, st>>>(a);
+      {
+        // algorithmic bytes of this launch: R0 + R1 (20 B/px each), flow in (8 B/px, or 8 B per coarse px, or none),
+        // flow out (8 B/px)
+        double px = (double)L.w * L.h;
+        double bytes = pairs * (48.0 * px + (a.mode == 1 ? 8.0 * px : a.mode == 2 ? 8.0 * cw * ch : 0.0));
+        ProfScope ps(last_level ? PT_FB_ITER_FINEST : PT_FB_ITER_COARSE, st, bytes);
+        if (gauss) fb_iter<true><<<grid, IT_THREADS, smem, st>>>(a);
+        else fb_iter<false><<<grid, IT_THREADS, smem, st>>>(a);
+      }
       B2OF_LAUNCH_CHECK();
       cur = dst; cur_pitch = dpitch; cur_stride = dstride;
     }

@@ -367,7 +367,13 @@ int pyrlk_dev(const uint8_t* prev, const uint8_t* next, size_t step, size_t fram
     max_set.store(smem);
   }
   dim3 grid(cdiv(n_pts, LK_WARPS), batch);
-  lk_track<<<grid, LK_WARPS * 32, smem, st>>>(a);
+  {
+    // algorithmic bytes: both pyramids once (u8) + derivatives of the first (4 B/px) + 21 B per point
+    double px = 0;
+    for (int l = 0; l < a.L.n; ++l) px += (double)a.L.w[l] * a.L.h[l];
+    ProfScope ps(PT_LK_TRACK, st, batch * (6.0 * px + 21.0 * n_pts));
+    lk_track<<<grid, LK_WARPS * 32, smem, st>>>(a);
+  }
   B2OF_LAUNCH_CHECK();
   return B2OF_OK;
 }

@@ -53,6 +53,15 @@ const char* b2of_last_error(void);
 /* number of kernel launches issued by this library in this process (all threads) */
 unsigned long long b2of_launch_count(void);
 
+/* Optional per-kernel timing: when enabled, every kernel launch of the tagged families is bracketed by CUDA events
+ * on the stream it is launched on.  b2of_profile_read synchronises those events and returns the summed device
+ * time, launch count and algorithmic bytes (DESIGN.md per-kernel figures) recorded for one tag since the last reset. */
+void b2of_profile_enable(int on);
+void b2of_profile_reset(void);
+int b2of_profile_tag_count(void);
+const char* b2of_profile_tag_name(int tag);
+int b2of_profile_read(int tag, double* ms_total, unsigned long long* launches, double* bytes_total);
+
 /* ---- K1: cv2.cvtColor(img, cv2.COLOR_BGR2GRAY) --------------------------------
  * replaces viewer.py:244, :280; DenseOF.py:481, :510; SparseOF.py:28.
  * `batch` images, `src_batch_stride`/`dst_batch_stride` bytes apart. Bit-exact. */

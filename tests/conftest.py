@@ -1,0 +1,42 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def crops():
+    return np.load(os.path.join(GOLDEN, "real_crops.npz"))
+
+
+@pytest.fixture(scope="session")
+def full1080():
+    return np.load(os.path.join(GOLDEN, "real_1080p.npz"))
+
+
+@pytest.fixture(scope="session")
+def synth_small():
+    return np.load(os.path.join(GOLDEN, "synth_small.npz"))
+
+
+def epe(a, b):
+    d = np.sqrt(((a.astype(np.float64) - b.astype(np.float64)) ** 2).sum(-1))
+    return float(d.mean()), float(d.max())
+
+
+def have_cv2():
+    try:
+        import cv2  # noqa: F401
+        return True
+    except Exception:
+        return False

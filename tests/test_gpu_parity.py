@@ -1,0 +1,387 @@
+"""GPU parity tests: every call goes through the C-ABI of libb2of.so (cv2compat -> *_host entry points, batch ->
+*_dev entry points) and is checked against (1) the committed cv2 golden vectors, (2) the numpy oracle on seeded
+inputs, (3) live cv2 when the wheel is importable on the box, and (4) size-independent properties at the
+BASELINE full size (1920x1080).
+
+Tolerances (BASELINE.json north_star): gray / pyrDown bit-exact; dense flow mean EPE <= 0.02 px and max <= 0.5 px;
+LK status match >= 99.5 % and positions within 0.05 px; downstream masks agree on >= 99.5 % of points.
+"""
+import numpy as np
+import pytest
+
+from conftest import epe, have_cv2
+
+pytestmark = pytest.mark.gpu
+
+FB_MEAN_TOL, FB_MAX_TOL = 0.02, 0.5     # north_star tolerance
+LK_STATUS_TOL, LK_POS_TOL = 0.995, 0.05
+MASK_TOL = 0.995
+REF_FB = (0.5, 3, 15, 3, 5, 1.2, 0)      # DenseOF.py:127-128
+LK_GRID = dict(winSize=(45, 45), maxLevel=2, criteria=(3, 10, 0.03))    # pathfinder_viewer.py:154-158
+LK_TRACK = dict(winSize=(15, 15), maxLevel=2, criteria=(3, 10, 0.03))   # SparseOF.py:6-8
+GFTT = dict(maxCorners=20, qualityLevel=0.3, minDistance=10, blockSize=7)  # SparseOF.py:10-13
+
+
+@pytest.fixture(scope="module")
+def b2():
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    from hackathonopticalflow_b200 import cv2compat
+    return cv2compat
+
+
+@pytest.fixture(scope="module")
+def batch():
+    from hackathonopticalflow_b200 import batch as m
+    return m
+
+
+def _decode_png(buf):
+    if have_cv2():
+        import cv2
+        return cv2.imdecode(buf, cv2.IMREAD_GRAYSCALE)
+    from io import BytesIO
+    from PIL import Image
+    return np.array(Image.open(BytesIO(buf.tobytes())))
+
+
+def test_native_library_is_the_one_in_tree(b2):
+    import os
+    from hackathonopticalflow_b200 import _lib
+    assert os.path.samefile(_lib.LIB_PATH, os.path.join(os.path.dirname(_lib.__file__), "csrc", "libb2of.so"))
+    before = _lib.lib().b2of_launch_count()
+    b2.cvtColor(np.zeros((8, 8, 3), np.uint8), b2.COLOR_BGR2GRAY)
+    assert _lib.lib().b2of_launch_count() > before
+
+
+# ------------------------------------------------------------------ K1 / K2 (bit-exact)
+@pytest.mark.parametrize("i", range(4))
+def test_gray_pyrdown_golden(b2, crops, i):
+    g0 = b2.cvtColor(crops[f"bgr0_{i}"], b2.COLOR_BGR2GRAY)
+    assert g0.dtype == np.uint8 and np.array_equal(g0, crops[f"gray0_{i}"])
+    p1 = b2.pyrDown(g0)
+    assert np.array_equal(p1, crops[f"pyr1_{i}"])
+    assert np.array_equal(b2.pyrDown(p1), crops[f"pyr2_{i}"])
+
+
+@pytest.mark.parametrize("h,w", [(1, 1), (1, 17), (3, 5), (33, 1919), (101, 77), (1080, 1920), (2160, 3840)])
+def test_gray_pyrdown_vs_oracle_ragged_sizes(b2, h, w):
+    from oracle import gray_pyr as ogp
+    rng = np.random.default_rng(h * 10007 + w)
+    bgr = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    g = b2.cvtColor(bgr, b2.COLOR_BGR2GRAY)
+    assert np.array_equal(g, ogp.bgr2gray(bgr))
+    assert np.array_equal(b2.pyrDown(g), ogp.pyrdown_u8(g))
+
+
+def test_gray_all_colours_exhaustive(b2, batch):
+    """All 2^24 BGR triples through the device entry point against the integer formula."""
+    import torch
+    v = torch.arange(1 << 24, dtype=torch.int64, device="cuda")
+    bgr = torch.stack([v & 255, (v >> 8) & 255, v >> 16], -1).to(torch.uint8).reshape(1, 4096, 4096, 3).contiguous()
+    got = batch.bgr2gray(bgr).reshape(-1).to(torch.int64)
+    want = (3735 * (v & 255) + 19235 * ((v >> 8) & 255) + 9798 * (v >> 16) + 16384) >> 15
+    assert torch.equal(got, want)
+
+
+def test_gray_noncontiguous_and_dst_buffer(b2):
+    rng = np.random.default_rng(5)
+    big = rng.integers(0, 256, (40, 64, 3), dtype=np.uint8)
+    view = big[3:35, 5:50]                       # strided rows
+    from oracle import gray_pyr as ogp
+    dst = np.empty(view.shape[:2], np.uint8)
+    out = b2.cvtColor(view, b2.COLOR_BGR2GRAY, dst)
+    assert out is dst and np.array_equal(out, ogp.bgr2gray(view))
+
+
+def test_pyrdown_batched_device_chain(batch):
+    import torch
+    from oracle import gray_pyr as ogp
+    rng = np.random.default_rng(9)
+    imgs = rng.integers(0, 256, (3, 135, 241), dtype=np.uint8)
+    d1 = batch.pyrdown(torch.from_numpy(imgs).cuda())
+    d2 = batch.pyrdown(d1)
+    for k in range(3):
+        w1 = ogp.pyrdown_u8(imgs[k])
+        assert np.array_equal(d1[k].cpu().numpy(), w1)
+        assert np.array_equal(d2[k].cpu().numpy(), ogp.pyrdown_u8(w1))
+
+
+# ------------------------------------------------------------------ K3-K6 Farneback
+@pytest.mark.parametrize("i", range(4))
+def test_farneback_golden_real_crops(b2, crops, i):
+    flow = b2.calcOpticalFlowFarneback(crops[f"gray0_{i}"], crops[f"gray1_{i}"], None, *REF_FB)
+    assert flow.shape == (360, 640, 2) and flow.dtype == np.float32
+    mean, mx = epe(flow[::4, ::4], crops[f"flow_s4_{i}"])
+    assert mean <= FB_MEAN_TOL and mx <= FB_MAX_TOL, (mean, mx)
+    assert mean <= 1e-3 and mx <= 0.1, ("regression guard", mean, mx)
+
+
+def test_farneback_golden_full_1080p(b2, full1080):
+    g0, g1 = _decode_png(full1080["png0"]), _decode_png(full1080["png1"])
+    flow = b2.calcOpticalFlowFarneback(g0, g1, None, *REF_FB)
+    mean, mx = epe(flow[::8, ::8], full1080["flow_s8"])
+    assert mean <= FB_MEAN_TOL and mx <= FB_MAX_TOL, (mean, mx)
+    assert mean <= 1e-3 and mx <= 0.1, ("regression guard", mean, mx)
+
+
+@pytest.mark.parametrize("name", ["ref", "gauss", "p08", "even", "sig0"])
+def test_farneback_parameter_sets_golden_and_oracle(b2, synth_small, name):
+    from oracle import farneback as ofb
+    a = synth_small[f"args_{name}"]
+    args = (float(a[0]), int(a[1]), int(a[2]), int(a[3]), int(a[4]), float(a[5]), int(a[6]))
+    flow = b2.calcOpticalFlowFarneback(synth_small["f0"], synth_small["f1"], None, *args)
+    mean, mx = epe(flow, synth_small[f"flow_{name}"])
+    assert mean <= 1e-4 and mx <= 1e-2, (name, mean, mx)
+    mean, mx = epe(flow, ofb.farneback(synth_small["f0"], synth_small["f1"], None, *args))
+    assert mean <= 1e-4 and mx <= 1e-2, (name, "oracle", mean, mx)
+
+
+def test_farneback_returns_passed_buffer(b2, synth_small):
+    buf = np.zeros((135, 241, 2), np.float32)
+    out = b2.calcOpticalFlowFarneback(synth_small["f0"], synth_small["f1"], buf, *REF_FB)
+    assert out is buf and np.abs(buf).max() > 0
+
+
+def test_farneback_loud_on_unsupported(b2, synth_small):
+    from hackathonopticalflow_b200 import error
+    with pytest.raises(error):
+        b2.calcOpticalFlowFarneback(synth_small["f0"], synth_small["f1"],
+                                    np.zeros((135, 241, 2), np.float32), 0.5, 3, 15, 3, 5, 1.2, 4)
+
+
+@pytest.fixture(scope="module")
+def seq1080():
+    from hackathonopticalflow_b200 import synth
+    return synth.sequence(1080, 1920, 5, seed=1000)
+
+
+def test_farneback_full_size_properties(batch, seq1080):
+    """BASELINE size: sequence == independent pairs == one-pair-at-a-time, bit for bit, and run-to-run."""
+    import torch
+    frames = torch.from_numpy(seq1080).cuda()
+    eng = batch.FarnebackEngine(1080, 1920, chunk_pairs=4)
+    seq = eng.flow_sequence(frames)
+    pairs = eng.flow_pairs(frames[:-1].contiguous(), frames[1:].contiguous())
+    assert torch.equal(seq, pairs)
+    assert torch.equal(seq, eng.flow_sequence(frames))
+    single = batch.FarnebackEngine(1080, 1920, chunk_pairs=1)
+    one = single.flow_pairs(frames[2:3].contiguous(), frames[3:4].contiguous())
+    assert torch.equal(one[0], seq[2])
+    assert torch.isfinite(seq).all()
+    # the synthetic flight has a known flow field: zoom 1.5 %/frame about the centre plus drift (synth.py)
+    t = 2
+    z = 1.015 ** t
+    ys, xs = torch.meshgrid(torch.arange(1080.0, device="cuda"), torch.arange(1920.0, device="cuda"), indexing="ij")
+    gt = torch.stack([(1.015 - 1) * (xs - 959.5) - 1.7 * z * 1.015, (1.015 - 1) * (ys - 539.5) + 0.9 * z * 1.015], -1)
+    err = (seq[t] - gt)[100:-100, 100:-100].norm(dim=-1)
+    assert err.mean().item() < 0.25, err.mean().item()
+
+
+@pytest.mark.skipif(not have_cv2(), reason="cv2 wheel not importable on this box")
+def test_farneback_live_cv2_1080p_and_720p(b2, seq1080):
+    import cv2
+    from hackathonopticalflow_b200 import synth
+    for fr in (seq1080, synth.sequence(720, 1280, 2, seed=1001)):
+        ref = cv2.calcOpticalFlowFarneback(fr[0], fr[1], None, *REF_FB)
+        mean, mx = epe(b2.calcOpticalFlowFarneback(fr[0], fr[1], None, *REF_FB), ref)
+        assert mean <= FB_MEAN_TOL and mx <= FB_MAX_TOL, (mean, mx)
+        assert mean <= 1e-4 and mx <= 1e-2, ("regression guard", mean, mx)
+
+
+def test_farneback_host_batch_matches_single_calls(b2, synth_small):
+    f0, f1 = synth_small["f0"], synth_small["f1"]
+    prev = np.stack([f0, f1, f0, f1, f0, f1, f0])
+    nxt = np.stack([f1, f0, f1, f0, f1, f0, f1])
+    out = b2.calcOpticalFlowFarnebackBatch(prev, nxt)
+    a = b2.calcOpticalFlowFarneback(f0, f1, None, *REF_FB)
+    c = b2.calcOpticalFlowFarneback(f1, f0, None, *REF_FB)
+    for k in range(7):
+        assert np.array_equal(out[k], a if k % 2 == 0 else c)
+
+
+# ------------------------------------------------------------------ K10-K11 PyrLK
+def _lk_check(got, want_next, want_status, want_err=None):
+    nxt, st, err = got
+    assert st.dtype == np.uint8 and st.shape == want_status.shape and err.shape == want_status.shape
+    assert (st == want_status).mean() >= LK_STATUS_TOL
+    # failed points keep their last estimate and the viewer consumes them (it ignores status): compare all
+    assert np.abs(nxt.reshape(-1, 2) - want_next.reshape(-1, 2)).max() <= LK_POS_TOL
+    if want_err is not None:
+        ok = (st.ravel() == 1) & (want_status.ravel() == 1)
+        assert np.abs(err - want_err).ravel()[ok].max() <= 0.05
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_lk_grid_golden_real_crops(b2, crops, i):
+    from hackathonopticalflow_b200 import pathfinder
+    g0, g1 = crops[f"gray0_{i}"], crops[f"gray1_{i}"]
+    pts = pathfinder.grid_points(640, 360, 30)
+    got = b2.calcOpticalFlowPyrLK(g1, g0, pts, None, **LK_GRID)   # current frame first, as the viewer does
+    assert got[0].shape == pts.shape
+    _lk_check(got, crops[f"lk_next_{i}"], crops[f"lk_status_{i}"], crops[f"lk_err_{i}"])
+
+
+def test_lk_grid_golden_full_1080p(b2, full1080):
+    from hackathonopticalflow_b200 import pathfinder
+    g0, g1 = _decode_png(full1080["png0"]), _decode_png(full1080["png1"])
+    pts = pathfinder.grid_points(1920, 1080, 30)
+    assert len(pts) == 2304
+    _lk_check(b2.calcOpticalFlowPyrLK(g1, g0, pts, None, **LK_GRID), full1080["lk_next"], full1080["lk_status"],
+              full1080["lk_err"])
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_lk_track_forward_backward_golden(b2, crops, i):
+    if f"trk_p1_{i}" not in crops.files:
+        pytest.skip("no corners in this crop")
+    g0, g1, p0 = crops[f"gray0_{i}"], crops[f"gray1_{i}"], crops[f"gftt_{i}"]
+    p1, st, _ = b2.calcOpticalFlowPyrLK(g0, g1, p0, None, **LK_TRACK)          # SparseOF.py:35
+    p0r, st_b, _ = b2.calcOpticalFlowPyrLK(g1, g0, p1, None, **LK_TRACK)       # SparseOF.py:36
+    assert p1.shape == p0.shape == (len(p0), 1, 2)
+    assert np.array_equal(st, crops[f"trk_st_f_{i}"])
+    assert np.abs(p1 - crops[f"trk_p1_{i}"]).max() <= LK_POS_TOL
+    good = np.abs(p0 - p0r).reshape(-1, 2).max(-1) < 1                           # SparseOF.py:37-38
+    assert (good == crops[f"trk_good_{i}"]).mean() >= LK_STATUS_TOL
+
+
+def test_lk_edge_points_and_oracle(b2, crops):
+    """Out-of-frame, border and sub-pixel points against the numpy oracle (status semantics of failed points)."""
+    from oracle import pyrlk as olk
+    g0, g1 = crops["gray0_1"], crops["gray1_1"]
+    pts = np.float32([[0, 0], [639, 359], [-50, 10], [700, 400], [3.5, 100.25], [637.5, 7.75], [320, 180],
+                      [-45.5, -45.5], [639.9, 359.9], [100000, 5]])
+    for win, lvl in [((45, 45), 2), ((15, 15), 2), ((9, 31), 1), ((21, 21), 3)]:
+        want = olk.pyrlk(g1, g0, pts, None, win, lvl, (3, 10, 0.03))
+        got = b2.calcOpticalFlowPyrLK(g1, g0, pts, None, winSize=win, maxLevel=lvl, criteria=(3, 10, 0.03))
+        assert np.array_equal(got[1], want[1]), (win, got[1].ravel(), want[1].ravel())
+        assert np.abs(got[0] - want[0]).max() <= LK_POS_TOL
+
+
+def test_lk_initial_flow_and_min_eig_flags(b2, crops):
+    from oracle import pyrlk as olk
+    from hackathonopticalflow_b200 import pathfinder
+    g0, g1 = crops["gray0_0"], crops["gray1_0"]
+    pts = pathfinder.grid_points(640, 360, 60)
+    guess = pts + np.float32([1.5, -0.5])
+    want = olk.pyrlk(g0, g1, pts, guess, (21, 21), 2, (3, 10, 0.03), flags=4 | 8)
+    got = b2.calcOpticalFlowPyrLK(g0, g1, pts, guess.copy(), winSize=(21, 21), maxLevel=2, criteria=(3, 10, 0.03),
+                                  flags=b2.OPTFLOW_USE_INITIAL_FLOW | b2.OPTFLOW_LK_GET_MIN_EIGENVALS)
+    assert np.array_equal(got[1], want[1])
+    assert np.abs(got[0] - want[0]).max() <= LK_POS_TOL
+    assert np.allclose(got[2], want[2], rtol=1e-3, atol=1e-6)
+
+
+def test_lk_batched_shared_grid_matches_single(batch, seq1080):
+    import torch
+    from hackathonopticalflow_b200 import cv2compat as b2m, pathfinder
+    fr = torch.from_numpy(seq1080).cuda()
+    pts = pathfinder.grid_points(1920, 1080, 30)
+    nxt, st, err = batch.pyrlk(fr[1:].contiguous(), fr[:-1].contiguous(), torch.from_numpy(pts).cuda(),
+                               **batch.LK_GRID_DEFAULTS)
+    one = b2m.calcOpticalFlowPyrLK(seq1080[3], seq1080[2], pts, None, **LK_GRID)
+    assert np.array_equal(nxt[2].cpu().numpy(), one[0]) and np.array_equal(st[2].cpu().numpy(), one[1].ravel())
+    assert st.float().mean().item() > 0.99     # the synthetic flight is fully trackable
+    # ground truth of the flight, backwards in time (current -> previous)
+    flow = (nxt[2] - torch.from_numpy(pts).cuda())
+    assert flow.norm(dim=-1).mean().item() > 1.0
+
+
+# ------------------------------------------------------------------ K7-K9 GFTT
+@pytest.mark.parametrize("i", range(4))
+def test_gftt_golden_exact(b2, crops, i):
+    g0, g1 = crops[f"gray0_{i}"], crops[f"gray1_{i}"]
+    want = crops[f"gftt_{i}"]
+    got = b2.goodFeaturesToTrack(g0, mask=None, **GFTT)
+    if len(want) == 0:
+        assert got is None
+        return
+    assert got.dtype == np.float32 and got.shape == want.shape and np.array_equal(got, want)
+    masked = b2.goodFeaturesToTrack(g1, mask=crops[f"gftt_mask_{i}"], **GFTT)      # SparseOF.py:61-69
+    wm = crops[f"gftt_masked_{i}"]
+    assert (masked is None and len(wm) == 0) or np.array_equal(masked, wm)
+    dense = b2.goodFeaturesToTrack(g0, 500, 0.01, 5, blockSize=3)
+    assert np.array_equal(dense, crops[f"gftt_dense_{i}"])
+
+
+def test_gftt_full_1080p_golden_and_none(b2, full1080):
+    g0 = _decode_png(full1080["png0"])
+    assert np.array_equal(b2.goodFeaturesToTrack(g0, mask=None, **GFTT), full1080["gftt"])
+    assert b2.goodFeaturesToTrack(np.full((64, 64), 7, np.uint8), mask=None, **GFTT) is None
+    assert b2.goodFeaturesToTrack(g0, mask=np.zeros_like(g0), **GFTT) is None
+
+
+def test_gftt_unbounded_list_same_set_as_oracle(b2, crops):
+    """maxCorners=0, minDistance=0: every local maximum above threshold; the SET must match the oracle (order of
+    near-equal scores may differ by float summation order, SURVEY hard parts)."""
+    from oracle import gftt as ogf
+    g = crops["gray0_3"]
+    got = b2.goodFeaturesToTrack(g, 0, 0.05, 0, blockSize=5)
+    want = ogf.good_features_to_track(g, 0, 0.05, 0, None, 5)
+    a, c = set(map(tuple, got.reshape(-1, 2))), set(map(tuple, want.reshape(-1, 2)))
+    assert len(a ^ c) <= max(1, len(c) // 200)
+
+
+# ------------------------------------------------------------------ K12 downstream filter
+def test_vector_filter_and_danger_points_vs_reference_restatement(batch, crops, full1080):
+    import torch
+    from hackathonopticalflow_b200 import pathfinder
+    from oracle import pathfinder as opf
+    cases = [(pathfinder.grid_points(1920, 1080, 30), full1080["lk_next"], 1920, 1080)]
+    cases += [(pathfinder.grid_points(640, 360, 30), crops[f"lk_next_{i}"], 640, 360) for i in range(4)]
+    for pts, nxt, w, h in cases:
+        flow_o, pts_o, mask_o, mod_o = opf.vector_filter(nxt, pts, w, h)
+        out = batch.pathfinder_filter(torch.from_numpy(pts).cuda(), torch.from_numpy(nxt).cuda()[None], w, h)
+        mask = out["mask"][0].cpu().numpy().astype(bool)
+        assert (mask == mask_o).mean() >= MASK_TOL
+        k = int(out["n_kept"][0])
+        if np.array_equal(mask, mask_o):
+            assert np.array_equal(out["kept_pts"][0, :k].cpu().numpy(), pts_o)
+            same = (out["kept_flow"][0, :k].cpu().numpy() == flow_o).all(axis=1).mean()
+            assert same >= MASK_TOL
+            v = opf.danger_intensity(out["kept_flow"][0, :k].cpu().numpy(), pts_o)
+            assert np.array_equal(out["danger_v"][0, :k].cpu().numpy(), v)
+        s = out["stats"][0].cpu().numpy()
+        assert abs(s[4] - np.median(mod_o)) <= 1e-5 * max(1, abs(s[4])) and s[6] == k
+
+
+def test_get_flow_lk_drop_in_end_to_end(crops):
+    """The viewer's get_flow_lk (LK + filter) end to end against cv2 LK golden + the reference restatement."""
+    from hackathonopticalflow_b200 import pathfinder
+    from oracle import pathfinder as opf
+    pts = pathfinder.grid_points(640, 360, 30)
+    for i in range(4):
+        flow, kept = pathfinder.get_flow_lk(crops[f"gray0_{i}"], crops[f"gray1_{i}"], pts)
+        flow_o, pts_o, mask_o, _ = opf.vector_filter(crops[f"lk_next_{i}"], pts, 640, 360)
+        a = set(map(tuple, kept))
+        c = set(map(tuple, pts_o))
+        assert len(a & c) / max(len(c), 1) >= MASK_TOL
+
+
+def test_full_pipeline_4k_config5(batch):
+    """Config 5 shape: 3840x2160 BGR frames -> gray -> 9216-point grid LK -> filter + danger + dense flow stats."""
+    import torch
+    from hackathonopticalflow_b200 import pathfinder, synth
+    bgr = torch.from_numpy(synth.sequence(2160, 3840, 3, seed=1004, gray=False)).cuda()
+    pipe = pathfinder.PathfinderPipeline(2160, 3840, dense=True, chunk_pairs=2)
+    out = pipe.run(bgr)
+    assert out["next_pts"].shape == (2, 9216, 2)
+    assert out["flow"].shape == (2, 2160, 3840, 2) and torch.isfinite(out["flow"]).all()
+    assert (out["n_kept"] > 4000).all() and (out["n_kept"] <= 4608).all()
+    fs = out["flow_stats"].cpu().numpy()
+    assert (fs[:, 0] > 1).all() and (fs[:, 1] >= fs[:, 0]).all()
+    # gray is the bit-exact luma
+    want = synth.to_gray(bgr[1].cpu().numpy())
+    assert np.array_equal(out["gray"][1].cpu().numpy(), want)
+
+
+def test_flow_stats_deterministic_and_correct(batch):
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(1)
+    flow = torch.randn((3, 270, 480, 2), device="cuda", generator=g) * 3
+    s1, s2 = batch.flow_stats(flow), batch.flow_stats(flow)
+    assert torch.equal(s1, s2)
+    mag = flow.double().norm(dim=-1)
+    assert torch.allclose(s1[:, 0].double(), mag.mean(dim=(1, 2)), rtol=1e-5)
+    assert torch.allclose(s1[:, 1].double(), mag.amax(dim=(1, 2)), rtol=1e-6)
+    assert torch.allclose(s1[:, 2].double(), flow[..., 0].double().mean(dim=(1, 2)), atol=1e-5)

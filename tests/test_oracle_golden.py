@@ -1,0 +1,129 @@
+"""CPU: the numpy oracle against the committed cv2 golden vectors (tests/golden/make_golden.py) and, when the
+cv2 wheel is importable, against live cv2 on the same inputs.  This is what pins the oracle."""
+import numpy as np
+import pytest
+
+from conftest import epe, have_cv2
+from oracle import farneback as ofb
+from oracle import gftt as ogf
+from oracle import gray_pyr as ogp
+from oracle import pathfinder as opf
+from oracle import pyrlk as olk
+
+LK_GRID = dict(win=(45, 45), max_level=2, criteria=(3, 10, 0.03))
+LK_TRACK = dict(win=(15, 15), max_level=2, criteria=(3, 10, 0.03))
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_gray_and_pyrdown_bit_exact(crops, i):
+    g0 = ogp.bgr2gray(crops[f"bgr0_{i}"])
+    assert np.array_equal(g0, crops[f"gray0_{i}"])
+    assert np.array_equal(ogp.bgr2gray(crops[f"bgr1_{i}"]), crops[f"gray1_{i}"])
+    p1 = ogp.pyrdown_u8(g0)
+    assert np.array_equal(p1, crops[f"pyr1_{i}"])
+    assert np.array_equal(ogp.pyrdown_u8(p1), crops[f"pyr2_{i}"])
+
+
+def test_gray_exhaustive_formula_edges():
+    # extremes and the rounding boundary of the 15-bit fixed-point luma
+    bgr = np.array([[[0, 0, 0], [255, 255, 255], [255, 0, 0], [0, 255, 0], [0, 0, 255], [1, 2, 3]]], np.uint8)
+    assert ogp.bgr2gray(bgr).tolist() == [[0, 255, 29, 150, 76, 2]]
+
+
+@pytest.mark.parametrize("i", [0, 2])
+def test_farneback_real_crops(crops, i):
+    flow = ofb.farneback(crops[f"gray0_{i}"], crops[f"gray1_{i}"])
+    mean, mx = epe(flow[::4, ::4], crops[f"flow_s4_{i}"])
+    assert mean < 1e-4 and mx < 5e-2, (mean, mx)  # ill-conditioned real-footage pixels: survey saw 0.017
+
+
+@pytest.mark.parametrize("name", ["ref", "gauss", "p08", "even", "sig0"])
+def test_farneback_parameter_sets(synth_small, name):
+    a = synth_small[f"args_{name}"]
+    flow = ofb.farneback(synth_small["f0"], synth_small["f1"], None, float(a[0]), int(a[1]), int(a[2]), int(a[3]),
+                         int(a[4]), float(a[5]), int(a[6]))
+    mean, mx = epe(flow, synth_small[f"flow_{name}"])
+    assert mean < 1e-5 and mx < 1e-3, (name, mean, mx)
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_lk_grid_real_crops(crops, i):
+    g0, g1 = crops[f"gray0_{i}"], crops[f"gray1_{i}"]
+    pts = opf.grid_points(g0.shape[1], g0.shape[0], 30)
+    nxt, st, err = olk.pyrlk(g1, g0, pts, None, **LK_GRID)  # viewer order: current frame first
+    assert (st == crops[f"lk_status_{i}"]).mean() >= 0.995
+    ok = (st.ravel() == 1) & (crops[f"lk_status_{i}"].ravel() == 1)
+    assert np.abs(nxt - crops[f"lk_next_{i}"]).max() < 0.05
+    assert np.abs(err - crops[f"lk_err_{i}"])[ok].max() < 0.01
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_lk_track_forward_backward(crops, i):
+    if f"trk_p1_{i}" not in crops.files:
+        pytest.skip("no corners in this crop")
+    g0, g1 = crops[f"gray0_{i}"], crops[f"gray1_{i}"]
+    p0 = crops[f"gftt_{i}"]
+    p1, st, _ = olk.pyrlk(g0, g1, p0, None, **LK_TRACK)
+    p0r, st_b, _ = olk.pyrlk(g1, g0, p1, None, **LK_TRACK)
+    assert p1.shape == p0.shape
+    assert np.array_equal(st, crops[f"trk_st_f_{i}"])
+    assert np.abs(p1 - crops[f"trk_p1_{i}"]).max() < 0.05
+    good = np.abs(p0 - p0r).reshape(-1, 2).max(-1) < 1
+    assert (good == crops[f"trk_good_{i}"]).mean() >= 0.995
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_gftt_real_crops(crops, i):
+    g0, g1 = crops[f"gray0_{i}"], crops[f"gray1_{i}"]
+    want = crops[f"gftt_{i}"]
+    got = ogf.good_features_to_track(g0, 20, 0.3, 10, None, 7)
+    if len(want) == 0:
+        assert got is None
+    else:
+        assert np.array_equal(got, want)
+        masked = ogf.good_features_to_track(g1, 20, 0.3, 10, crops[f"gftt_mask_{i}"], 7)
+        wm = crops[f"gftt_masked_{i}"]
+        assert (masked is None and len(wm) == 0) or np.array_equal(masked, wm)
+    dense = ogf.good_features_to_track(g0, 500, 0.01, 5, None, 3)
+    assert np.array_equal(dense, crops[f"gftt_dense_{i}"])
+
+
+def test_gftt_none_on_flat_image():
+    assert ogf.good_features_to_track(np.full((64, 64), 7, np.uint8), 20, 0.3, 10, None, 7) is None
+
+
+def test_full_1080p_golden_lk_and_gftt(full1080):
+    cv2 = pytest.importorskip("cv2")
+    g0 = cv2.imdecode(full1080["png0"], cv2.IMREAD_GRAYSCALE)
+    g1 = cv2.imdecode(full1080["png1"], cv2.IMREAD_GRAYSCALE)
+    assert g0.shape == (1080, 1920)
+    assert np.array_equal(ogf.good_features_to_track(g0, 20, 0.3, 10, None, 7), full1080["gftt"])
+    pts = opf.grid_points(1920, 1080, 30)
+    sel = np.arange(0, len(pts), 9)  # 256 of the 2304 grid points keeps the python loop to seconds
+    nxt, st, _ = olk.pyrlk(g1, g0, pts[sel], None, **LK_GRID)
+    assert (st == full1080["lk_status"][sel]).mean() >= 0.995
+    assert np.abs(nxt - full1080["lk_next"][sel]).max() < 0.05
+
+
+def test_vector_filter_counts(full1080):
+    pts = opf.grid_points(1920, 1080, 30)
+    flow, kept, mask, mod = opf.vector_filter(full1080["lk_next"], pts, 1920, 1080)
+    assert len(pts) == 2304 and mask.sum() == len(kept) == len(flow)
+    assert 1100 <= mask.sum() <= 1152  # N/2 minus the top 1 % (ties aside)
+    v = opf.danger_intensity(flow, kept)
+    assert v.dtype == np.uint8 and v.min() >= 50
+
+
+@pytest.mark.skipif(not have_cv2(), reason="cv2 wheel not importable")
+def test_oracle_matches_live_cv2_small():
+    import cv2
+    rng = np.random.default_rng(3)
+    for (h, w) in [(101, 77), (1, 9), (64, 1)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        g = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+        assert np.array_equal(ogp.bgr2gray(img), g)
+        assert np.array_equal(ogp.pyrdown_u8(g), cv2.pyrDown(g))
+    g = rng.integers(0, 256, (90, 120), dtype=np.uint8)
+    s = ogp.scharr_s16(g)
+    assert np.array_equal(s[..., 0], cv2.Scharr(g, cv2.CV_16S, 1, 0))
+    assert np.array_equal(s[..., 1], cv2.Scharr(g, cv2.CV_16S, 0, 1))
