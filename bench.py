@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU)
     ap.add_argument("--chunk", type=int, default=CHUNK_PAIRS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -223,12 +224,12 @@ def main():
     value = world * P * args.steps / (ms * 1e-3)
 
     # ---- end to end through the cv2-compatible host call: pinned host frames in, host flow out ----
-    E = E2E_PAIRS
+    E = min(E2E_PAIRS, P)
     prev_h = torch.from_numpy(frames_host[:E]).pin_memory()
     next_h = torch.from_numpy(frames_host[1:E + 1]).pin_memory()
     flow_h = torch.empty((E, H, W, 2), dtype=torch.float32).pin_memory()
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
+    e2e_steps = 0 if args.no_e2e else max(3, min(args.steps, 10))
+    for _ in range(0 if args.no_e2e else 2):
         cv2compat.calcOpticalFlowFarnebackBatch(prev_h.numpy(), next_h.numpy(), flow=flow_h.numpy(), **PARAMS)
     barrier()
     te0 = time.perf_counter()
@@ -236,7 +237,7 @@ def main():
         cv2compat.calcOpticalFlowFarnebackBatch(prev_h.numpy(), next_h.numpy(), flow=flow_h.numpy(), **PARAMS)
     torch.cuda.synchronize()
     e2e_ms = b2dist.max_over_ranks((time.perf_counter() - te0) * 1e3, dev)
-    e2e_value = world * E * e2e_steps / (e2e_ms * 1e-3)
+    e2e_value = world * E * e2e_steps / (e2e_ms * 1e-3) if e2e_steps else None
 
     if rank != 0:
         if world > 1:
