@@ -10,6 +10,7 @@
 // solve are one kernel per (level, iteration); the x(1/pyr_scale) bilinear flow upsample is folded into
 // the first iteration of each level.
 #include <math.h>
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -36,6 +37,9 @@ struct FbLevel {
   // flow upsample tables from the next-coarser level (valid when k < top level)
   int *ux0, *ux1, *uy0, *uy1;
   float *ufx, *ufy;
+  // fused level-image kernel: output tile and the largest source region any tile needs (0 = use two-pass path)
+  int f_tw, f_th, f_rw, f_rh, f_rw_pad;
+  size_t f_smem;
 };
 
 struct FbPlan {
@@ -196,8 +200,32 @@ static int build_plan(int rows, int cols, const b2of_farneback_params& p, FbPlan
     std::vector<float> f;
     linear_tables(L.w, cols, s0, s1, f);
     offs[i].sx0 = put(s0.data(), s0.size() * 4); offs[i].sx1 = put(s1.data(), s1.size() * 4); offs[i].fx = put(f.data(), f.size() * 4);
-    linear_tables(L.h, rows, s0, s1, f);
-    offs[i].sy0 = put(s0.data(), s0.size() * 4); offs[i].sy1 = put(s1.data(), s1.size() * 4); offs[i].fy = put(f.data(), f.size() * 4);
+    std::vector<int> t0, t1;
+    std::vector<float> tf;
+    linear_tables(L.h, rows, t0, t1, tf);
+    offs[i].sy0 = put(t0.data(), t0.size() * 4); offs[i].sy1 = put(t1.data(), t1.size() * 4); offs[i].fy = put(tf.data(), tf.size() * 4);
+    {
+      // pick the largest output tile whose source region fits in ~100 KB of shared memory (2 CTAs/SM)
+      const int cand[4][2] = {{64, 16}, {32, 16}, {32, 8}, {16, 8}};
+      L.f_tw = 0;
+      int r = L.ksz / 2;
+      for (int c = 0; c < 4 && !L.f_tw; ++c) {
+        int tw = cand[c][0], th = cand[c][1], rw = 0, rh = 0;
+        for (int x0 = 0; x0 < L.w; x0 += tw) {
+          int x1 = std::min(x0 + tw, L.w) - 1;
+          rw = std::max(rw, s1[x1] + r - (s0[x0] - r) + 1);
+        }
+        for (int y0 = 0; y0 < L.h; y0 += th) {
+          int y1 = std::min(y0 + th, L.h) - 1;
+          rh = std::max(rh, t1[y1] + r - (t0[y0] - r) + 1);
+        }
+        int rw_pad = (int)align_up(rw, 16);
+        size_t smem = (size_t)rh * rw_pad + (size_t)rh * tw * sizeof(float);
+        if (smem <= 100 * 1024) {
+          L.f_tw = tw; L.f_th = th; L.f_rw = rw; L.f_rh = rh; L.f_rw_pad = rw_pad; L.f_smem = smem;
+        }
+      }
+    }
     if (i > 0) {
       const FbLevel& C = pl->lv[i - 1];
       linear_tables(L.w, C.w, s0, s1, f);
@@ -318,8 +346,75 @@ __global__ void __launch_bounds__(128) fb_level_vpass(const float* __restrict__ 
 }
 
 // ----------------------------------------------------------------------------------------------
+// K3 (fused form): one kernel per level straight from the u8 frame.  The CTA stages the source region of its
+// output tile in shared memory (REFLECT_101 applied while loading), runs the horizontal blur+resample into a
+// second shared buffer and the vertical blur+resample out of it.  Used whenever the region fits in shared
+// memory; otherwise the two-pass kernels above (global scratch T) take over.
+// ----------------------------------------------------------------------------------------------
+struct LevelFusedArgs {
+  const uint8_t* frames; size_t step, frame_stride; int W, H;
+  float* I; int wk, hk, pitch; size_t i_frame_stride;
+  const float* taps; int ksz;
+  const int *sx0, *sx1, *sy0, *sy1; const float *fx, *fy;
+  int tw, th;          // output tile
+  int rw, rh;          // max source region (cols, rows) over all tiles
+  int rw_pad;          // rw rounded up to 16
+};
+
+__global__ void __launch_bounds__(256) fb_level_fused(LevelFusedArgs a) {
+  extern __shared__ __align__(16) unsigned char lsm[];
+  uint8_t* s_src = lsm;                                        // [rh][rw_pad]
+  float* s_h = (float*)(lsm + (size_t)a.rh * a.rw_pad);        // [rh][tw]
+  const int x0 = blockIdx.x * a.tw, y0 = blockIdx.y * a.th;
+  const int x1 = min(x0 + a.tw, a.wk) - 1, y1 = min(y0 + a.th, a.hk) - 1;
+  const int r = a.ksz >> 1;
+  const int c_lo = a.sx0[x0] - r, c_hi = a.sx1[x1] + r;
+  const int r_lo = a.sy0[y0] - r, r_hi = a.sy1[y1] + r;
+  const int nc = c_hi - c_lo + 1, nr = r_hi - r_lo + 1;
+  const uint8_t* fb = a.frames + blockIdx.z * a.frame_stride;
+  const int t = threadIdx.x;
+  for (int i = t; i < nr * nc; i += 256) {
+    int rr = i / nc, cc = i - rr * nc;
+    int gy = reflect101(r_lo + rr, a.H), gx = reflect101(c_lo + cc, a.W);
+    s_src[rr * a.rw_pad + cc] = fb[(size_t)gy * a.step + gx];
+  }
+  __syncthreads();
+  const int tw = x1 - x0 + 1;
+  for (int i = t; i < nr * tw; i += 256) {
+    int rr = i / tw, x = i - rr * tw;
+    int ia = a.sx0[x0 + x] - c_lo - r, ib = a.sx1[x0 + x] - c_lo - r;
+    float f = a.fx[x0 + x];
+    const uint8_t* row = s_src + rr * a.rw_pad;
+    float va = 0.f, vb = 0.f;
+    for (int k = 0; k < a.ksz; ++k) {
+      float kt = __ldg(a.taps + k);
+      va = fmaf(kt, (float)row[ia + k], va);
+      vb = fmaf(kt, (float)row[ib + k], vb);
+    }
+    s_h[rr * a.tw + x] = va * (1.f - f) + vb * f;
+  }
+  __syncthreads();
+  const int th = y1 - y0 + 1;
+  float* ob = a.I + blockIdx.z * a.i_frame_stride;
+  for (int i = t; i < th * tw; i += 256) {
+    int y = i / tw, x = i - y * tw;
+    int ia = a.sy0[y0 + y] - r_lo - r, ib = a.sy1[y0 + y] - r_lo - r;
+    float f = a.fy[y0 + y];
+    float va = 0.f, vb = 0.f;
+    for (int k = 0; k < a.ksz; ++k) {
+      float kt = __ldg(a.taps + k);
+      va = fmaf(kt, s_h[(ia + k) * a.tw + x], va);
+      vb = fmaf(kt, s_h[(ib + k) * a.tw + x], vb);
+    }
+    ob[(size_t)(y0 + y) * a.pitch + x0 + x] = va * (1.f - f) + vb * f;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // K4: polynomial expansion. 64x32 output tile per CTA; the (32+2n)x(64+2n) input tile and the three
-// vertically filtered rows live in shared memory; REPLICATE borders; planar 5-channel output.
+// vertically filtered rows live in shared memory; REPLICATE borders.
+// Output layout per frame and level: Ra = float4 plane (ch0..3) followed by Rb = float plane (ch4), so the
+// bilinear gather of the warped frame in K5 is 2 loads per corner instead of 5.
 // ----------------------------------------------------------------------------------------------
 constexpr int PE_TW = 64, PE_TH = 32;
 
@@ -358,9 +453,11 @@ __global__ void __launch_bounds__(256) fb_polyexp(const float* __restrict__ I, i
     s_r0[i] = r0; s_r1[i] = r1; s_r2[i] = r2;
   }
   __syncthreads();
-  // horizontal pass: 64x32 outputs, 8 per thread (same column group, rows ty, ty+8, ...)
+  // horizontal pass: 64x32 outputs, 8 per thread (same column, rows ty, ty+4, ...)
   const int tx = t & 63, ty = t >> 6;
   float* rb = R + blockIdx.z * r_frame_stride;
+  float4* ra4 = (float4*)rb;
+  float* rb1 = rb + 4 * plane_stride;
   for (int r = ty; r < PE_TH; r += 4) {
     int gx = x0 + tx, gy = y0 + r;
     if (gx >= w || gy >= h) continue;
@@ -379,26 +476,27 @@ __global__ void __launch_bounds__(256) fb_polyexp(const float* __restrict__ I, i
       b5 = fmaf(p2[k] + p2[-k], pc.g[k], b5);
     }
     size_t o = (size_t)gy * pitch + gx;
-    rb[o] = b3 * pc.ig11;
-    rb[o + plane_stride] = b2 * pc.ig11;
-    rb[o + 2 * plane_stride] = b1 * pc.ig03 + b5 * pc.ig33;
-    rb[o + 3 * plane_stride] = b1 * pc.ig03 + b4 * pc.ig33;
-    rb[o + 4 * plane_stride] = b6 * pc.ig55;
+    ra4[o] = make_float4(b3 * pc.ig11, b2 * pc.ig11, b1 * pc.ig03 + b5 * pc.ig33, b1 * pc.ig03 + b4 * pc.ig33);
+    rb1[o] = b6 * pc.ig55;
   }
 }
 
 // ----------------------------------------------------------------------------------------------
 // K5/K6: one fused kernel per (level, iteration):
 //   flow_in (zero | previous iteration | bilinear x(1/pyr_scale) upsample of the coarser level)
-//   -> UpdateMatrices on a (T+2m)^2 halo tile (bilinear warp of R1, border attenuation)   [smem M, 5 ch]
-//   -> separable (2m+1)^2 window sum, BORDER_REPLICATE (box, or Gaussian taps with flag 256)
+//   -> UpdateMatrices on a (T+2m)^2 halo tile (bilinear warp of R1, border attenuation)   [smem M: float4 + float]
+//   -> separable (2m+1)^2 window sum, BORDER_REPLICATE (box, or Gaussian taps with flag 256):
+//        horizontal pass IN PLACE (one thread owns a whole row: output x only needs inputs >= x),
+//        vertical pass straight into the solve
 //   -> per-pixel 2x2 solve -> flow_out
+// Packed f32x2 adds (FADD2) carry 4 of the 5 channels two at a time.
+// Specialised for the reference's window (T=56, m=7: 99.4 KB smem, 2 CTAs/SM); generic <0,0> takes any m.
 // ----------------------------------------------------------------------------------------------
-constexpr int IT_T = 32;       // output tile edge
-constexpr int IT_THREADS = 256;
+constexpr int IT_THREADS = 512;
+constexpr int IT_T_FAST = 56;
 
 struct IterArgs {
-  const float* R;          // level base, [frame][5][h][pitch]
+  const float* R;          // level base, [frame]{float4 plane ch0..3, float plane ch4}
   size_t r_frame_stride, plane_stride;
   int pitch, w, h;
   int pair_frame_step;     // 1: sequence (pair p = frames p, p+1); 2: independent pairs (2p, 2p+1)
@@ -414,9 +512,28 @@ struct IterArgs {
   size_t flow_out_pair_stride;
   int out_pitch;           // in float2
   int m;                   // winsize / 2
+  int tile;                // output tile edge (generic kernel)
   float inv_area;          // 1 / winsize^2 (box)
   const float* gtaps;      // Gaussian window taps or nullptr
 };
+
+__device__ __forceinline__ float4 add4(float4 a, float4 b) {
+  float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 sub4(float4 a, float4 b) {  // a - b (exact: fma with -1)
+  const float2 m1 = make_float2(-1.f, -1.f);
+  float2 lo = __ffma2_rn(make_float2(b.x, b.y), m1, make_float2(a.x, a.y));
+  float2 hi = __ffma2_rn(make_float2(b.z, b.w), m1, make_float2(a.z, a.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 fma4s(float4 v, float s, float4 acc) {  // acc + v*s
+  const float2 ss = make_float2(s, s);
+  float2 lo = __ffma2_rn(make_float2(v.x, v.y), ss, make_float2(acc.x, acc.y));
+  float2 hi = __ffma2_rn(make_float2(v.z, v.w), ss, make_float2(acc.z, acc.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
 
 __device__ __forceinline__ float2 fetch_flow(const IterArgs& a, const float2* fin, int x, int y) {
   if (a.mode == 0) return make_float2(0.f, 0.f);
@@ -439,25 +556,33 @@ __device__ __forceinline__ float border_w(int i, int n) {
   return s;
 }
 
-template <bool GAUSS>
-__global__ void __launch_bounds__(IT_THREADS) fb_iter(IterArgs a) {
-  extern __shared__ float smem[];
-  const int m = a.m;
-  const int E = IT_T + 2 * m;       // halo tile edge
-  const int ES = E | 1;             // odd row stride: conflict-free column walks
-  float* sM = smem;                 // [5][E][ES]
-  float* sH = sM + 5 * E * ES;      // [5][E][IT_T+1]   horizontal sums
-  const int HS = IT_T + 1;
+__device__ __forceinline__ float2 solve2x2(float g11, float g12, float g22, float h1, float h2) {
+  float idet = 1.f / (g11 * g22 - g12 * g12 + 1e-3f);
+  return make_float2((g11 * h2 - g12 * h1) * idet, (g22 * h1 - g12 * h2) * idet);
+}
+
+template <int CT, int CM, bool GAUSS>
+__global__ void __launch_bounds__(IT_THREADS, CT ? 2 : 1) fb_iter(IterArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int T = CT ? CT : a.tile;
+  const int m = CT ? CM : a.m;
+  const int E = T + 2 * m;          // halo tile edge
+  const int ES = E | 1;             // odd row stride (in elements): conflict-free row walks
+  float4* sM4 = (float4*)smem;      // [E][ES]  (M0..M3)
+  float* sM1 = smem + 4 * E * ES;   // [E][ES]  (M4)
   const int pair = blockIdx.z;
-  const int x0 = blockIdx.x * IT_T, y0 = blockIdx.y * IT_T;
+  const int x0 = blockIdx.x * T, y0 = blockIdx.y * T;
   const int w = a.w, h = a.h, pitch = a.pitch;
-  const float* R0 = a.R + (size_t)pair * a.pair_frame_step * a.r_frame_stride;
-  const float* R1 = R0 + a.r_frame_stride;
-  const size_t ps = a.plane_stride;
+  const float* base0 = a.R + (size_t)pair * a.pair_frame_step * a.r_frame_stride;
+  const float4* __restrict__ R0a = (const float4*)base0;
+  const float* __restrict__ R0b = base0 + 4 * a.plane_stride;
+  const float4* __restrict__ R1a = (const float4*)(base0 + a.r_frame_stride);
+  const float* __restrict__ R1b = base0 + a.r_frame_stride + 4 * a.plane_stride;
   const float2* fin = a.flow_in ? a.flow_in + (size_t)pair * a.flow_in_pair_stride : nullptr;
   const int t = threadIdx.x;
 
   // ---- step A: M on the halo tile (positions clamped to the image = BORDER_REPLICATE of M) ----
+#pragma unroll 2
   for (int i = t; i < E * E; i += IT_THREADS) {
     int iy = i / E, ix = i - iy * E;
     int x = clampi(x0 - m + ix, 0, w - 1), y = clampi(y0 - m + iy, 0, h - 1);
@@ -466,26 +591,29 @@ __global__ void __launch_bounds__(IT_THREADS) fb_iter(IterArgs a) {
     float flx = floorf(fx), fly = floorf(fy);
     int x1 = (int)flx, y1 = (int)fly;
     fx -= flx; fy -= fly;
-    size_t o = (size_t)y * pitch + x;
-    float q0 = R0[o], q1 = R0[o + ps], q2 = R0[o + 2 * ps], q3 = R0[o + 3 * ps], q4 = R0[o + 4 * ps];
+    int o = y * pitch + x;
+    float4 q = R0a[o];
+    float q4 = R0b[o];
     float r2, r3, r4, r5, r6;
     if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
       float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-      const float* p = R1 + (size_t)y1 * pitch + x1;
-      r2 = a00 * p[0] + a01 * p[1] + a10 * p[pitch] + a11 * p[pitch + 1]; p += ps;
-      r3 = a00 * p[0] + a01 * p[1] + a10 * p[pitch] + a11 * p[pitch + 1]; p += ps;
-      r4 = a00 * p[0] + a01 * p[1] + a10 * p[pitch] + a11 * p[pitch + 1]; p += ps;
-      r5 = a00 * p[0] + a01 * p[1] + a10 * p[pitch] + a11 * p[pitch + 1]; p += ps;
-      r6 = a00 * p[0] + a01 * p[1] + a10 * p[pitch] + a11 * p[pitch + 1];
-      r4 = (q2 + r4) * 0.5f;
-      r5 = (q3 + r5) * 0.5f;
+      int o1 = y1 * pitch + x1;
+      float4 p00 = R1a[o1], p01 = R1a[o1 + 1], p10 = R1a[o1 + pitch], p11 = R1a[o1 + pitch + 1];
+      float s00 = R1b[o1], s01 = R1b[o1 + 1], s10 = R1b[o1 + pitch], s11 = R1b[o1 + pitch + 1];
+      r2 = a00 * p00.x + a01 * p01.x + a10 * p10.x + a11 * p11.x;
+      r3 = a00 * p00.y + a01 * p01.y + a10 * p10.y + a11 * p11.y;
+      r4 = a00 * p00.z + a01 * p01.z + a10 * p10.z + a11 * p11.z;
+      r5 = a00 * p00.w + a01 * p01.w + a10 * p10.w + a11 * p11.w;
+      r6 = a00 * s00 + a01 * s01 + a10 * s10 + a11 * s11;
+      r4 = (q.z + r4) * 0.5f;
+      r5 = (q.w + r5) * 0.5f;
       r6 = (q4 + r6) * 0.25f;
     } else {
       r2 = r3 = 0.f;
-      r4 = q2; r5 = q3; r6 = q4 * 0.5f;
+      r4 = q.z; r5 = q.w; r6 = q4 * 0.5f;
     }
-    r2 = (q0 - r2) * 0.5f;
-    r3 = (q1 - r3) * 0.5f;
+    r2 = (q.x - r2) * 0.5f;
+    r3 = (q.y - r3) * 0.5f;
     r2 += r4 * d.y + r6 * d.x;
     r3 += r6 * d.y + r5 * d.x;
     if (x < 5 || x >= w - 5 || y < 5 || y >= h - 5) {
@@ -493,82 +621,95 @@ __global__ void __launch_bounds__(IT_THREADS) fb_iter(IterArgs a) {
       r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
     }
     int so = iy * ES + ix;
-    sM[so] = r4 * r4 + r6 * r6;
-    sM[so + E * ES] = (r4 + r5) * r6;
-    sM[so + 2 * E * ES] = r5 * r5 + r6 * r6;
-    sM[so + 3 * E * ES] = r4 * r2 + r6 * r3;
-    sM[so + 4 * E * ES] = r6 * r2 + r5 * r3;
+    sM4[so] = make_float4(r4 * r4 + r6 * r6, (r4 + r5) * r6, r5 * r5 + r6 * r6, r4 * r2 + r6 * r3);
+    sM1[so] = r6 * r2 + r5 * r3;
   }
   __syncthreads();
 
-  // ---- step B: horizontal window sums, one (channel, row) per work item ----
-  for (int i = t; i < 5 * E; i += IT_THREADS) {
-    const float* row = sM + i * ES;   // (c*E + iy) * ES
-    float* out = sH + i * HS;
-    if (GAUSS) {
-      for (int x = 0; x < IT_T; ++x) {
-        float s = row[x + m] * a.gtaps[0];
-        for (int k = 1; k <= m; ++k) s = fmaf(row[x + m - k] + row[x + m + k], a.gtaps[k], s);
-        out[x] = s;
+  // ---- step B: horizontal window sums in place; thread = one row of the float4 plane or of the float plane ----
+  {
+    const int g1 = (E + 31) & ~31;   // float-plane rows start at the next warp boundary
+    if (t < E) {
+      float4* row = sM4 + t * ES;
+      if (GAUSS) {
+        for (int x = 0; x < T; ++x) {
+          float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+          s = fma4s(row[x + m], a.gtaps[0], s);
+          for (int k = 1; k <= m; ++k) s = fma4s(add4(row[x + m - k], row[x + m + k]), a.gtaps[k], s);
+          row[x] = s;
+        }
+      } else {
+        float4 s = row[0];
+        for (int k = 1; k < 2 * m; ++k) s = add4(s, row[k]);
+        for (int x = 0; x < T; ++x) {
+          s = add4(s, row[x + 2 * m]);
+          float4 old = row[x];
+          row[x] = s;
+          s = sub4(s, old);
+        }
       }
-    } else {
-      float s = 0.f;
-      for (int k = 0; k < 2 * m; ++k) s += row[k];
-      for (int x = 0; x < IT_T; ++x) {
-        s += row[x + 2 * m];
-        out[x] = s;
-        s -= row[x];
+    } else if (t >= g1 && t < g1 + E) {
+      float* row = sM1 + (t - g1) * ES;
+      if (GAUSS) {
+        for (int x = 0; x < T; ++x) {
+          float s = row[x + m] * a.gtaps[0];
+          for (int k = 1; k <= m; ++k) s = fmaf(row[x + m - k] + row[x + m + k], a.gtaps[k], s);
+          row[x] = s;
+        }
+      } else {
+        float s = row[0];
+        for (int k = 1; k < 2 * m; ++k) s += row[k];
+        for (int x = 0; x < T; ++x) {
+          s += row[x + 2 * m];
+          float old = row[x];
+          row[x] = s;
+          s -= old;
+        }
       }
     }
   }
   __syncthreads();
 
-  // ---- step C: vertical window sums + 2x2 solve; thread = (column, 4-row segment) ----
+  // ---- step C: vertical window sums + 2x2 solve; thread = (column, row segment) ----
   {
-    const int x = t & 31, seg = t >> 5;   // 8 segments of 4 rows
+    const int nseg = IT_THREADS / T;
+    const int segr = (T + nseg - 1) / nseg;
+    const int seg = t / T, x = t - seg * T;
     const int gx = x0 + x;
-    float acc[5];
-    float2* fo = a.flow_out + (size_t)pair * a.flow_out_pair_stride;
-    if (GAUSS) {
-      for (int r = 0; r < 4; ++r) {
-        int y = seg * 4 + r;
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {
-          const float* col = sH + (c * E + y + m) * HS + x;
-          float s = col[0] * a.gtaps[0];
-          for (int k = 1; k <= m; ++k) s = fmaf(col[-k * HS] + col[k * HS], a.gtaps[k], s);
-          acc[c] = s;
+    if (seg < nseg && gx < w) {
+      float2* fo = a.flow_out + (size_t)pair * a.flow_out_pair_stride;
+      const int r0 = seg * segr;
+      const int r1 = min(r0 + segr, T);
+      if (GAUSS) {
+        for (int y = r0; y < r1; ++y) {
+          const float4* c4 = sM4 + (y + m) * ES + x;
+          const float* c1 = sM1 + (y + m) * ES + x;
+          float4 s4 = fma4s(c4[0], a.gtaps[0], make_float4(0.f, 0.f, 0.f, 0.f));
+          float s1 = c1[0] * a.gtaps[0];
+          for (int k = 1; k <= m; ++k) {
+            s4 = fma4s(add4(c4[-k * ES], c4[k * ES]), a.gtaps[k], s4);
+            s1 = fmaf(c1[-k * ES] + c1[k * ES], a.gtaps[k], s1);
+          }
+          int gy = y0 + y;
+          if (gy < h) fo[(size_t)gy * a.out_pitch + gx] = solve2x2(s4.x, s4.y, s4.z, s4.w, s1);
         }
-        int gy = y0 + y;
-        if (gx < w && gy < h) {
-          float g11 = acc[0], g12 = acc[1], g22 = acc[2], h1 = acc[3], h2 = acc[4];
-          float idet = 1.f / (g11 * g22 - g12 * g12 + 1e-3f);
-          fo[(size_t)gy * a.out_pitch + gx] = make_float2((g11 * h2 - g12 * h1) * idet, (g22 * h1 - g12 * h2) * idet);
-        }
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < 5; ++c) {
-        const float* col = sH + (c * E + seg * 4) * HS + x;
-        float s = 0.f;
-        for (int k = 0; k < 2 * m; ++k) s += col[k * HS];
-        acc[c] = s;
-      }
-      for (int r = 0; r < 4; ++r) {
-        int y = seg * 4 + r;
-        float v[5];
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {
-          const float* col = sH + (c * E + y) * HS + x;
-          acc[c] += col[2 * m * HS];
-          v[c] = acc[c] * a.inv_area;
-          acc[c] -= col[0];
-        }
-        int gy = y0 + y;
-        if (gx < w && gy < h) {
-          float g11 = v[0], g12 = v[1], g22 = v[2], h1 = v[3], h2 = v[4];
-          float idet = 1.f / (g11 * g22 - g12 * g12 + 1e-3f);
-          fo[(size_t)gy * a.out_pitch + gx] = make_float2((g11 * h2 - g12 * h1) * idet, (g22 * h1 - g12 * h2) * idet);
+      } else if (r0 < r1) {
+        const float4* c4 = sM4 + r0 * ES + x;
+        const float* c1 = sM1 + r0 * ES + x;
+        float4 s4 = c4[0];
+        float s1 = c1[0];
+        for (int k = 1; k < 2 * m; ++k) { s4 = add4(s4, c4[k * ES]); s1 += c1[k * ES]; }
+        for (int y = r0; y < r1; ++y) {
+          s4 = add4(s4, c4[2 * m * ES]);
+          s1 += c1[2 * m * ES];
+          int gy = y0 + y;
+          if (gy < h) {
+            float sc = a.inv_area;
+            fo[(size_t)gy * a.out_pitch + gx] = solve2x2(s4.x * sc, s4.y * sc, s4.z * sc, s4.w * sc, s1 * sc);
+          }
+          s4 = sub4(s4, c4[0]);
+          s1 -= c1[0];
+          c4 += ES; c1 += ES;
         }
       }
     }
@@ -638,20 +779,36 @@ static int fb_frames(const FbPlan* pl, const FbWorkspace& ws, const uint8_t* fra
     float* Ib = ws.I + (size_t)total_slots * lvl_off + (size_t)slot0 * plane;
     float* Rb = ws.R + (size_t)total_slots * 5 * lvl_off + (size_t)slot0 * 5 * plane;
     size_t t_stride = (size_t)H * pitch0 * slot_step, i_stride = plane * slot_step, r_stride = 5 * plane * slot_step;
-    dim3 g1(cdiv(L.w, 128), H, frames);
-    {
-      ProfScope ps(PT_FB_LEVEL_H, st, (double)frames * ((double)W * H + 4.0 * H * L.w));
-    fb_level_hpass<<<g1, 128, 0, st>>>(frames_dev, step, frame_stride, W, H, Tb, L.w, L.pitch, t_stride, L.taps, L.ksz,
-                                       L.sx0, L.sx1, L.fx);
+    if (L.f_tw) {
+      LevelFusedArgs fa{};
+      fa.frames = frames_dev; fa.step = step; fa.frame_stride = frame_stride; fa.W = W; fa.H = H;
+      fa.I = Ib; fa.wk = L.w; fa.hk = L.h; fa.pitch = L.pitch; fa.i_frame_stride = i_stride;
+      fa.taps = L.taps; fa.ksz = L.ksz;
+      fa.sx0 = L.sx0; fa.sx1 = L.sx1; fa.sy0 = L.sy0; fa.sy1 = L.sy1; fa.fx = L.fx; fa.fy = L.fy;
+      fa.tw = L.f_tw; fa.th = L.f_th; fa.rw = L.f_rw; fa.rh = L.f_rh; fa.rw_pad = L.f_rw_pad;
+      dim3 gf(cdiv(L.w, L.f_tw), cdiv(L.h, L.f_th), frames);
+      {
+        // algorithmic bytes: the u8 frame once + the f32 level image
+        ProfScope ps(PT_FB_LEVEL_H, st, (double)frames * ((double)W * H + 4.0 * L.h * L.w));
+        fb_level_fused<<<gf, 256, L.f_smem, st>>>(fa);
+      }
+      B2OF_LAUNCH_CHECK();
+    } else {
+      dim3 g1(cdiv(L.w, 128), H, frames);
+      {
+        ProfScope ps(PT_FB_LEVEL_H, st, (double)frames * ((double)W * H + 4.0 * H * L.w));
+        fb_level_hpass<<<g1, 128, 0, st>>>(frames_dev, step, frame_stride, W, H, Tb, L.w, L.pitch, t_stride, L.taps,
+                                           L.ksz, L.sx0, L.sx1, L.fx);
+      }
+      B2OF_LAUNCH_CHECK();
+      dim3 g2(cdiv(L.w, 128), L.h, frames);
+      {
+        ProfScope ps(PT_FB_LEVEL_V, st, (double)frames * (4.0 * H * L.w + 4.0 * L.h * L.w));
+        fb_level_vpass<<<g2, 128, 0, st>>>(Tb, H, L.pitch, t_stride, Ib, L.w, L.h, i_stride, L.taps, L.ksz, L.sy0,
+                                           L.sy1, L.fy);
+      }
+      B2OF_LAUNCH_CHECK();
     }
-    B2OF_LAUNCH_CHECK();
-    dim3 g2(cdiv(L.w, 128), L.h, frames);
-    {
-      ProfScope ps(PT_FB_LEVEL_V, st, (double)frames * (4.0 * H * L.w + 4.0 * L.h * L.w));
-      fb_level_vpass<<<g2, 128, 0, st>>>(Tb, H, L.pitch, t_stride, Ib, L.w, L.h, i_stride, L.taps, L.ksz, L.sy0,
-                                         L.sy1, L.fy);
-    }
-    B2OF_LAUNCH_CHECK();
     int n = pl->p.poly_n;
     size_t smem = ((size_t)(PE_TH + 2 * n) * (PE_TW + 2 * n) + 3 * (size_t)PE_TH * (PE_TW + 2 * n)) * sizeof(float);
     dim3 g3(cdiv(L.w, PE_TW), cdiv(L.h, PE_TH), frames);
@@ -667,9 +824,12 @@ static int fb_frames(const FbPlan* pl, const FbWorkspace& ws, const uint8_t* fra
 
 static std::once_flag g_attr_once;
 static void set_func_attrs() {
-  cudaFuncSetAttribute(fb_iter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(fb_iter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(fb_polyexp, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  const int big = 227 * 1024;
+  cudaFuncSetAttribute(fb_iter<IT_T_FAST, 7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(fb_iter<0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(fb_iter<0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(fb_polyexp, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(fb_level_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 }
 
 // iterations for `pairs` pairs whose frames sit in workspace slots (pair p -> slots p*fstep, p*fstep+1)
@@ -678,9 +838,17 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
   const b2of_farneback_params& p = pl->p;
   const int m = p.winsize / 2;
   const bool gauss = (p.flags & B2OF_OPTFLOW_FARNEBACK_GAUSSIAN) != 0;
-  const int E = IT_T + 2 * m;
-  size_t smem = ((size_t)5 * E * (E | 1) + (size_t)5 * E * (IT_T + 1)) * sizeof(float);
-  if (smem > 227 * 1024) return fail(B2OF_E_UNSUPPORTED, "winsize %d needs %zu B of shared memory", p.winsize, smem);
+  // tile: the specialised kernel for the reference's window, else the largest tile whose halo fits one SM
+  const bool fast = !gauss && m == 7;
+  int tile = IT_T_FAST;
+  if (!fast) {
+    tile = 64;
+    while (tile > 16 && (size_t)5 * (tile + 2 * m) * ((tile + 2 * m) | 1) * sizeof(float) > 200 * 1024) tile -= 8;
+  }
+  const int E = tile + 2 * m;
+  size_t smem = (size_t)5 * E * (E | 1) * sizeof(float);
+  if (smem > 227 * 1024 || E > IT_THREADS / 2)
+    return fail(B2OF_E_UNSUPPORTED, "winsize %d needs %zu B of shared memory", p.winsize, smem);
   size_t lvl_off = 0;
   const float2* coarse = nullptr;
   int cpitch = 0, cw = 0, ch = 0;
@@ -698,6 +866,7 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
     a.pitch = L.pitch; a.w = L.w; a.h = L.h;
     a.pair_frame_step = fstep;
     a.m = m;
+    a.tile = tile;
     a.inv_area = (float)(1.0 / ((double)p.winsize * p.winsize));
     a.gtaps = gauss ? pl->gauss_taps : nullptr;
     a.ux0 = L.ux0; a.ux1 = L.ux1; a.uy0 = L.uy0; a.uy1 = L.uy1; a.ufx = L.ufx; a.ufy = L.ufy;
@@ -705,7 +874,7 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
     const float2* cur = nullptr;  // flow at this level after the previous iteration
     int cur_pitch = 0;
     size_t cur_stride = 0;
-    dim3 grid(cdiv(L.w, IT_T), cdiv(L.h, IT_T), pairs);
+    dim3 grid(cdiv(L.w, tile), cdiv(L.h, tile), pairs);
     int iters = p.iterations;
     if (iters == 0) {
       // cv2 with iterations == 0 returns the (upsampled) initial flow of the finest level untouched;
@@ -738,8 +907,9 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
         double px = (double)L.w * L.h;
         double bytes = pairs * (48.0 * px + (a.mode == 1 ? 8.0 * px : a.mode == 2 ? 8.0 * cw * ch : 0.0));
         ProfScope ps(last_level ? PT_FB_ITER_FINEST : PT_FB_ITER_COARSE, st, bytes);
-        if (gauss) fb_iter<true><<<grid, IT_THREADS, smem, st>>>(a);
-        else fb_iter<false><<<grid, IT_THREADS, smem, st>>>(a);
+        if (fast) fb_iter<IT_T_FAST, 7, false><<<grid, IT_THREADS, smem, st>>>(a);
+        else if (gauss) fb_iter<0, 0, true><<<grid, IT_THREADS, smem, st>>>(a);
+        else fb_iter<0, 0, false><<<grid, IT_THREADS, smem, st>>>(a);
       }
       B2OF_LAUNCH_CHECK();
       cur = dst; cur_pitch = dpitch; cur_stride = dstride;
