@@ -40,6 +40,10 @@ struct FbLevel {
   // fused level-image kernel: output tile and the largest source region any tile needs (0 = use two-pass path)
   int f_tw, f_th, f_rw, f_rh, f_rw_pad;
   size_t f_smem;
+  // regular (exact 1/S) form: K combined taps, or r_K == 0
+  int r_K, r_S, r_c0, r_tw, r_th, r_rwp, r_hts;
+  size_t r_smem;
+  float r_c[24];
 };
 
 struct FbPlan {
@@ -204,6 +208,44 @@ static int build_plan(int rows, int cols, const b2of_farneback_params& p, FbPlan
     std::vector<float> tf;
     linear_tables(L.h, rows, t0, t1, tf);
     offs[i].sy0 = put(t0.data(), t0.size() * 4); offs[i].sy1 = put(t1.data(), t1.size() * 4); offs[i].fy = put(tf.data(), tf.size() * 4);
+    {
+      // regular form: sx0 = S*x + off, sx1 = sx0 + (f != 0), f constant -- in both axes with the same S, off, f
+      L.r_K = 0;
+      std::vector<float> taps_h;
+      gaussian_kernel(L.ksz, L.sigma, taps_h);
+      auto regular = [&](const std::vector<int>& a0, const std::vector<int>& a1, const std::vector<float>& ff, int n,
+                         int src_n, int& S, int& off, float& fr) {
+        if (n < 2) return false;
+        S = a0[1] - a0[0]; off = a0[0]; fr = ff[0];
+        if (S < 1) return false;
+        for (int q = 0; q < n; ++q) {
+          if (a0[q] != S * q + off || ff[q] != fr) return false;
+          if (fr != 0.f && (a1[q] != a0[q] + 1 || a1[q] > src_n - 1)) return false;
+        }
+        return true;
+      };
+      int Sx, Sy, ox, oy; float fxr, fyr;
+      if (regular(s0, s1, f, L.w, cols, Sx, ox, fxr) && regular(t0, t1, tf, L.h, rows, Sy, oy, fyr) && Sx == Sy &&
+          ox == oy && fxr == fyr) {
+        int K = L.ksz + (fxr != 0.f ? 1 : 0);
+        if (K == 3 || K == 10 || K == 20) {
+          for (int j = 0; j < K; ++j) {
+            float a = j < L.ksz ? taps_h[j] * (1.f - fxr) : 0.f;
+            float b = (j >= 1 && fxr != 0.f) ? taps_h[j - 1] * fxr : 0.f;
+            L.r_c[j] = a + b;
+          }
+          L.r_K = K; L.r_S = Sx; L.r_c0 = ox - L.ksz / 2;
+          L.r_tw = 64; L.r_th = Sx >= 8 ? 8 : 16;
+          int RW = Sx * (L.r_tw - 1) + K + 7, RH = Sx * (L.r_th - 1) + K;
+          int w4 = (RW + 3) / 4;
+          if (w4 % 2 == 0) ++w4;
+          L.r_rwp = 4 * w4;
+          L.r_hts = RH | 1;
+          L.r_smem = align_up((size_t)RH * L.r_rwp, 16) + (size_t)L.r_tw * L.r_hts * sizeof(float);
+          if (L.r_smem > 110 * 1024) L.r_K = 0;
+        }
+      }
+    }
     {
       // pick the largest output tile whose source region fits in ~100 KB of shared memory (2 CTAs/SM)
       const int cand[4][2] = {{64, 16}, {32, 16}, {32, 8}, {16, 8}};
@@ -407,6 +449,75 @@ __global__ void __launch_bounds__(256) fb_level_fused(LevelFusedArgs a) {
       vb = fmaf(kt, s_h[(ib + k) * a.tw + x], vb);
     }
     ob[(size_t)(y0 + y) * a.pitch + x0 + x] = va * (1.f - f) + vb * f;
+  }
+}
+
+
+// ----------------------------------------------------------------------------------------------
+// K3 (regular form): exact 1/S down-scales (the reference's pyr_scale = 0.5 gives S = 1, 2, 4, 8).  There the
+// resample taps are the same for every output pixel (sx0 = S*x + off, sx1 = sx0 + 1, f constant), so blur and
+// linear resample collapse into ONE K-tap filter per axis (K = ksz, or ksz + 1 when f != 0) whose taps sit in
+// the constant bank.  Source region as u8 in shared memory (word loads), horizontal pass with lanes along rows
+// into a transposed float buffer, vertical pass with lanes along x: bank-conflict-free for every S.
+// ----------------------------------------------------------------------------------------------
+struct LevelRegArgs {
+  const uint8_t* frames; size_t step, frame_stride; int W, H;
+  float* I; int wk, hk, pitch; size_t i_frame_stride;
+  int S, c0;           // first source column/row of output 0 is c0 (= sx0[0] - ksz/2); output x starts at S*x + c0
+  int tw, th;
+  int rwp, hts;        // smem pitches: u8 region pitch (4*odd), transposed float pitch (odd)
+  float c[24];         // combined taps
+};
+
+template <int K>
+__global__ void __launch_bounds__(256) fb_level_regular(LevelRegArgs a) {
+  extern __shared__ __align__(16) unsigned char lsm[];
+  const int S = a.S;
+  const int x0 = blockIdx.x * a.tw, y0 = blockIdx.y * a.th;
+  const int tw = min(a.tw, a.wk - x0), th = min(a.th, a.hk - y0);
+  const int RW = S * (tw - 1) + K, RH = S * (th - 1) + K;
+  const int gx0 = S * x0 + a.c0, gy0 = S * y0 + a.c0;
+  const int lpad = gx0 & 3;                     // region starts at the word boundary below gx0
+  const int nwords = (lpad + RW + 3) >> 2;
+  uint8_t* s_src = lsm;                         // [RH][rwp]
+  float* s_hT = (float*)(lsm + (((size_t)(S * (a.th - 1) + K) * a.rwp + 15) & ~(size_t)15));  // [tw][hts]
+  const uint8_t* fb = a.frames + blockIdx.z * a.frame_stride;
+  const int t = threadIdx.x;
+  const bool interior = gx0 - lpad >= 0 && gx0 - lpad + 4 * nwords <= a.W && gy0 >= 0 && gy0 + RH <= a.H &&
+                        ((a.step | (size_t)fb) & 3) == 0;
+  if (interior) {
+    for (int i = t; i < RH * nwords; i += 256) {
+      int rr = i / nwords, wc = i - rr * nwords;
+      uint32_t v = __ldg((const uint32_t*)(fb + (size_t)(gy0 + rr) * a.step + (gx0 - lpad)) + wc);
+      *((uint32_t*)(s_src + rr * a.rwp) + wc) = v;
+    }
+  } else {
+    const int nb = lpad + RW;
+    for (int i = t; i < RH * nb; i += 256) {
+      int rr = i / nb, cc = i - rr * nb;
+      int gy = reflect101(gy0 + rr, a.H), gx = reflect101(gx0 - lpad + cc, a.W);
+      s_src[rr * a.rwp + cc] = fb[(size_t)gy * a.step + gx];
+    }
+  }
+  __syncthreads();
+  // horizontal: item = (x, rr), rr fastest over lanes
+  for (int i = t; i < tw * RH; i += 256) {
+    int x = i / RH, rr = i - x * RH;
+    const uint8_t* p = s_src + rr * a.rwp + lpad + S * x;
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) v = fmaf(a.c[j], (float)p[j], v);
+    s_hT[x * a.hts + rr] = v;
+  }
+  __syncthreads();
+  float* ob = a.I + blockIdx.z * a.i_frame_stride;
+  for (int i = t; i < th * tw; i += 256) {
+    int y = i / tw, x = i - y * tw;
+    const float* p = s_hT + x * a.hts + S * y;
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) v = fmaf(a.c[j], p[j], v);
+    ob[(size_t)(y0 + y) * a.pitch + x0 + x] = v;
   }
 }
 
@@ -779,7 +890,21 @@ static int fb_frames(const FbPlan* pl, const FbWorkspace& ws, const uint8_t* fra
     float* Ib = ws.I + (size_t)total_slots * lvl_off + (size_t)slot0 * plane;
     float* Rb = ws.R + (size_t)total_slots * 5 * lvl_off + (size_t)slot0 * 5 * plane;
     size_t t_stride = (size_t)H * pitch0 * slot_step, i_stride = plane * slot_step, r_stride = 5 * plane * slot_step;
-    if (L.f_tw) {
+    if (L.r_K) {
+      LevelRegArgs ra{};
+      ra.frames = frames_dev; ra.step = step; ra.frame_stride = frame_stride; ra.W = W; ra.H = H;
+      ra.I = Ib; ra.wk = L.w; ra.hk = L.h; ra.pitch = L.pitch; ra.i_frame_stride = i_stride;
+      ra.S = L.r_S; ra.c0 = L.r_c0; ra.tw = L.r_tw; ra.th = L.r_th; ra.rwp = L.r_rwp; ra.hts = L.r_hts;
+      memcpy(ra.c, L.r_c, sizeof ra.c);
+      dim3 gr(cdiv(L.w, L.r_tw), cdiv(L.h, L.r_th), frames);
+      {
+        ProfScope ps(PT_FB_LEVEL_H, st, (double)frames * ((double)W * H + 4.0 * L.h * L.w));
+        if (L.r_K == 3) fb_level_regular<3><<<gr, 256, L.r_smem, st>>>(ra);
+        else if (L.r_K == 10) fb_level_regular<10><<<gr, 256, L.r_smem, st>>>(ra);
+        else fb_level_regular<20><<<gr, 256, L.r_smem, st>>>(ra);
+      }
+      B2OF_LAUNCH_CHECK();
+    } else if (L.f_tw) {
       LevelFusedArgs fa{};
       fa.frames = frames_dev; fa.step = step; fa.frame_stride = frame_stride; fa.W = W; fa.H = H;
       fa.I = Ib; fa.wk = L.w; fa.hk = L.h; fa.pitch = L.pitch; fa.i_frame_stride = i_stride;
@@ -830,6 +955,9 @@ static void set_func_attrs() {
   cudaFuncSetAttribute(fb_iter<0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   cudaFuncSetAttribute(fb_polyexp, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   cudaFuncSetAttribute(fb_level_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(fb_level_regular<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(fb_level_regular<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(fb_level_regular<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 }
 
 // iterations for `pairs` pairs whose frames sit in workspace slots (pair p -> slots p*fstep, p*fstep+1)
