@@ -41,8 +41,7 @@ struct FbLevel {
   int f_tw, f_th, f_rw, f_rh, f_rw_pad;
   size_t f_smem;
   // regular (exact 1/S) form: K combined taps, or r_K == 0
-  int r_K, r_S, r_c0, r_tw, r_th, r_rwp, r_hts;
-  size_t r_smem;
+  int r_K, r_S, r_c0;
   float r_c[24];
 };
 
@@ -147,6 +146,11 @@ static void poly_constants(int n, double sigma, PolyConst& pc) {
   pc.ig55 = (float)inv[5][5];
 }
 
+// (K, S) pairs with a compiled regular level-image kernel: the reference's four levels
+static bool level_regular_supported(int K, int S) {
+  return (K == 3 && S == 1) || (K == 4 && S == 2) || (K == 10 && S == 4) || (K == 20 && S == 8);
+}
+
 struct PlanKey {
   int dev, rows, cols, levels, winsize, poly_n, flags;
   double pyr_scale, poly_sigma;
@@ -228,21 +232,14 @@ static int build_plan(int rows, int cols, const b2of_farneback_params& p, FbPlan
       if (regular(s0, s1, f, L.w, cols, Sx, ox, fxr) && regular(t0, t1, tf, L.h, rows, Sy, oy, fyr) && Sx == Sy &&
           ox == oy && fxr == fyr) {
         int K = L.ksz + (fxr != 0.f ? 1 : 0);
-        if (K == 3 || K == 10 || K == 20) {
+        // source overshoot at the borders must stay below one reflection (reflect_once)
+        if (level_regular_supported(K, Sx) && K < std::min(rows, cols)) {
           for (int j = 0; j < K; ++j) {
             float a = j < L.ksz ? taps_h[j] * (1.f - fxr) : 0.f;
             float b = (j >= 1 && fxr != 0.f) ? taps_h[j - 1] * fxr : 0.f;
             L.r_c[j] = a + b;
           }
           L.r_K = K; L.r_S = Sx; L.r_c0 = ox - L.ksz / 2;
-          L.r_tw = 64; L.r_th = Sx >= 8 ? 8 : 16;
-          int RW = Sx * (L.r_tw - 1) + K + 7, RH = Sx * (L.r_th - 1) + K;
-          int w4 = (RW + 3) / 4;
-          if (w4 % 2 == 0) ++w4;
-          L.r_rwp = 4 * w4;
-          L.r_hts = RH | 1;
-          L.r_smem = align_up((size_t)RH * L.r_rwp, 16) + (size_t)L.r_tw * L.r_hts * sizeof(float);
-          if (L.r_smem > 110 * 1024) L.r_K = 0;
         }
       }
     }
@@ -463,63 +460,87 @@ __global__ void __launch_bounds__(256) fb_level_fused(LevelFusedArgs a) {
 struct LevelRegArgs {
   const uint8_t* frames; size_t step, frame_stride; int W, H;
   float* I; int wk, hk, pitch; size_t i_frame_stride;
-  int S, c0;           // first source column/row of output 0 is c0 (= sx0[0] - ksz/2); output x starts at S*x + c0
-  int tw, th;
-  int rwp, hts;        // smem pitches: u8 region pitch (4*odd), transposed float pitch (odd)
+  int c0;              // first source column/row of output 0 (= sx0[0] - ksz/2); output x starts at S*x + c0
   float c[24];         // combined taps
 };
 
-template <int K>
+constexpr int LR_TW = 64;
+__host__ __device__ constexpr int lr_th(int S) { return S >= 8 ? 8 : 16; }
+__host__ __device__ constexpr int lr_rwp(int K, int S) { return ((S * (LR_TW - 1) + K + 3 + 3) / 4 + 1) * 4; }
+__host__ __device__ constexpr int lr_rh(int K, int S) { return S * (lr_th(S) - 1) + K; }
+__host__ __device__ constexpr size_t lr_smem(int K, int S) {
+  return (size_t)lr_rh(K, S) * lr_rwp(K, S) + (size_t)lr_rh(K, S) * LR_TW * sizeof(float);
+}
+
+__device__ __forceinline__ int reflect_once(int i, int n) {  // REFLECT_101 for |overshoot| < n
+  i = i < 0 ? -i : i;
+  return i >= n ? 2 * n - 2 - i : i;
+}
+
+template <int K, int S>
 __global__ void __launch_bounds__(256) fb_level_regular(LevelRegArgs a) {
+  constexpr int TH = lr_th(S), RWP = lr_rwp(K, S), RH = lr_rh(K, S), RW = S * (LR_TW - 1) + K;
   extern __shared__ __align__(16) unsigned char lsm[];
-  const int S = a.S;
-  const int x0 = blockIdx.x * a.tw, y0 = blockIdx.y * a.th;
-  const int tw = min(a.tw, a.wk - x0), th = min(a.th, a.hk - y0);
-  const int RW = S * (tw - 1) + K, RH = S * (th - 1) + K;
+  uint8_t* s_src = lsm;                               // [RH][RWP] u8
+  float* s_h = (float*)(lsm + (size_t)RH * RWP);      // [RH][LR_TW]  (RH*RWP is a multiple of 4)
+  const int x0 = blockIdx.x * LR_TW, y0 = blockIdx.y * TH;
   const int gx0 = S * x0 + a.c0, gy0 = S * y0 + a.c0;
-  const int lpad = gx0 & 3;                     // region starts at the word boundary below gx0
-  const int nwords = (lpad + RW + 3) >> 2;
-  uint8_t* s_src = lsm;                         // [RH][rwp]
-  float* s_hT = (float*)(lsm + (((size_t)(S * (a.th - 1) + K) * a.rwp + 15) & ~(size_t)15));  // [tw][hts]
+  const int lpad = gx0 & 3;                           // region starts at the word boundary below gx0
+  const int gxa = gx0 - lpad;
+  constexpr int NW = (3 + RW + 3) / 4;                // words per region row (upper bound)
   const uint8_t* fb = a.frames + blockIdx.z * a.frame_stride;
-  const int t = threadIdx.x;
-  const bool interior = gx0 - lpad >= 0 && gx0 - lpad + 4 * nwords <= a.W && gy0 >= 0 && gy0 + RH <= a.H &&
-                        ((a.step | (size_t)fb) & 3) == 0;
-  if (interior) {
-    for (int i = t; i < RH * nwords; i += 256) {
-      int rr = i / nwords, wc = i - rr * nwords;
-      uint32_t v = __ldg((const uint32_t*)(fb + (size_t)(gy0 + rr) * a.step + (gx0 - lpad)) + wc);
-      *((uint32_t*)(s_src + rr * a.rwp) + wc) = v;
-    }
-  } else {
-    const int nb = lpad + RW;
-    for (int i = t; i < RH * nb; i += 256) {
-      int rr = i / nb, cc = i - rr * nb;
-      int gy = reflect101(gy0 + rr, a.H), gx = reflect101(gx0 - lpad + cc, a.W);
-      s_src[rr * a.rwp + cc] = fb[(size_t)gy * a.step + gx];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const bool cols_in = gxa >= 0 && gxa + 4 * NW <= a.W && ((a.step | (size_t)fb) & 3) == 0;
+  // only what valid outputs consume is loaded (keeps the border overshoot below one reflection)
+  const int rows_needed = S * (min(TH, a.hk - y0) - 1) + K;
+  const int cols_needed = lpad + S * (min(LR_TW, a.wk - x0) - 1) + K;
+  for (int rr = warp; rr < rows_needed; rr += 8) {
+    const uint8_t* row = fb + (size_t)reflect_once(gy0 + rr, a.H) * a.step;
+    if (cols_in) {
+      for (int wc = lane; wc < NW; wc += 32)
+        *((uint32_t*)(s_src + rr * RWP) + wc) = __ldg((const uint32_t*)(row + gxa) + wc);
+    } else {
+      for (int cc = lane; cc < cols_needed; cc += 32) s_src[rr * RWP + cc] = row[reflect_once(gxa + cc, a.W)];
     }
   }
   __syncthreads();
-  // horizontal: item = (x, rr), rr fastest over lanes
-  for (int i = t; i < tw * RH; i += 256) {
-    int x = i / RH, rr = i - x * RH;
-    const uint8_t* p = s_src + rr * a.rwp + lpad + S * x;
-    float v = 0.f;
+  const int x = t & (LR_TW - 1), q = t >> 6;          // 64 columns x 4 row phases
+  {
+    const uint8_t* p = s_src + lpad + S * x;
+    for (int rr = q; rr < rows_needed; rr += 4) {
+      const uint8_t* pr = p + rr * RWP;
+      float v = 0.f;
 #pragma unroll
-    for (int j = 0; j < K; ++j) v = fmaf(a.c[j], (float)p[j], v);
-    s_hT[x * a.hts + rr] = v;
+      for (int j = 0; j < K; ++j) v = fmaf(a.c[j], (float)pr[j], v);
+      s_h[rr * LR_TW + x] = v;
+    }
   }
   __syncthreads();
-  float* ob = a.I + blockIdx.z * a.i_frame_stride;
-  for (int i = t; i < th * tw; i += 256) {
-    int y = i / tw, x = i - y * tw;
-    const float* p = s_hT + x * a.hts + S * y;
-    float v = 0.f;
+  if (x0 + x < a.wk) {
+    float* ob = a.I + blockIdx.z * a.i_frame_stride + x0 + x;
 #pragma unroll
-    for (int j = 0; j < K; ++j) v = fmaf(a.c[j], p[j], v);
-    ob[(size_t)(y0 + y) * a.pitch + x0 + x] = v;
+    for (int y = q; y < TH; y += 4) {
+      if (y0 + y >= a.hk) break;
+      const float* p = s_h + (S * y) * LR_TW + x;
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < K; ++j) v = fmaf(a.c[j], p[j * LR_TW], v);
+      ob[(size_t)(y0 + y) * a.pitch] = v;
+    }
   }
 }
+
+template <int K, int S>
+static void launch_level_regular(const LevelRegArgs& ra, int frames, cudaStream_t st) {
+  static bool attr_done = false;  // benign race: idempotent
+  if (!attr_done) {
+    cudaFuncSetAttribute(fb_level_regular<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lr_smem(K, S));
+    attr_done = true;
+  }
+  dim3 g(cdiv(ra.wk, LR_TW), cdiv(ra.hk, lr_th(S)), frames);
+  fb_level_regular<K, S><<<g, 256, lr_smem(K, S), st>>>(ra);
+}
+
 
 // ----------------------------------------------------------------------------------------------
 // K4: polynomial expansion. 64x32 output tile per CTA; the (32+2n)x(64+2n) input tile and the three
@@ -589,6 +610,101 @@ __global__ void __launch_bounds__(256) fb_polyexp(const float* __restrict__ I, i
     size_t o = (size_t)gy * pitch + gx;
     ra4[o] = make_float4(b3 * pc.ig11, b2 * pc.ig11, b1 * pc.ig03 + b5 * pc.ig33, b1 * pc.ig03 + b4 * pc.ig33);
     rb1[o] = b6 * pc.ig55;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K4 (specialised, poly_n known at compile time): 64x32 output tile, 320 threads.
+//   phase 1: thread = (halo column, 8-row segment); 8+2N rows go global -> registers (all loads in flight), the
+//            three vertical filters come out of a register window, results to shared memory
+//   phase 2: thread = two adjacent x (8-byte LDS of the filtered rows), warps over rows; 32 B + 8 B stores per thread
+// ----------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(320) fb_polyexp_n(const float* __restrict__ I, int w, int h, int pitch,
+                                                     size_t i_frame_stride, float* __restrict__ R,
+                                                     size_t plane_stride, size_t r_frame_stride, PolyConst pc) {
+  constexpr int CW = PE_TW + 2 * N;        // halo columns (74 for N = 5)
+  constexpr int CP = (CW + 7) / 8 * 8;     // phase-1 thread columns (80), also the smem pitch (even)
+  constexpr int SEG = 8, NSEG = PE_TH / SEG;
+  static_assert(CP * NSEG <= 320, "phase 1 does not fit the block");
+  __shared__ __align__(16) float s_r[3][PE_TH][CP];
+  const int x0 = blockIdx.x * PE_TW, y0 = blockIdx.y * PE_TH;
+  const float* ib = I + blockIdx.z * i_frame_stride;
+  const int t = threadIdx.x;
+  {
+    const int seg = t / CP, c = t - seg * CP;
+    if (seg < NSEG && c < CW) {
+      const int gx = clampi(x0 + c - N, 0, w - 1);
+      const int yb = y0 + seg * SEG - N;
+      float v[SEG + 2 * N];
+#pragma unroll
+      for (int j = 0; j < SEG + 2 * N; ++j) v[j] = ib[(size_t)clampi(yb + j, 0, h - 1) * pitch + gx];
+#pragma unroll
+      for (int j = 0; j < SEG; ++j) {
+        float r0 = v[j + N] * pc.g[0], r1 = 0.f, r2 = 0.f;
+#pragma unroll
+        for (int k = 1; k <= N; ++k) {
+          float a = v[j + N - k], b = v[j + N + k];
+          float sum = a + b;
+          r0 = fmaf(pc.g[k], sum, r0);
+          r1 = fmaf(pc.xg[k], b - a, r1);
+          r2 = fmaf(pc.xxg[k], sum, r2);
+        }
+        const int r = seg * SEG + j;
+        s_r[0][r][c] = r0; s_r[1][r][c] = r1; s_r[2][r][c] = r2;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int warp = t >> 5, lane = t & 31;
+    const int xl = 2 * lane;                 // local x of the first of two outputs
+    const int gx = x0 + xl;
+    float* rb = R + blockIdx.z * r_frame_stride;
+    float4* ra4 = (float4*)rb;
+    float* rb1 = rb + 4 * plane_stride;
+    for (int r = warp; r < PE_TH; r += 10) {
+      const int gy = y0 + r;
+      if (gy >= h || gx >= w) continue;
+      float p0[2 * N + 2], p1[2 * N + 2], p2[2 * N + 2];
+#pragma unroll
+      for (int j = 0; j < N + 1; ++j) {
+        float2 a = *(const float2*)&s_r[0][r][xl + 2 * j];
+        float2 b = *(const float2*)&s_r[1][r][xl + 2 * j];
+        float2 c = *(const float2*)&s_r[2][r][xl + 2 * j];
+        p0[2 * j] = a.x; p0[2 * j + 1] = a.y;
+        p1[2 * j] = b.x; p1[2 * j + 1] = b.y;
+        p2[2 * j] = c.x; p2[2 * j + 1] = c.y;
+      }
+      float4 oa[2];
+      float ob[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ctr = e + N;
+        float b1 = p0[ctr] * pc.g[0], b3 = p1[ctr] * pc.g[0], b5 = p2[ctr] * pc.g[0];
+        float b2 = 0.f, b4 = 0.f, b6 = 0.f;
+#pragma unroll
+        for (int k = 1; k <= N; ++k) {
+          float tg = p0[ctr + k] + p0[ctr - k];
+          b1 = fmaf(tg, pc.g[k], b1);
+          b4 = fmaf(tg, pc.xxg[k], b4);
+          b2 = fmaf(p0[ctr + k] - p0[ctr - k], pc.xg[k], b2);
+          b3 = fmaf(p1[ctr + k] + p1[ctr - k], pc.g[k], b3);
+          b6 = fmaf(p1[ctr + k] - p1[ctr - k], pc.xg[k], b6);
+          b5 = fmaf(p2[ctr + k] + p2[ctr - k], pc.g[k], b5);
+        }
+        oa[e] = make_float4(b3 * pc.ig11, b2 * pc.ig11, b1 * pc.ig03 + b5 * pc.ig33, b1 * pc.ig03 + b4 * pc.ig33);
+        ob[e] = b6 * pc.ig55;
+      }
+      size_t o = (size_t)gy * pitch + gx;
+      ra4[o] = oa[0];
+      if (gx + 1 < w) {
+        ra4[o + 1] = oa[1];
+        *(float2*)(rb1 + o) = make_float2(ob[0], ob[1]);   // o is even: pitch % 32 == 0, gx even
+      } else {
+        rb1[o] = ob[0];
+      }
+    }
   }
 }
 
@@ -894,14 +1010,14 @@ static int fb_frames(const FbPlan* pl, const FbWorkspace& ws, const uint8_t* fra
       LevelRegArgs ra{};
       ra.frames = frames_dev; ra.step = step; ra.frame_stride = frame_stride; ra.W = W; ra.H = H;
       ra.I = Ib; ra.wk = L.w; ra.hk = L.h; ra.pitch = L.pitch; ra.i_frame_stride = i_stride;
-      ra.S = L.r_S; ra.c0 = L.r_c0; ra.tw = L.r_tw; ra.th = L.r_th; ra.rwp = L.r_rwp; ra.hts = L.r_hts;
+      ra.c0 = L.r_c0;
       memcpy(ra.c, L.r_c, sizeof ra.c);
-      dim3 gr(cdiv(L.w, L.r_tw), cdiv(L.h, L.r_th), frames);
       {
         ProfScope ps(PT_FB_LEVEL_H, st, (double)frames * ((double)W * H + 4.0 * L.h * L.w));
-        if (L.r_K == 3) fb_level_regular<3><<<gr, 256, L.r_smem, st>>>(ra);
-        else if (L.r_K == 10) fb_level_regular<10><<<gr, 256, L.r_smem, st>>>(ra);
-        else fb_level_regular<20><<<gr, 256, L.r_smem, st>>>(ra);
+        if (L.r_K == 3) launch_level_regular<3, 1>(ra, frames, st);
+        else if (L.r_K == 4) launch_level_regular<4, 2>(ra, frames, st);
+        else if (L.r_K == 10) launch_level_regular<10, 4>(ra, frames, st);
+        else launch_level_regular<20, 8>(ra, frames, st);
       }
       B2OF_LAUNCH_CHECK();
     } else if (L.f_tw) {
@@ -939,7 +1055,9 @@ static int fb_frames(const FbPlan* pl, const FbWorkspace& ws, const uint8_t* fra
     dim3 g3(cdiv(L.w, PE_TW), cdiv(L.h, PE_TH), frames);
     {
       ProfScope ps(PT_FB_POLYEXP, st, (double)frames * 24.0 * L.w * L.h);
-      fb_polyexp<<<g3, 256, smem, st>>>(Ib, L.w, L.h, L.pitch, i_stride, Rb, plane, r_stride, pl->pc, n);
+      if (n == 5) fb_polyexp_n<5><<<g3, 320, 0, st>>>(Ib, L.w, L.h, L.pitch, i_stride, Rb, plane, r_stride, pl->pc);
+      else if (n == 7) fb_polyexp_n<7><<<g3, 320, 0, st>>>(Ib, L.w, L.h, L.pitch, i_stride, Rb, plane, r_stride, pl->pc);
+      else fb_polyexp<<<g3, 256, smem, st>>>(Ib, L.w, L.h, L.pitch, i_stride, Rb, plane, r_stride, pl->pc, n);
     }
     B2OF_LAUNCH_CHECK();
     lvl_off += plane;
@@ -955,9 +1073,6 @@ static void set_func_attrs() {
   cudaFuncSetAttribute(fb_iter<0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   cudaFuncSetAttribute(fb_polyexp, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   cudaFuncSetAttribute(fb_level_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  cudaFuncSetAttribute(fb_level_regular<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  cudaFuncSetAttribute(fb_level_regular<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  cudaFuncSetAttribute(fb_level_regular<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 }
 
 // iterations for `pairs` pairs whose frames sit in workspace slots (pair p -> slots p*fstep, p*fstep+1)
