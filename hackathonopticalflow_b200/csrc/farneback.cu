@@ -762,18 +762,6 @@ __device__ __forceinline__ float4 fma4s(float4 v, float s, float4 acc) {  // acc
   return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
-__device__ __forceinline__ float2 fetch_flow(const IterArgs& a, const float2* fin, int x, int y) {
-  if (a.mode == 0) return make_float2(0.f, 0.f);
-  if (a.mode == 1) return fin[(size_t)y * a.in_pitch + x];
-  int xa = a.ux0[x], xb = a.ux1[x], ya = a.uy0[y], yb = a.uy1[y];
-  float fx = a.ufx[x], fy = a.ufy[y];
-  float2 p00 = fin[(size_t)ya * a.in_pitch + xa], p01 = fin[(size_t)ya * a.in_pitch + xb];
-  float2 p10 = fin[(size_t)yb * a.in_pitch + xa], p11 = fin[(size_t)yb * a.in_pitch + xb];
-  float tx0 = p00.x * (1.f - fx) + p01.x * fx, ty0 = p00.y * (1.f - fx) + p01.y * fx;
-  float tx1 = p10.x * (1.f - fx) + p11.x * fx, ty1 = p10.y * (1.f - fx) + p11.y * fx;
-  return make_float2((tx0 * (1.f - fy) + tx1 * fy) * a.up_mult, (ty0 * (1.f - fy) + ty1 * fy) * a.up_mult);
-}
-
 __device__ __forceinline__ float border_w(int i, int n) {
   // product of the 5-px attenuation table from both ends (UpdateMatrices)
   const float tab[5] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f};
@@ -788,13 +776,30 @@ __device__ __forceinline__ float2 solve2x2(float g11, float g12, float g22, floa
   return make_float2((g11 * h2 - g12 * h1) * idet, (g22 * h1 - g12 * h2) * idet);
 }
 
-template <int CT, int CM, bool GAUSS>
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int MODE>
+__device__ __forceinline__ float2 fetch_flow_m(const IterArgs& a, const float2* fin, int x, int y, int xa, int xb,
+                                               float ufx) {
+  if (MODE == 0) return make_float2(0.f, 0.f);
+  if (MODE == 1) return fin[y * a.in_pitch + x];
+  int ya = a.uy0[y], yb = a.uy1[y];
+  float fy = a.ufy[y];
+  float2 p00 = fin[ya * a.in_pitch + xa], p01 = fin[ya * a.in_pitch + xb];
+  float2 p10 = fin[yb * a.in_pitch + xa], p11 = fin[yb * a.in_pitch + xb];
+  float tx0 = p00.x * (1.f - ufx) + p01.x * ufx, ty0 = p00.y * (1.f - ufx) + p01.y * ufx;
+  float tx1 = p10.x * (1.f - ufx) + p11.x * ufx, ty1 = p10.y * (1.f - ufx) + p11.y * ufx;
+  return make_float2((tx0 * (1.f - fy) + tx1 * fy) * a.up_mult, (ty0 * (1.f - fy) + ty1 * fy) * a.up_mult);
+}
+
+template <int CT, int CM, bool GAUSS, int MODE>
 __global__ void __launch_bounds__(IT_THREADS, CT ? 2 : 1) fb_iter(IterArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int T = CT ? CT : a.tile;
   const int m = CT ? CM : a.m;
   const int E = T + 2 * m;          // halo tile edge
   const int ES = E | 1;             // odd row stride (in elements): conflict-free row walks
+  const int HL = T >> 1;            // outputs [0,HL) are summed left->right, [HL,T) right->left (see step B)
   float4* sM4 = (float4*)smem;      // [E][ES]  (M0..M3)
   float* sM1 = smem + 4 * E * ES;   // [E][ES]  (M4)
   const int pair = blockIdx.z;
@@ -805,92 +810,184 @@ __global__ void __launch_bounds__(IT_THREADS, CT ? 2 : 1) fb_iter(IterArgs a) {
   const float* __restrict__ R0b = base0 + 4 * a.plane_stride;
   const float4* __restrict__ R1a = (const float4*)(base0 + a.r_frame_stride);
   const float* __restrict__ R1b = base0 + a.r_frame_stride + 4 * a.plane_stride;
-  const float2* fin = a.flow_in ? a.flow_in + (size_t)pair * a.flow_in_pair_stride : nullptr;
+  const float2* __restrict__ fin = MODE ? a.flow_in + (size_t)pair * a.flow_in_pair_stride : nullptr;
   const int t = threadIdx.x;
 
   // ---- step A: M on the halo tile (positions clamped to the image = BORDER_REPLICATE of M) ----
-#pragma unroll 2
-  for (int i = t; i < E * E; i += IT_THREADS) {
-    int iy = i / E, ix = i - iy * E;
-    int x = clampi(x0 - m + ix, 0, w - 1), y = clampi(y0 - m + iy, 0, h - 1);
-    float2 d = fetch_flow(a, fin, x, y);
-    float fx = (float)x + d.x, fy = (float)y + d.y;
-    float flx = floorf(fx), fly = floorf(fy);
-    int x1 = (int)flx, y1 = (int)fly;
-    fx -= flx; fy -= fly;
-    int o = y * pitch + x;
-    float4 q = R0a[o];
-    float q4 = R0b[o];
-    float r2, r3, r4, r5, r6;
-    if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
-      float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-      int o1 = y1 * pitch + x1;
-      float4 p00 = R1a[o1], p01 = R1a[o1 + 1], p10 = R1a[o1 + pitch], p11 = R1a[o1 + pitch + 1];
-      float s00 = R1b[o1], s01 = R1b[o1 + 1], s10 = R1b[o1 + pitch], s11 = R1b[o1 + pitch + 1];
-      r2 = a00 * p00.x + a01 * p01.x + a10 * p10.x + a11 * p11.x;
-      r3 = a00 * p00.y + a01 * p01.y + a10 * p10.y + a11 * p11.y;
-      r4 = a00 * p00.z + a01 * p01.z + a10 * p10.z + a11 * p11.z;
-      r5 = a00 * p00.w + a01 * p01.w + a10 * p10.w + a11 * p11.w;
-      r6 = a00 * s00 + a01 * s01 + a10 * s10 + a11 * s11;
-      r4 = (q.z + r4) * 0.5f;
-      r5 = (q.w + r5) * 0.5f;
-      r6 = (q4 + r6) * 0.25f;
-    } else {
-      r2 = r3 = 0.f;
-      r4 = q.z; r5 = q.w; r6 = q4 * 0.5f;
+  // thread = one halo column and a run of RS consecutive rows.  Walking down a column, the bottom corners of
+  // one pixel's bilinear gather are the top corners of the next one whenever the integer part of the warp did
+  // not jump (almost always: the flow is smooth), so they are carried in registers and only the two new
+  // corners are loaded -- half the gather traffic through L1.  The flow vector and the R0 record of the NEXT
+  // row are fetched before the current gathers are consumed (software pipeline); gathers are branch-free
+  // (clamped address + select).
+  {
+    const int RP = IT_THREADS / E;            // row runs per tile (7 for E = 70)
+    const int RS = (E + RP - 1) / RP;         // rows per run (10)
+    const int ty = t / E, ix = t - ty * E;
+    if (ty < RP) {
+      const int x = clampi(x0 - m + ix, 0, w - 1);
+      const float xf = (float)x;
+      const bool xb_border = x < 5 || x >= w - 5;
+      const float bwx = border_w(x, w);
+      int uxa = 0, uxb = 0;
+      float ufx = 0.f;
+      if (MODE == 2) { uxa = a.ux0[x]; uxb = a.ux1[x]; ufx = a.ufx[x]; }
+      int iy = ty * RS;
+      const int iy_end = min(iy + RS, E);
+      // everything this thread will stream (flow, R0) is a first touch from HBM, and so is most of the R1
+      // neighbourhood: pull the whole column run into L2 now so the pipelined loads below see L2 latency
+      for (int r = iy; r < iy_end; ++r) {
+        const int yy = clampi(y0 - m + r, 0, h - 1);
+        const int o = yy * pitch + x;
+        if (MODE == 1) prefetch_l2(fin + yy * a.in_pitch + x);
+        prefetch_l2(R0a + o);
+        prefetch_l2(R0b + o);
+        prefetch_l2(R1a + o);
+        prefetch_l2(R1b + o);
+      }
+      int y_n = clampi(y0 - m + iy, 0, h - 1);
+      float2 d_n = fetch_flow_m<MODE>(a, fin, x, y_n, uxa, uxb, ufx);
+      float4 q_n = R0a[y_n * pitch + x];
+      float q4_n = R0b[y_n * pitch + x];
+      // carried bottom corners of the previous row and where they came from
+      float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+      float e0 = 0.f, e1 = 0.f;
+      int ox_prev = -1 << 30;                 // offset of the carried row (o1 + pitch of the previous pixel)
+      for (; iy < iy_end; ++iy) {
+        const float2 d = d_n;
+        const float4 q = q_n;
+        const float q4 = q4_n;
+        const int y = y_n;
+        float fx = xf + d.x, fy = (float)y + d.y;
+        float flx = floorf(fx), fly = floorf(fy);
+        int x1 = (int)flx, y1 = (int)fly;
+        fx -= flx; fy -= fly;
+        const bool inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
+        const int o1 = inside ? y1 * pitch + x1 : 0;
+        const float4* g4 = R1a + o1;
+        const float* g1 = R1b + o1;
+        float4 p00, p01;
+        float s00, s01;
+        if (o1 == ox_prev) {                  // top corners = carried bottom corners
+          p00 = c0; p01 = c1; s00 = e0; s01 = e1;
+        } else {
+          p00 = g4[0]; p01 = g4[1]; s00 = g1[0]; s01 = g1[1];
+        }
+        const float4 p10 = g4[pitch], p11 = g4[pitch + 1];
+        const float s10 = g1[pitch], s11 = g1[pitch + 1];
+        if (iy + 1 < iy_end) {                // prefetch the next row of this thread
+          y_n = clampi(y0 - m + iy + 1, 0, h - 1);
+          d_n = fetch_flow_m<MODE>(a, fin, x, y_n, uxa, uxb, ufx);
+          q_n = R0a[y_n * pitch + x];
+          q4_n = R0b[y_n * pitch + x];
+        }
+        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+        float r2 = a00 * p00.x + a01 * p01.x + a10 * p10.x + a11 * p11.x;
+        float r3 = a00 * p00.y + a01 * p01.y + a10 * p10.y + a11 * p11.y;
+        float r4 = a00 * p00.z + a01 * p01.z + a10 * p10.z + a11 * p11.z;
+        float r5 = a00 * p00.w + a01 * p01.w + a10 * p10.w + a11 * p11.w;
+        float r6 = a00 * s00 + a01 * s01 + a10 * s10 + a11 * s11;
+        c0 = p10; c1 = p11; e0 = s10; e1 = s11;
+        ox_prev = o1 + pitch;
+        r2 = inside ? r2 : 0.f;
+        r3 = inside ? r3 : 0.f;
+        r4 = inside ? (q.z + r4) * 0.5f : q.z;
+        r5 = inside ? (q.w + r5) * 0.5f : q.w;
+        r6 = inside ? (q4 + r6) * 0.25f : q4 * 0.5f;
+        r2 = (q.x - r2) * 0.5f;
+        r3 = (q.y - r3) * 0.5f;
+        r2 += r4 * d.y + r6 * d.x;
+        r3 += r6 * d.y + r5 * d.x;
+        if (xb_border || y < 5 || y >= h - 5) {
+          float s = bwx * border_w(y, h);
+          r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
+        }
+        const int so = iy * ES + ix;
+        sM4[so] = make_float4(r4 * r4 + r6 * r6, (r4 + r5) * r6, r5 * r5 + r6 * r6, r4 * r2 + r6 * r3);
+        sM1[so] = r6 * r2 + r5 * r3;
+      }
     }
-    r2 = (q.x - r2) * 0.5f;
-    r3 = (q.y - r3) * 0.5f;
-    r2 += r4 * d.y + r6 * d.x;
-    r3 += r6 * d.y + r5 * d.x;
-    if (x < 5 || x >= w - 5 || y < 5 || y >= h - 5) {
-      float s = border_w(x, w) * border_w(y, h);
-      r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
-    }
-    int so = iy * ES + ix;
-    sM4[so] = make_float4(r4 * r4 + r6 * r6, (r4 + r5) * r6, r5 * r5 + r6 * r6, r4 * r2 + r6 * r3);
-    sM1[so] = r6 * r2 + r5 * r3;
   }
   __syncthreads();
 
-  // ---- step B: horizontal window sums in place; thread = one row of the float4 plane or of the float plane ----
+  // ---- step B: horizontal window sums IN PLACE.  One thread owns half a row of one plane:
+  //   left half : outputs x in [0,HL)  computed left->right,  stored at position x        (reads positions >= x)
+  //   right half: outputs x in [HL,T)  computed right->left,  stored at position x + 2m   (reads positions <= x+2m)
+  // positions [HL, HL+2m) are written by neither, so the two halves never race.
   {
-    const int g1 = (E + 31) & ~31;   // float-plane rows start at the next warp boundary
-    if (t < E) {
-      float4* row = sM4 + t * ES;
-      if (GAUSS) {
-        for (int x = 0; x < T; ++x) {
-          float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-          s = fma4s(row[x + m], a.gtaps[0], s);
-          for (int k = 1; k <= m; ++k) s = fma4s(add4(row[x + m - k], row[x + m + k]), a.gtaps[k], s);
-          row[x] = s;
+    const int gs = (E + 31) & ~31;            // group stride: each group starts on a warp boundary
+    const int g = t / gs, r = t - g * gs;
+    if (g < 4 && r < E) {
+      const bool right = g & 1;
+      if (g < 2) {
+        float4* row = sM4 + r * ES;
+        if (GAUSS) {
+          if (!right) {
+            for (int x = 0; x < HL; ++x) {
+              float4 s = fma4s(row[x + m], a.gtaps[0], make_float4(0.f, 0.f, 0.f, 0.f));
+              for (int k = 1; k <= m; ++k) s = fma4s(add4(row[x + m - k], row[x + m + k]), a.gtaps[k], s);
+              row[x] = s;
+            }
+          } else {
+            for (int x = T - 1; x >= HL; --x) {
+              float4 s = fma4s(row[x + m], a.gtaps[0], make_float4(0.f, 0.f, 0.f, 0.f));
+              for (int k = 1; k <= m; ++k) s = fma4s(add4(row[x + m - k], row[x + m + k]), a.gtaps[k], s);
+              row[x + 2 * m] = s;
+            }
+          }
+        } else if (!right) {
+          float4 s = row[0];
+          for (int k = 1; k < 2 * m; ++k) s = add4(s, row[k]);
+          for (int x = 0; x < HL; ++x) {
+            s = add4(s, row[x + 2 * m]);
+            float4 old = row[x];
+            row[x] = s;
+            s = sub4(s, old);
+          }
+        } else {
+          float4 s = row[T];
+          for (int k = 1; k < 2 * m; ++k) s = add4(s, row[T + k]);
+          for (int x = T - 1; x >= HL; --x) {
+            s = add4(s, row[x]);
+            float4 old = row[x + 2 * m];
+            row[x + 2 * m] = s;
+            s = sub4(s, old);
+          }
         }
       } else {
-        float4 s = row[0];
-        for (int k = 1; k < 2 * m; ++k) s = add4(s, row[k]);
-        for (int x = 0; x < T; ++x) {
-          s = add4(s, row[x + 2 * m]);
-          float4 old = row[x];
-          row[x] = s;
-          s = sub4(s, old);
-        }
-      }
-    } else if (t >= g1 && t < g1 + E) {
-      float* row = sM1 + (t - g1) * ES;
-      if (GAUSS) {
-        for (int x = 0; x < T; ++x) {
-          float s = row[x + m] * a.gtaps[0];
-          for (int k = 1; k <= m; ++k) s = fmaf(row[x + m - k] + row[x + m + k], a.gtaps[k], s);
-          row[x] = s;
-        }
-      } else {
-        float s = row[0];
-        for (int k = 1; k < 2 * m; ++k) s += row[k];
-        for (int x = 0; x < T; ++x) {
-          s += row[x + 2 * m];
-          float old = row[x];
-          row[x] = s;
-          s -= old;
+        float* row = sM1 + r * ES;
+        if (GAUSS) {
+          if (!right) {
+            for (int x = 0; x < HL; ++x) {
+              float s = row[x + m] * a.gtaps[0];
+              for (int k = 1; k <= m; ++k) s = fmaf(row[x + m - k] + row[x + m + k], a.gtaps[k], s);
+              row[x] = s;
+            }
+          } else {
+            for (int x = T - 1; x >= HL; --x) {
+              float s = row[x + m] * a.gtaps[0];
+              for (int k = 1; k <= m; ++k) s = fmaf(row[x + m - k] + row[x + m + k], a.gtaps[k], s);
+              row[x + 2 * m] = s;
+            }
+          }
+        } else if (!right) {
+          float s = row[0];
+          for (int k = 1; k < 2 * m; ++k) s += row[k];
+          for (int x = 0; x < HL; ++x) {
+            s += row[x + 2 * m];
+            float old = row[x];
+            row[x] = s;
+            s -= old;
+          }
+        } else {
+          float s = row[T];
+          for (int k = 1; k < 2 * m; ++k) s += row[T + k];
+          for (int x = T - 1; x >= HL; --x) {
+            s += row[x];
+            float old = row[x + 2 * m];
+            row[x + 2 * m] = s;
+            s -= old;
+          }
         }
       }
     }
@@ -903,14 +1000,15 @@ __global__ void __launch_bounds__(IT_THREADS, CT ? 2 : 1) fb_iter(IterArgs a) {
     const int segr = (T + nseg - 1) / nseg;
     const int seg = t / T, x = t - seg * T;
     const int gx = x0 + x;
+    const int xs = x < HL ? x : x + 2 * m;     // where step B left this column's sums
     if (seg < nseg && gx < w) {
       float2* fo = a.flow_out + (size_t)pair * a.flow_out_pair_stride;
       const int r0 = seg * segr;
       const int r1 = min(r0 + segr, T);
       if (GAUSS) {
         for (int y = r0; y < r1; ++y) {
-          const float4* c4 = sM4 + (y + m) * ES + x;
-          const float* c1 = sM1 + (y + m) * ES + x;
+          const float4* c4 = sM4 + (y + m) * ES + xs;
+          const float* c1 = sM1 + (y + m) * ES + xs;
           float4 s4 = fma4s(c4[0], a.gtaps[0], make_float4(0.f, 0.f, 0.f, 0.f));
           float s1 = c1[0] * a.gtaps[0];
           for (int k = 1; k <= m; ++k) {
@@ -921,8 +1019,8 @@ __global__ void __launch_bounds__(IT_THREADS, CT ? 2 : 1) fb_iter(IterArgs a) {
           if (gy < h) fo[(size_t)gy * a.out_pitch + gx] = solve2x2(s4.x, s4.y, s4.z, s4.w, s1);
         }
       } else if (r0 < r1) {
-        const float4* c4 = sM4 + r0 * ES + x;
-        const float* c1 = sM1 + r0 * ES + x;
+        const float4* c4 = sM4 + r0 * ES + xs;
+        const float* c1 = sM1 + r0 * ES + xs;
         float4 s4 = c4[0];
         float s1 = c1[0];
         for (int k = 1; k < 2 * m; ++k) { s4 = add4(s4, c4[k * ES]); s1 += c1[k * ES]; }
@@ -1068,9 +1166,15 @@ static int fb_frames(const FbPlan* pl, const FbWorkspace& ws, const uint8_t* fra
 static std::once_flag g_attr_once;
 static void set_func_attrs() {
   const int big = 227 * 1024;
-  cudaFuncSetAttribute(fb_iter<IT_T_FAST, 7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  cudaFuncSetAttribute(fb_iter<0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  cudaFuncSetAttribute(fb_iter<0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(fb_iter<IT_T_FAST, 7, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(fb_iter<IT_T_FAST, 7, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(fb_iter<IT_T_FAST, 7, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(fb_iter<0, 0, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(fb_iter<0, 0, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(fb_iter<0, 0, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(fb_iter<0, 0, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(fb_iter<0, 0, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(fb_iter<0, 0, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   cudaFuncSetAttribute(fb_polyexp, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   cudaFuncSetAttribute(fb_level_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 }
@@ -1150,9 +1254,16 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
         double px = (double)L.w * L.h;
         double bytes = pairs * (48.0 * px + (a.mode == 1 ? 8.0 * px : a.mode == 2 ? 8.0 * cw * ch : 0.0));
         ProfScope ps(last_level ? PT_FB_ITER_FINEST : PT_FB_ITER_COARSE, st, bytes);
-        if (fast) fb_iter<IT_T_FAST, 7, false><<<grid, IT_THREADS, smem, st>>>(a);
-        else if (gauss) fb_iter<0, 0, true><<<grid, IT_THREADS, smem, st>>>(a);
-        else fb_iter<0, 0, false><<<grid, IT_THREADS, smem, st>>>(a);
+#define B2OF_ITER_LAUNCH(CT_, CM_, G_)                                                       \
+  do {                                                                                      \
+    if (a.mode == 0) fb_iter<CT_, CM_, G_, 0><<<grid, IT_THREADS, smem, st>>>(a);           \
+    else if (a.mode == 1) fb_iter<CT_, CM_, G_, 1><<<grid, IT_THREADS, smem, st>>>(a);      \
+    else fb_iter<CT_, CM_, G_, 2><<<grid, IT_THREADS, smem, st>>>(a);                       \
+  } while (0)
+        if (fast) B2OF_ITER_LAUNCH(IT_T_FAST, 7, false);
+        else if (gauss) B2OF_ITER_LAUNCH(0, 0, true);
+        else B2OF_ITER_LAUNCH(0, 0, false);
+#undef B2OF_ITER_LAUNCH
       }
       B2OF_LAUNCH_CHECK();
       cur = dst; cur_pitch = dpitch; cur_stride = dstride;
