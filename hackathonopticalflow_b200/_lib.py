@@ -63,6 +63,7 @@ SIGNATURES = {
     "b2of_farneback_sequence_dev": (_i, [_vp, _sz, _sz, _i, _i, _i, _PF, _vp, _vp, _sz, _vp]),
     "b2of_farneback_host": (_i, [_vp, _vp, _sz, _i, _i, _PF, _vp]),
     "b2of_farneback_pairs_host": (_i, [_vp, _vp, _sz, _sz, _i, _i, _i, _PF, _vp]),
+    "b2of_farneback_sequence_host": (_i, [_vp, _sz, _sz, _i, _i, _i, _PF, _vp]),
     "b2of_pyrlk_workspace_bytes": (_sz, [_i, _i, _PL, _i]),
     "b2of_pyrlk_dev": (_i, [_vp, _vp, _sz, _sz, _i, _i, _i, _vp, _sz, _i, _vp, _vp, _vp, _PL, _vp, _sz, _vp]),
     "b2of_pyrlk_host": (_i, [_vp, _vp, _sz, _i, _i, _vp, _i, _vp, _vp, _vp, _PL]),

@@ -247,26 +247,31 @@ int b2of_farneback_sequence_dev(const uint8_t* frames, size_t step, size_t frame
                        ws_bytes, (cudaStream_t)stream);
 }
 
-int b2of_farneback_pairs_host(const uint8_t* prev, const uint8_t* next, size_t step, size_t frame_stride, int n_pairs,
-                              int rows, int cols, const b2of_farneback_params* p, float* flow) {
+// Pipelined host form shared by the pairs and the sequence entry points: H2D (st[1]) -> compute (st[0]) -> D2H
+// (st[2]), `chunk` pairs per stage, double-buffered device input/output.
+//   shared == 0: pair i = (prev + i*frame_stride, next + i*frame_stride)
+//   shared == 1: frames at prev + i*frame_stride, i in [0, n_pairs]; pair i = (frame i, frame i+1)
+static int farneback_host_pipeline(const uint8_t* prev, const uint8_t* next, size_t step, size_t frame_stride,
+                                   int n_pairs, int shared, int rows, int cols, const b2of_farneback_params* p,
+                                   float* flow) {
   const char* fn = "calcOpticalFlowFarneback";
-  B2OF_ASSERT(prev != nullptr && next != nullptr && flow != nullptr, fn);
+  B2OF_ASSERT(prev != nullptr && (shared || next != nullptr) && flow != nullptr, fn);
   B2OF_ASSERT(rows > 0 && cols > 0 && step >= (size_t)cols, fn);
   if (n_pairs <= 0) return B2OF_OK;
-  size_t one = b2of_farneback_workspace_bytes(rows, cols, p, 1, 0);
+  size_t one = b2of_farneback_workspace_bytes(rows, cols, p, 1, shared);
   if (one == 0) return B2OF_E_BADARG;  // message already set
   HostCtx* c;
   int rc = get_ctx(&c);
   if (rc) return rc;
   std::lock_guard<std::mutex> lock(c->mu);
   if ((rc = c->init())) return rc;
-  // double-buffered pipeline: H2D (st[1]) -> compute (st[0]) -> D2H (st[2]), `chunk` pairs per stage
   const size_t frame = (size_t)rows * cols, flow_pair = frame * 2 * sizeof(float);
-  int chunk = n_pairs < 4 ? n_pairs : 4;
-  size_t ws_bytes = b2of_farneback_workspace_bytes(rows, cols, p, chunk, 0);
+  int chunk = n_pairs < 8 ? n_pairs : 8;
+  const int fpc = shared ? chunk + 1 : 2 * chunk;   // device frames per chunk
+  size_t ws_bytes = b2of_farneback_workspace_bytes(rows, cols, p, chunk, shared);
   if ((rc = c->ws.ensure(ws_bytes))) return rc;
   for (int b = 0; b < 2; ++b) {
-    if ((rc = c->in[b].ensure(2 * frame * chunk))) return rc;
+    if ((rc = c->in[b].ensure(frame * fpc))) return rc;
     if ((rc = c->out[b].ensure(flow_pair * chunk))) return rc;
   }
   cudaStream_t s_c = c->st[0], s_in = c->st[1], s_out = c->st[2];
@@ -278,19 +283,34 @@ int b2of_farneback_pairs_host(const uint8_t* prev, const uint8_t* next, size_t s
     uint8_t* din = (uint8_t*)c->in[b].p;
     float* dout = (float*)c->out[b].p;
     if (ci >= 2) B2OF_CUDA(cudaStreamWaitEvent(s_in, c->ev[2 + b], 0));  // compute that read this input is done
-    for (int i = 0; i < np; ++i) {
-      if ((rc = copy2d(din + (size_t)(2 * i) * frame, cols, prev + (size_t)(p0 + i) * frame_stride, step, cols, rows,
-                       cudaMemcpyHostToDevice, s_in)))
-        return rc;
-      if ((rc = copy2d(din + (size_t)(2 * i + 1) * frame, cols, next + (size_t)(p0 + i) * frame_stride, step, cols,
-                       rows, cudaMemcpyHostToDevice, s_in)))
-        return rc;
+    if (shared) {
+      const uint8_t* src = prev + (size_t)p0 * frame_stride;
+      if (step == (size_t)cols && frame_stride == frame) {
+        B2OF_CUDA(cudaMemcpyAsync(din, src, frame * (np + 1), cudaMemcpyHostToDevice, s_in));
+      } else {
+        for (int i = 0; i <= np; ++i)
+          if ((rc = copy2d(din + (size_t)i * frame, cols, src + (size_t)i * frame_stride, step, cols, rows,
+                           cudaMemcpyHostToDevice, s_in)))
+            return rc;
+      }
+    } else {
+      for (int i = 0; i < np; ++i) {
+        if ((rc = copy2d(din + (size_t)(2 * i) * frame, cols, prev + (size_t)(p0 + i) * frame_stride, step, cols,
+                         rows, cudaMemcpyHostToDevice, s_in)))
+          return rc;
+        if ((rc = copy2d(din + (size_t)(2 * i + 1) * frame, cols, next + (size_t)(p0 + i) * frame_stride, step,
+                         cols, rows, cudaMemcpyHostToDevice, s_in)))
+          return rc;
+      }
     }
     B2OF_CUDA(cudaEventRecord(c->ev[b], s_in));
     B2OF_CUDA(cudaStreamWaitEvent(s_c, c->ev[b], 0));
     if (ci >= 2) B2OF_CUDA(cudaStreamWaitEvent(s_c, c->ev[4 + b], 0));  // previous output in this slot drained
-    if ((rc = farneback_dev(din, din + frame, cols, 2 * frame, np, 0, rows, cols, p, dout, c->ws.p, c->ws.cap, s_c)))
-      return rc;
+    if (shared)
+      rc = farneback_dev(din, din + frame, cols, frame, np, 1, rows, cols, p, dout, c->ws.p, c->ws.cap, s_c);
+    else
+      rc = farneback_dev(din, din + frame, cols, 2 * frame, np, 0, rows, cols, p, dout, c->ws.p, c->ws.cap, s_c);
+    if (rc) return rc;
     B2OF_CUDA(cudaEventRecord(c->ev[2 + b], s_c));
     B2OF_CUDA(cudaStreamWaitEvent(s_out, c->ev[2 + b], 0));
     B2OF_CUDA(cudaMemcpyAsync(flow + (size_t)p0 * frame * 2, dout, flow_pair * np, cudaMemcpyDeviceToHost, s_out));
@@ -299,6 +319,17 @@ int b2of_farneback_pairs_host(const uint8_t* prev, const uint8_t* next, size_t s
   B2OF_CUDA(cudaStreamSynchronize(s_out));
   B2OF_CUDA(cudaStreamSynchronize(s_c));
   return B2OF_OK;
+}
+
+int b2of_farneback_pairs_host(const uint8_t* prev, const uint8_t* next, size_t step, size_t frame_stride, int n_pairs,
+                              int rows, int cols, const b2of_farneback_params* p, float* flow) {
+  return farneback_host_pipeline(prev, next, step, frame_stride, n_pairs, 0, rows, cols, p, flow);
+}
+
+int b2of_farneback_sequence_host(const uint8_t* frames, size_t step, size_t frame_stride, int n_frames, int rows,
+                                 int cols, const b2of_farneback_params* p, float* flow) {
+  if (n_frames < 2) return B2OF_OK;
+  return farneback_host_pipeline(frames, nullptr, step, frame_stride, n_frames - 1, 1, rows, cols, p, flow);
 }
 
 int b2of_farneback_host(const uint8_t* prev, const uint8_t* next, size_t step, int rows, int cols,

@@ -10,6 +10,7 @@
 // solve are one kernel per (level, iteration); the x(1/pyr_scale) bilinear flow upsample is folded into
 // the first iteration of each level.
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <map>
 #include <mutex>
@@ -792,8 +793,8 @@ __device__ __forceinline__ float2 fetch_flow_m(const IterArgs& a, const float2* 
   return make_float2((tx0 * (1.f - fy) + tx1 * fy) * a.up_mult, (ty0 * (1.f - fy) + ty1 * fy) * a.up_mult);
 }
 
-template <int CT, int CM, bool GAUSS, int MODE>
-__global__ void __launch_bounds__(IT_THREADS, CT ? 2 : 1) fb_iter(IterArgs a) {
+template <int NT, int CT, int CM, bool GAUSS, int MODE>
+__global__ void __launch_bounds__(NT, (CT && NT <= 512) ? 2 : 1) fb_iter(IterArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int T = CT ? CT : a.tile;
   const int m = CT ? CM : a.m;
@@ -821,7 +822,7 @@ __global__ void __launch_bounds__(IT_THREADS, CT ? 2 : 1) fb_iter(IterArgs a) {
   // row are fetched before the current gathers are consumed (software pipeline); gathers are branch-free
   // (clamped address + select).
   {
-    const int RP = IT_THREADS / E;            // row runs per tile (7 for E = 70)
+    const int RP = NT / E;            // row runs per tile (7 for E = 70)
     const int RS = (E + RP - 1) / RP;         // rows per run (10)
     const int ty = t / E, ix = t - ty * E;
     if (ty < RP) {
@@ -996,7 +997,7 @@ __global__ void __launch_bounds__(IT_THREADS, CT ? 2 : 1) fb_iter(IterArgs a) {
 
   // ---- step C: vertical window sums + 2x2 solve; thread = (column, row segment) ----
   {
-    const int nseg = IT_THREADS / T;
+    const int nseg = NT / T;
     const int segr = (T + nseg - 1) / nseg;
     const int seg = t / T, x = t - seg * T;
     const int gx = x0 + x;
@@ -1166,15 +1167,15 @@ static int fb_frames(const FbPlan* pl, const FbWorkspace& ws, const uint8_t* fra
 static std::once_flag g_attr_once;
 static void set_func_attrs() {
   const int big = 227 * 1024;
-  cudaFuncSetAttribute(fb_iter<IT_T_FAST, 7, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  cudaFuncSetAttribute(fb_iter<IT_T_FAST, 7, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  cudaFuncSetAttribute(fb_iter<IT_T_FAST, 7, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  cudaFuncSetAttribute(fb_iter<0, 0, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  cudaFuncSetAttribute(fb_iter<0, 0, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  cudaFuncSetAttribute(fb_iter<0, 0, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  cudaFuncSetAttribute(fb_iter<0, 0, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  cudaFuncSetAttribute(fb_iter<0, 0, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  cudaFuncSetAttribute(fb_iter<0, 0, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+#define B2OF_ATTR(NT_, CT_, CM_, G_)                                                                        \
+  cudaFuncSetAttribute(fb_iter<NT_, CT_, CM_, G_, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);    \
+  cudaFuncSetAttribute(fb_iter<NT_, CT_, CM_, G_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);    \
+  cudaFuncSetAttribute(fb_iter<NT_, CT_, CM_, G_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  B2OF_ATTR(512, 56, 7, false)
+  B2OF_ATTR(1024, 88, 7, false)
+  B2OF_ATTR(512, 0, 0, false)
+  B2OF_ATTR(512, 0, 0, true)
+#undef B2OF_ATTR
   cudaFuncSetAttribute(fb_polyexp, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   cudaFuncSetAttribute(fb_level_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 }
@@ -1187,7 +1188,13 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
   const bool gauss = (p.flags & B2OF_OPTFLOW_FARNEBACK_GAUSSIAN) != 0;
   // tile: the specialised kernel for the reference's window, else the largest tile whose halo fits one SM
   const bool fast = !gauss && m == 7;
-  int tile = IT_T_FAST;
+  static const int fast_tile = [] {
+    const char* e = getenv("B2OF_ITER_TILE");   // 56 (2 CTAs/SM x 512 threads) or 88 (1 CTA/SM x 1024 threads)
+    int v = e ? atoi(e) : 56;
+    return v == 88 ? 88 : 56;
+  }();
+  int tile = fast_tile;
+  const int nthreads = (fast && fast_tile == 88) ? 1024 : IT_THREADS;
   if (!fast) {
     tile = 64;
     while (tile > 16 && (size_t)5 * (tile + 2 * m) * ((tile + 2 * m) | 1) * sizeof(float) > 200 * 1024) tile -= 8;
@@ -1254,15 +1261,16 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
         double px = (double)L.w * L.h;
         double bytes = pairs * (48.0 * px + (a.mode == 1 ? 8.0 * px : a.mode == 2 ? 8.0 * cw * ch : 0.0));
         ProfScope ps(last_level ? PT_FB_ITER_FINEST : PT_FB_ITER_COARSE, st, bytes);
-#define B2OF_ITER_LAUNCH(CT_, CM_, G_)                                                       \
+#define B2OF_ITER_LAUNCH(NT_, CT_, CM_, G_)                                                 \
   do {                                                                                      \
-    if (a.mode == 0) fb_iter<CT_, CM_, G_, 0><<<grid, IT_THREADS, smem, st>>>(a);           \
-    else if (a.mode == 1) fb_iter<CT_, CM_, G_, 1><<<grid, IT_THREADS, smem, st>>>(a);      \
-    else fb_iter<CT_, CM_, G_, 2><<<grid, IT_THREADS, smem, st>>>(a);                       \
+    if (a.mode == 0) fb_iter<NT_, CT_, CM_, G_, 0><<<grid, NT_, smem, st>>>(a);             \
+    else if (a.mode == 1) fb_iter<NT_, CT_, CM_, G_, 1><<<grid, NT_, smem, st>>>(a);        \
+    else fb_iter<NT_, CT_, CM_, G_, 2><<<grid, NT_, smem, st>>>(a);                         \
   } while (0)
-        if (fast) B2OF_ITER_LAUNCH(IT_T_FAST, 7, false);
-        else if (gauss) B2OF_ITER_LAUNCH(0, 0, true);
-        else B2OF_ITER_LAUNCH(0, 0, false);
+        if (fast && nthreads == 1024) B2OF_ITER_LAUNCH(1024, 88, 7, false);
+        else if (fast) B2OF_ITER_LAUNCH(512, 56, 7, false);
+        else if (gauss) B2OF_ITER_LAUNCH(512, 0, 0, true);
+        else B2OF_ITER_LAUNCH(512, 0, 0, false);
 #undef B2OF_ITER_LAUNCH
       }
       B2OF_LAUNCH_CHECK();

@@ -125,6 +125,24 @@ def calcOpticalFlowFarnebackBatch(prev, next, pyr_scale=0.5, levels=3, winsize=1
     return flow
 
 
+def calcOpticalFlowFarnebackSequence(frames, pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5,
+                                     poly_sigma=1.2, flags=0, flow=None):
+    """Extension for video: uint8 (F,H,W) consecutive gray frames -> float32 (F-1,H,W,2), flow[i] = frame i -> i+1
+    (what the reference's per-frame loop computes, DenseOF.py:510-525).  Per-frame work is done once per frame;
+    host<->device copies are pipelined with the kernels."""
+    fn = "calcOpticalFlowFarneback"
+    _assert(isinstance(frames, np.ndarray) and frames.dtype == np.uint8 and frames.ndim == 3,
+            "prev0.type() == CV_8UC1", fn)
+    frames = np.ascontiguousarray(frames)
+    f, h, w = frames.shape
+    if flow is None:
+        flow = _new_host((max(f - 1, 0), h, w, 2), np.float32)
+    p = FarnebackParams(float(pyr_scale), int(levels), int(winsize), int(iterations), int(poly_n), float(poly_sigma),
+                        int(flags))
+    _lib.check(_lib.lib().b2of_farneback_sequence_host(_ptr(frames), w, h * w, f, h, w, C.byref(p), _ptr(flow)))
+    return flow
+
+
 def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts, status=None, err=None, winSize=(21, 21), maxLevel=3,
                          criteria=(TERM_CRITERIA_COUNT + TERM_CRITERIA_EPS, 30, 0.01), flags=0,
                          minEigThreshold=1e-4):

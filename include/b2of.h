@@ -115,6 +115,10 @@ int b2of_farneback_host(const uint8_t* prev, const uint8_t* next, size_t step, i
 int b2of_farneback_pairs_host(const uint8_t* prev, const uint8_t* next, size_t step, size_t frame_stride, int n_pairs,
                               int rows, int cols, const b2of_farneback_params* p, float* flow);
 
+/* pipelined host form for a video: n_frames consecutive host frames -> n_frames-1 host flows */
+int b2of_farneback_sequence_host(const uint8_t* frames, size_t step, size_t frame_stride, int n_frames, int rows,
+                                 int cols, const b2of_farneback_params* p, float* flow);
+
 /* ---- K10-K11: cv2.calcOpticalFlowPyrLK ------------------------------------------
  * replaces viewer.py:156-158 / DenseOF.py:183-185 (45x45 grid form, prev = current
  * frame) and SparseOF.py:35-36 (15x15 track form, forward + backward). */

@@ -200,6 +200,18 @@ def test_farneback_host_batch_matches_single_calls(b2, synth_small):
         assert np.array_equal(out[k], a if k % 2 == 0 else c)
 
 
+def test_farneback_host_sequence_matches_single_calls(b2, synth_small):
+    f0, f1 = synth_small["f0"], synth_small["f1"]
+    frames = np.stack([f0, f1, f0, f1, f0, f1, f0, f1, f0, f1, f0])      # 10 pairs: more than one pipeline chunk
+    out = b2.calcOpticalFlowFarnebackSequence(frames)
+    a = b2.calcOpticalFlowFarneback(f0, f1, None, *REF_FB)
+    c = b2.calcOpticalFlowFarneback(f1, f0, None, *REF_FB)
+    assert out.shape == (10, 135, 241, 2)
+    for k in range(10):
+        assert np.array_equal(out[k], a if k % 2 == 0 else c)
+    assert b2.calcOpticalFlowFarnebackSequence(frames[:1]).shape == (0, 135, 241, 2)
+
+
 # ------------------------------------------------------------------ K10-K11 PyrLK
 def _lk_check(got, want_next, want_status, want_err=None):
     nxt, st, err = got
