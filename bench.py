@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 
 H, W = 1080, 1920
 PAIRS_PER_GPU = 64          # pairs per step per GPU (65 frames = 135 MB of input, > L2)
-CHUNK_PAIRS = 16            # pairs in flight per pass inside the engine
+CHUNK_PAIRS = 64            # pairs in flight per pass inside the engine (13 GB of scratch)
 E2E_PAIRS = 32              # pairs per end-to-end step (68 MB H2D, 531 MB D2H)
 PARAMS = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)  # DenseOF.py:127-128
 WORKLOAD = "configs[2]: DenseOF Farneback on synthetic 1920x1080 frame-pair batches, reference parameters"
@@ -250,7 +250,8 @@ def main():
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            traffic = json.load(f).get("fb_iter_finest_dram_bytes_per_launch")
+            per_pair = json.load(f).get("fb_iter_finest_dram_bytes_per_pair_launch")
+            traffic = per_pair * min(args.chunk, P) if per_pair else None
     except Exception:
         pass
     b_stream = stream_bytes_per_pair()
@@ -263,7 +264,7 @@ def main():
         "config": {"workload": WORKLOAD, "height": H, "width": W, "pairs_per_gpu_per_step": P,
                    "frames_per_gpu": P + 1, "chunk_pairs": args.chunk, "input_form": "consecutive frames "
                    "(per-frame work reused, B_stream accounting)", "sharding": f"frames x{world} contiguous + 1-frame halo",
-                   "l2": "inputs (135 MB/GPU) and intermediates (>3 GB/GPU) exceed the 126 MB L2; no explicit flush",
+                   "l2": "inputs (135 MB/GPU) and intermediates (13 GB/GPU) exceed the 126 MB L2; no explicit flush",
                    "step_includes": "flow_sequence + flow_stats + gather of per-pair stats to rank 0"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": (E + 1) * H * W,

@@ -794,7 +794,7 @@ __device__ __forceinline__ float2 fetch_flow_m(const IterArgs& a, const float2* 
 }
 
 template <int NT, int CT, int CM, bool GAUSS, int MODE>
-__global__ void __launch_bounds__(NT, (CT && NT <= 512) ? 2 : 1) fb_iter(IterArgs a) {
+__global__ void __launch_bounds__(NT, CT == 0 ? 1 : (NT == 256 ? 4 : NT == 320 ? 3 : NT == 512 ? 2 : 1)) fb_iter(IterArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int T = CT ? CT : a.tile;
   const int m = CT ? CM : a.m;
@@ -1173,6 +1173,10 @@ static void set_func_attrs() {
   cudaFuncSetAttribute(fb_iter<NT_, CT_, CM_, G_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   B2OF_ATTR(512, 56, 7, false)
   B2OF_ATTR(1024, 88, 7, false)
+  B2OF_ATTR(512, 48, 7, false)
+  B2OF_ATTR(256, 32, 7, false)
+  B2OF_ATTR(320, 40, 7, false)
+  B2OF_ATTR(512, 64, 7, false)
   B2OF_ATTR(512, 0, 0, false)
   B2OF_ATTR(512, 0, 0, true)
 #undef B2OF_ATTR
@@ -1191,7 +1195,7 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
   static const int fast_tile = [] {
     const char* e = getenv("B2OF_ITER_TILE");   // 56 (2 CTAs/SM x 512 threads) or 88 (1 CTA/SM x 1024 threads)
     int v = e ? atoi(e) : 56;
-    return v == 88 ? 88 : 56;
+    return (v == 88 || v == 48 || v == 64 || v == 32 || v == 40) ? v : 56;
   }();
   int tile = fast_tile;
   const int nthreads = (fast && fast_tile == 88) ? 1024 : IT_THREADS;
@@ -1201,7 +1205,7 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
   }
   const int E = tile + 2 * m;
   size_t smem = (size_t)5 * E * (E | 1) * sizeof(float);
-  if (smem > 227 * 1024 || E > IT_THREADS / 2)
+  if (smem > 227 * 1024 || (!fast && E > IT_THREADS / 4))
     return fail(B2OF_E_UNSUPPORTED, "winsize %d needs %zu B of shared memory", p.winsize, smem);
   size_t lvl_off = 0;
   const float2* coarse = nullptr;
@@ -1268,6 +1272,10 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
     else fb_iter<NT_, CT_, CM_, G_, 2><<<grid, NT_, smem, st>>>(a);                         \
   } while (0)
         if (fast && nthreads == 1024) B2OF_ITER_LAUNCH(1024, 88, 7, false);
+        else if (fast && tile == 48) B2OF_ITER_LAUNCH(512, 48, 7, false);
+        else if (fast && tile == 32) B2OF_ITER_LAUNCH(256, 32, 7, false);
+        else if (fast && tile == 40) B2OF_ITER_LAUNCH(320, 40, 7, false);
+        else if (fast && tile == 64) B2OF_ITER_LAUNCH(512, 64, 7, false);
         else if (fast) B2OF_ITER_LAUNCH(512, 56, 7, false);
         else if (gauss) B2OF_ITER_LAUNCH(512, 0, 0, true);
         else B2OF_ITER_LAUNCH(512, 0, 0, false);
