@@ -741,6 +741,7 @@ struct IterArgs {
   int out_pitch;           // in float2
   int m;                   // winsize / 2
   int tile;                // output tile edge (generic kernel)
+  int nb;                  // vertically adjacent tiles walked by one CTA
   float inv_area;          // 1 / winsize^2 (box)
   const float* gtaps;      // Gaussian window taps or nullptr
 };
@@ -801,10 +802,10 @@ __global__ void __launch_bounds__(NT, CT == 0 ? 1 : (NT == 256 ? 4 : NT == 320 ?
   const int E = T + 2 * m;          // halo tile edge
   const int ES = E | 1;             // odd row stride (in elements): conflict-free row walks
   const int HL = T >> 1;            // outputs [0,HL) are summed left->right, [HL,T) right->left (see step B)
-  float4* sM4 = (float4*)smem;      // [E][ES]  (M0..M3)
+  float4* sM4 = (float4*)smem;      // [E][ES]  (M0..M3)   rows form a ring (see `off`)
   float* sM1 = smem + 4 * E * ES;   // [E][ES]  (M4)
   const int pair = blockIdx.z;
-  const int x0 = blockIdx.x * T, y0 = blockIdx.y * T;
+  const int x0 = blockIdx.x * T;
   const int w = a.w, h = a.h, pitch = a.pitch;
   const float* base0 = a.R + (size_t)pair * a.pair_frame_step * a.r_frame_stride;
   const float4* __restrict__ R0a = (const float4*)base0;
@@ -812,32 +813,43 @@ __global__ void __launch_bounds__(NT, CT == 0 ? 1 : (NT == 256 ? 4 : NT == 320 ?
   const float4* __restrict__ R1a = (const float4*)(base0 + a.r_frame_stride);
   const float* __restrict__ R1b = base0 + a.r_frame_stride + 4 * a.plane_stride;
   const float2* __restrict__ fin = MODE ? a.flow_in + (size_t)pair * a.flow_in_pair_stride : nullptr;
+  float2* __restrict__ fo = a.flow_out + (size_t)pair * a.flow_out_pair_stride;
   const int t = threadIdx.x;
 
-  // ---- step A: M on the halo tile (positions clamped to the image = BORDER_REPLICATE of M) ----
-  // thread = one halo column and a run of RS consecutive rows.  Walking down a column, the bottom corners of
-  // one pixel's bilinear gather are the top corners of the next one whenever the integer part of the warp did
-  // not jump (almost always: the flow is smooth), so they are carried in registers and only the two new
-  // corners are loaded -- half the gather traffic through L1.  The flow vector and the R0 record of the NEXT
-  // row are fetched before the current gathers are consumed (software pipeline); gathers are branch-free
-  // (clamped address + select).
-  {
-    const int RP = NT / E;            // row runs per tile (7 for E = 70)
-    const int RS = (E + RP - 1) / RP;         // rows per run (10)
-    const int ty = t / E, ix = t - ty * E;
+  // per-thread constants of step A: one halo column per thread
+  const int RP = NT / E;                      // row runs per tile (7 for E = 70)
+  const int ty = t / E, ix = t - ty * E;
+  const int x = clampi(x0 - m + ix, 0, w - 1);
+  const float xf = (float)x;
+  const bool xb_border = x < 5 || x >= w - 5;
+  const float bwx = border_w(x, w);
+  int uxa = 0, uxb = 0;
+  float ufx = 0.f;
+  if (MODE == 2) { uxa = a.ux0[x]; uxb = a.ux1[x]; ufx = a.ufx[x]; }
+
+  // The CTA walks `nb` vertically adjacent tiles.  The last 2m horizontally-summed rows of one tile are the
+  // first 2m rows of the next one, so they stay in shared memory (ring of E rows, logical row l of the current
+  // tile lives at physical row (l + off) mod E) and only T new rows of M are computed: halo recompute drops
+  // from E*E/(T*T) to E/T per tile after the first.
+  int off = 0;
+  for (int c = 0; c < a.nb; ++c) {
+    const int y0 = (blockIdx.y * a.nb + c) * T;
+    if (y0 >= h) break;
+    const int lstart = c == 0 ? 0 : 2 * m;    // first logical row that is new in this tile
+    const int nrows = E - lstart;
+
+    // ---- step A: M on the new halo rows (positions clamped to the image = BORDER_REPLICATE of M) ----
+    // thread = one halo column and a run of RS consecutive rows.  Walking down a column, the bottom corners of
+    // one pixel's bilinear gather are the top corners of the next one whenever the integer part of the warp
+    // did not jump (almost always: the flow is smooth), so they are carried in registers and only the two new
+    // corners are loaded.  Flow vector and R0 record of the NEXT row are fetched before the current gathers are
+    // consumed (software pipeline); gathers are branch-free (clamped address + select).
     if (ty < RP) {
-      const int x = clampi(x0 - m + ix, 0, w - 1);
-      const float xf = (float)x;
-      const bool xb_border = x < 5 || x >= w - 5;
-      const float bwx = border_w(x, w);
-      int uxa = 0, uxb = 0;
-      float ufx = 0.f;
-      if (MODE == 2) { uxa = a.ux0[x]; uxb = a.ux1[x]; ufx = a.ufx[x]; }
-      int iy = ty * RS;
-      const int iy_end = min(iy + RS, E);
-      // everything this thread will stream (flow, R0) is a first touch from HBM, and so is most of the R1
-      // neighbourhood: pull the whole column run into L2 now so the pipelined loads below see L2 latency
-      for (int r = iy; r < iy_end; ++r) {
+      const int RS = (nrows + RP - 1) / RP;
+      int l = lstart + ty * RS;
+      const int l_end = min(l + RS, E);
+      // first touches from HBM (flow, R0, most of the R1 neighbourhood): pull the run into L2 now
+      for (int r = l; r < l_end; ++r) {
         const int yy = clampi(y0 - m + r, 0, h - 1);
         const int o = yy * pitch + x;
         if (MODE == 1) prefetch_l2(fin + yy * a.in_pitch + x);
@@ -846,199 +858,214 @@ __global__ void __launch_bounds__(NT, CT == 0 ? 1 : (NT == 256 ? 4 : NT == 320 ?
         prefetch_l2(R1a + o);
         prefetch_l2(R1b + o);
       }
-      int y_n = clampi(y0 - m + iy, 0, h - 1);
-      float2 d_n = fetch_flow_m<MODE>(a, fin, x, y_n, uxa, uxb, ufx);
-      float4 q_n = R0a[y_n * pitch + x];
-      float q4_n = R0b[y_n * pitch + x];
-      // carried bottom corners of the previous row and where they came from
-      float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
-      float e0 = 0.f, e1 = 0.f;
-      int ox_prev = -1 << 30;                 // offset of the carried row (o1 + pitch of the previous pixel)
-      for (; iy < iy_end; ++iy) {
-        const float2 d = d_n;
-        const float4 q = q_n;
-        const float q4 = q4_n;
-        const int y = y_n;
-        float fx = xf + d.x, fy = (float)y + d.y;
-        float flx = floorf(fx), fly = floorf(fy);
-        int x1 = (int)flx, y1 = (int)fly;
-        fx -= flx; fy -= fly;
-        const bool inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
-        const int o1 = inside ? y1 * pitch + x1 : 0;
-        const float4* g4 = R1a + o1;
-        const float* g1 = R1b + o1;
-        float4 p00, p01;
-        float s00, s01;
-        if (o1 == ox_prev) {                  // top corners = carried bottom corners
-          p00 = c0; p01 = c1; s00 = e0; s01 = e1;
-        } else {
-          p00 = g4[0]; p01 = g4[1]; s00 = g1[0]; s01 = g1[1];
+      if (l < l_end) {
+        int y_n = clampi(y0 - m + l, 0, h - 1);
+        float2 d_n = fetch_flow_m<MODE>(a, fin, x, y_n, uxa, uxb, ufx);
+        float4 q_n = R0a[y_n * pitch + x];
+        float q4_n = R0b[y_n * pitch + x];
+        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;   // carried bottom corners of the previous row
+        float e0 = 0.f, e1 = 0.f;
+        int ox_prev = -1 << 30;                                   // R1 offset they were loaded from
+        int pr = l + off;
+        if (pr >= E) pr -= E;
+        for (; l < l_end; ++l) {
+          const float2 d = d_n;
+          const float4 q = q_n;
+          const float q4 = q4_n;
+          const int y = y_n;
+          float fx = xf + d.x, fy = (float)y + d.y;
+          float flx = floorf(fx), fly = floorf(fy);
+          int x1 = (int)flx, y1 = (int)fly;
+          fx -= flx; fy -= fly;
+          const bool inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
+          const int o1 = inside ? y1 * pitch + x1 : 0;
+          const float4* g4 = R1a + o1;
+          const float* g1 = R1b + o1;
+          float4 p00, p01;
+          float s00, s01;
+          if (o1 == ox_prev) {                  // top corners = carried bottom corners
+            p00 = c0; p01 = c1; s00 = e0; s01 = e1;
+          } else {
+            p00 = g4[0]; p01 = g4[1]; s00 = g1[0]; s01 = g1[1];
+          }
+          const float4 p10 = g4[pitch], p11 = g4[pitch + 1];
+          const float s10 = g1[pitch], s11 = g1[pitch + 1];
+          if (l + 1 < l_end) {                  // prefetch the next row of this thread
+            y_n = clampi(y0 - m + l + 1, 0, h - 1);
+            d_n = fetch_flow_m<MODE>(a, fin, x, y_n, uxa, uxb, ufx);
+            q_n = R0a[y_n * pitch + x];
+            q4_n = R0b[y_n * pitch + x];
+          }
+          const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+          float r2 = a00 * p00.x + a01 * p01.x + a10 * p10.x + a11 * p11.x;
+          float r3 = a00 * p00.y + a01 * p01.y + a10 * p10.y + a11 * p11.y;
+          float r4 = a00 * p00.z + a01 * p01.z + a10 * p10.z + a11 * p11.z;
+          float r5 = a00 * p00.w + a01 * p01.w + a10 * p10.w + a11 * p11.w;
+          float r6 = a00 * s00 + a01 * s01 + a10 * s10 + a11 * s11;
+          c0 = p10; c1 = p11; e0 = s10; e1 = s11;
+          ox_prev = o1 + pitch;
+          r2 = inside ? r2 : 0.f;
+          r3 = inside ? r3 : 0.f;
+          r4 = inside ? (q.z + r4) * 0.5f : q.z;
+          r5 = inside ? (q.w + r5) * 0.5f : q.w;
+          r6 = inside ? (q4 + r6) * 0.25f : q4 * 0.5f;
+          r2 = (q.x - r2) * 0.5f;
+          r3 = (q.y - r3) * 0.5f;
+          r2 += r4 * d.y + r6 * d.x;
+          r3 += r6 * d.y + r5 * d.x;
+          if (xb_border || y < 5 || y >= h - 5) {
+            float s = bwx * border_w(y, h);
+            r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
+          }
+          const int so = pr * ES + ix;
+          sM4[so] = make_float4(r4 * r4 + r6 * r6, (r4 + r5) * r6, r5 * r5 + r6 * r6, r4 * r2 + r6 * r3);
+          sM1[so] = r6 * r2 + r5 * r3;
+          if (++pr == E) pr = 0;
         }
-        const float4 p10 = g4[pitch], p11 = g4[pitch + 1];
-        const float s10 = g1[pitch], s11 = g1[pitch + 1];
-        if (iy + 1 < iy_end) {                // prefetch the next row of this thread
-          y_n = clampi(y0 - m + iy + 1, 0, h - 1);
-          d_n = fetch_flow_m<MODE>(a, fin, x, y_n, uxa, uxb, ufx);
-          q_n = R0a[y_n * pitch + x];
-          q4_n = R0b[y_n * pitch + x];
-        }
-        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-        float r2 = a00 * p00.x + a01 * p01.x + a10 * p10.x + a11 * p11.x;
-        float r3 = a00 * p00.y + a01 * p01.y + a10 * p10.y + a11 * p11.y;
-        float r4 = a00 * p00.z + a01 * p01.z + a10 * p10.z + a11 * p11.z;
-        float r5 = a00 * p00.w + a01 * p01.w + a10 * p10.w + a11 * p11.w;
-        float r6 = a00 * s00 + a01 * s01 + a10 * s10 + a11 * s11;
-        c0 = p10; c1 = p11; e0 = s10; e1 = s11;
-        ox_prev = o1 + pitch;
-        r2 = inside ? r2 : 0.f;
-        r3 = inside ? r3 : 0.f;
-        r4 = inside ? (q.z + r4) * 0.5f : q.z;
-        r5 = inside ? (q.w + r5) * 0.5f : q.w;
-        r6 = inside ? (q4 + r6) * 0.25f : q4 * 0.5f;
-        r2 = (q.x - r2) * 0.5f;
-        r3 = (q.y - r3) * 0.5f;
-        r2 += r4 * d.y + r6 * d.x;
-        r3 += r6 * d.y + r5 * d.x;
-        if (xb_border || y < 5 || y >= h - 5) {
-          float s = bwx * border_w(y, h);
-          r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
-        }
-        const int so = iy * ES + ix;
-        sM4[so] = make_float4(r4 * r4 + r6 * r6, (r4 + r5) * r6, r5 * r5 + r6 * r6, r4 * r2 + r6 * r3);
-        sM1[so] = r6 * r2 + r5 * r3;
       }
     }
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---- step B: horizontal window sums IN PLACE.  One thread owns half a row of one plane:
-  //   left half : outputs x in [0,HL)  computed left->right,  stored at position x        (reads positions >= x)
-  //   right half: outputs x in [HL,T)  computed right->left,  stored at position x + 2m   (reads positions <= x+2m)
-  // positions [HL, HL+2m) are written by neither, so the two halves never race.
-  {
-    const int gs = (E + 31) & ~31;            // group stride: each group starts on a warp boundary
-    const int g = t / gs, r = t - g * gs;
-    if (g < 4 && r < E) {
-      const bool right = g & 1;
-      if (g < 2) {
-        float4* row = sM4 + r * ES;
-        if (GAUSS) {
-          if (!right) {
-            for (int x = 0; x < HL; ++x) {
-              float4 s = fma4s(row[x + m], a.gtaps[0], make_float4(0.f, 0.f, 0.f, 0.f));
-              for (int k = 1; k <= m; ++k) s = fma4s(add4(row[x + m - k], row[x + m + k]), a.gtaps[k], s);
-              row[x] = s;
+    // ---- step B: horizontal window sums IN PLACE on the new rows.  One thread owns half a row of one plane:
+    //   left half : outputs x in [0,HL)  computed left->right,  stored at position x        (reads positions >= x)
+    //   right half: outputs x in [HL,T)  computed right->left,  stored at position x + 2m   (reads positions <= x+2m)
+    // positions [HL, HL+2m) are written by neither, so the two halves never race.
+    {
+      const int gs = (E + 31) & ~31;            // group stride: each group starts on a warp boundary
+      const int g = t / gs, r = t - g * gs;
+      if (g < 4 && r < nrows) {
+        int pr = lstart + r + off;
+        if (pr >= E) pr -= E;
+        const bool right = g & 1;
+        if (g < 2) {
+          float4* row = sM4 + pr * ES;
+          if (GAUSS) {
+            if (!right) {
+              for (int xx = 0; xx < HL; ++xx) {
+                float4 s = fma4s(row[xx + m], a.gtaps[0], make_float4(0.f, 0.f, 0.f, 0.f));
+                for (int k = 1; k <= m; ++k) s = fma4s(add4(row[xx + m - k], row[xx + m + k]), a.gtaps[k], s);
+                row[xx] = s;
+              }
+            } else {
+              for (int xx = T - 1; xx >= HL; --xx) {
+                float4 s = fma4s(row[xx + m], a.gtaps[0], make_float4(0.f, 0.f, 0.f, 0.f));
+                for (int k = 1; k <= m; ++k) s = fma4s(add4(row[xx + m - k], row[xx + m + k]), a.gtaps[k], s);
+                row[xx + 2 * m] = s;
+              }
+            }
+          } else if (!right) {
+            float4 s = row[0];
+            for (int k = 1; k < 2 * m; ++k) s = add4(s, row[k]);
+            for (int xx = 0; xx < HL; ++xx) {
+              s = add4(s, row[xx + 2 * m]);
+              float4 old = row[xx];
+              row[xx] = s;
+              s = sub4(s, old);
             }
           } else {
-            for (int x = T - 1; x >= HL; --x) {
-              float4 s = fma4s(row[x + m], a.gtaps[0], make_float4(0.f, 0.f, 0.f, 0.f));
-              for (int k = 1; k <= m; ++k) s = fma4s(add4(row[x + m - k], row[x + m + k]), a.gtaps[k], s);
-              row[x + 2 * m] = s;
+            float4 s = row[T];
+            for (int k = 1; k < 2 * m; ++k) s = add4(s, row[T + k]);
+            for (int xx = T - 1; xx >= HL; --xx) {
+              s = add4(s, row[xx]);
+              float4 old = row[xx + 2 * m];
+              row[xx + 2 * m] = s;
+              s = sub4(s, old);
             }
           }
-        } else if (!right) {
-          float4 s = row[0];
-          for (int k = 1; k < 2 * m; ++k) s = add4(s, row[k]);
-          for (int x = 0; x < HL; ++x) {
-            s = add4(s, row[x + 2 * m]);
-            float4 old = row[x];
-            row[x] = s;
-            s = sub4(s, old);
-          }
         } else {
-          float4 s = row[T];
-          for (int k = 1; k < 2 * m; ++k) s = add4(s, row[T + k]);
-          for (int x = T - 1; x >= HL; --x) {
-            s = add4(s, row[x]);
-            float4 old = row[x + 2 * m];
-            row[x + 2 * m] = s;
-            s = sub4(s, old);
-          }
-        }
-      } else {
-        float* row = sM1 + r * ES;
-        if (GAUSS) {
-          if (!right) {
-            for (int x = 0; x < HL; ++x) {
-              float s = row[x + m] * a.gtaps[0];
-              for (int k = 1; k <= m; ++k) s = fmaf(row[x + m - k] + row[x + m + k], a.gtaps[k], s);
-              row[x] = s;
+          float* row = sM1 + pr * ES;
+          if (GAUSS) {
+            if (!right) {
+              for (int xx = 0; xx < HL; ++xx) {
+                float s = row[xx + m] * a.gtaps[0];
+                for (int k = 1; k <= m; ++k) s = fmaf(row[xx + m - k] + row[xx + m + k], a.gtaps[k], s);
+                row[xx] = s;
+              }
+            } else {
+              for (int xx = T - 1; xx >= HL; --xx) {
+                float s = row[xx + m] * a.gtaps[0];
+                for (int k = 1; k <= m; ++k) s = fmaf(row[xx + m - k] + row[xx + m + k], a.gtaps[k], s);
+                row[xx + 2 * m] = s;
+              }
+            }
+          } else if (!right) {
+            float s = row[0];
+            for (int k = 1; k < 2 * m; ++k) s += row[k];
+            for (int xx = 0; xx < HL; ++xx) {
+              s += row[xx + 2 * m];
+              float old = row[xx];
+              row[xx] = s;
+              s -= old;
             }
           } else {
-            for (int x = T - 1; x >= HL; --x) {
-              float s = row[x + m] * a.gtaps[0];
-              for (int k = 1; k <= m; ++k) s = fmaf(row[x + m - k] + row[x + m + k], a.gtaps[k], s);
-              row[x + 2 * m] = s;
+            float s = row[T];
+            for (int k = 1; k < 2 * m; ++k) s += row[T + k];
+            for (int xx = T - 1; xx >= HL; --xx) {
+              s += row[xx];
+              float old = row[xx + 2 * m];
+              row[xx + 2 * m] = s;
+              s -= old;
             }
           }
-        } else if (!right) {
-          float s = row[0];
-          for (int k = 1; k < 2 * m; ++k) s += row[k];
-          for (int x = 0; x < HL; ++x) {
-            s += row[x + 2 * m];
-            float old = row[x];
-            row[x] = s;
-            s -= old;
-          }
-        } else {
-          float s = row[T];
-          for (int k = 1; k < 2 * m; ++k) s += row[T + k];
-          for (int x = T - 1; x >= HL; --x) {
-            s += row[x];
-            float old = row[x + 2 * m];
-            row[x + 2 * m] = s;
-            s -= old;
-          }
         }
       }
     }
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---- step C: vertical window sums + 2x2 solve; thread = (column, row segment) ----
-  {
-    const int nseg = NT / T;
-    const int segr = (T + nseg - 1) / nseg;
-    const int seg = t / T, x = t - seg * T;
-    const int gx = x0 + x;
-    const int xs = x < HL ? x : x + 2 * m;     // where step B left this column's sums
-    if (seg < nseg && gx < w) {
-      float2* fo = a.flow_out + (size_t)pair * a.flow_out_pair_stride;
-      const int r0 = seg * segr;
-      const int r1 = min(r0 + segr, T);
-      if (GAUSS) {
-        for (int y = r0; y < r1; ++y) {
-          const float4* c4 = sM4 + (y + m) * ES + xs;
-          const float* c1 = sM1 + (y + m) * ES + xs;
-          float4 s4 = fma4s(c4[0], a.gtaps[0], make_float4(0.f, 0.f, 0.f, 0.f));
-          float s1 = c1[0] * a.gtaps[0];
-          for (int k = 1; k <= m; ++k) {
-            s4 = fma4s(add4(c4[-k * ES], c4[k * ES]), a.gtaps[k], s4);
-            s1 = fmaf(c1[-k * ES] + c1[k * ES], a.gtaps[k], s1);
+    // ---- step C: vertical window sums + 2x2 solve; thread = (column, row segment) ----
+    {
+      const int nseg = NT / T;
+      const int segr = (T + nseg - 1) / nseg;
+      const int seg = t / T, xo = t - seg * T;
+      const int gx = x0 + xo;
+      const int xs = xo < HL ? xo : xo + 2 * m;   // where step B left this column's sums
+      if (seg < nseg && gx < w) {
+        const int r0 = seg * segr;
+        const int r1 = min(r0 + segr, T);
+        if (GAUSS) {
+          for (int y = r0; y < r1; ++y) {
+            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float s1 = 0.f;
+            for (int k = 0; k <= 2 * m; ++k) {
+              int pr = y + k + off;
+              if (pr >= E) pr -= E;
+              float wk = a.gtaps[k < m ? m - k : k - m];
+              s4 = fma4s(sM4[pr * ES + xs], wk, s4);
+              s1 = fmaf(sM1[pr * ES + xs], wk, s1);
+            }
+            int gy = y0 + y;
+            if (gy < h) fo[(size_t)gy * a.out_pitch + gx] = solve2x2(s4.x, s4.y, s4.z, s4.w, s1);
           }
-          int gy = y0 + y;
-          if (gy < h) fo[(size_t)gy * a.out_pitch + gx] = solve2x2(s4.x, s4.y, s4.z, s4.w, s1);
-        }
-      } else if (r0 < r1) {
-        const float4* c4 = sM4 + r0 * ES + xs;
-        const float* c1 = sM1 + r0 * ES + xs;
-        float4 s4 = c4[0];
-        float s1 = c1[0];
-        for (int k = 1; k < 2 * m; ++k) { s4 = add4(s4, c4[k * ES]); s1 += c1[k * ES]; }
-        for (int y = r0; y < r1; ++y) {
-          s4 = add4(s4, c4[2 * m * ES]);
-          s1 += c1[2 * m * ES];
-          int gy = y0 + y;
-          if (gy < h) {
-            float sc = a.inv_area;
-            fo[(size_t)gy * a.out_pitch + gx] = solve2x2(s4.x * sc, s4.y * sc, s4.z * sc, s4.w * sc, s1 * sc);
+        } else if (r0 < r1) {
+          int pt = r0 + off;                    // tail (oldest row of the window)
+          if (pt >= E) pt -= E;
+          int ph = pt;                          // head
+          float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          float s1 = 0.f;
+          for (int k = 0; k < 2 * m; ++k) {
+            s4 = add4(s4, sM4[ph * ES + xs]);
+            s1 += sM1[ph * ES + xs];
+            if (++ph == E) ph = 0;
           }
-          s4 = sub4(s4, c4[0]);
-          s1 -= c1[0];
-          c4 += ES; c1 += ES;
+          for (int y = r0; y < r1; ++y) {
+            s4 = add4(s4, sM4[ph * ES + xs]);
+            s1 += sM1[ph * ES + xs];
+            if (++ph == E) ph = 0;
+            int gy = y0 + y;
+            if (gy < h) {
+              float sc = a.inv_area;
+              fo[(size_t)gy * a.out_pitch + gx] = solve2x2(s4.x * sc, s4.y * sc, s4.z * sc, s4.w * sc, s1 * sc);
+            }
+            s4 = sub4(s4, sM4[pt * ES + xs]);
+            s1 -= sM1[pt * ES + xs];
+            if (++pt == E) pt = 0;
+          }
         }
       }
     }
+    off += T;
+    if (off >= E) off -= E;
+    if (c + 1 < a.nb) __syncthreads();          // step C still reads the rows the next tile's step A overwrites
   }
 }
 
@@ -1232,7 +1259,14 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
     const float2* cur = nullptr;  // flow at this level after the previous iteration
     int cur_pitch = 0;
     size_t cur_stride = 0;
-    dim3 grid(cdiv(L.w, tile), cdiv(L.h, tile), pairs);
+    // vertical streaming: as many tiles per CTA as still leaves >= ~4 waves of CTAs
+    const int cx = cdiv(L.w, tile), cy = cdiv(L.h, tile);
+    int nb = (int)(((long long)cx * cy * pairs) / (4 * 296));
+    static const int nb_cap = [] { const char* e = getenv("B2OF_ITER_NB"); return e ? atoi(e) : 8; }();
+    nb = nb < 1 ? 1 : (nb > nb_cap ? nb_cap : nb);
+    nb = cdiv(cy, cdiv(cy, nb));                 // balance the row groups
+    a.nb = nb;
+    dim3 grid(cx, cdiv(cy, nb), pairs);
     int iters = p.iterations;
     if (iters == 0) {
       // cv2 with iterations == 0 returns the (upsampled) initial flow of the finest level untouched;
