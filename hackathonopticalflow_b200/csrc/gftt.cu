@@ -39,12 +39,17 @@ __global__ void __launch_bounds__(256) gftt_mineig(const uint8_t* __restrict__ i
     const uint8_t* r0 = ib + (size_t)reflect101(y - 1, h) * step;
     const uint8_t* r1 = ib + (size_t)y * step;
     const uint8_t* r2 = ib + (size_t)reflect101(y + 1, h) * step;
-    int dx = (r0[xp] + 2 * r1[xp] + r2[xp]) - (r0[xm] + 2 * r1[xm] + r2[xm]);
-    int dy = (r2[xm] + 2 * r2[x] + r2[xp]) - (r0[xm] + 2 * r0[x] + r0[xp]);
-    float fx = (float)dx * scale, fy = (float)dy * scale;
-    sC[i] = fx * fx;
-    sC[E * E + i] = fx * fy;
-    sC[2 * E * E + i] = fy * fy;
+    // cv2.Sobel(CV_32F, scale) as opencv's separable filter rounds it in its SIMD body (probed bit for bit against
+    // cv2 4.13, oracle/gftt.py::sobel3_f32): the scaled smoothing taps [s, 2s, s] go through fused multiply-adds
+    const float s2 = 2.f * scale;
+    float t0 = (float)(r0[xp] - r0[xm]), t1 = (float)(r1[xp] - r1[xm]), t2 = (float)(r2[xp] - r2[xm]);
+    float fx = __fmaf_rn(t0 + t2, scale, __fmul_rn(t1, s2));
+    float ra = __fmaf_rn((float)r0[xp], scale, __fmaf_rn((float)r0[x], s2, __fmul_rn((float)r0[xm], scale)));
+    float rb = __fmaf_rn((float)r2[xp], scale, __fmaf_rn((float)r2[x], s2, __fmul_rn((float)r2[xm], scale)));
+    float fy = __fsub_rn(rb, ra);
+    sC[i] = __fmul_rn(fx, fx);
+    sC[E * E + i] = __fmul_rn(fx, fy);
+    sC[2 * E * E + i] = __fmul_rn(fy, fy);
   }
   __syncthreads();
   for (int i = t; i < 3 * E * GF_T; i += 256) {

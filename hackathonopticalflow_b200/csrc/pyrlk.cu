@@ -333,15 +333,21 @@ int pyrlk_dev(const uint8_t* prev, const uint8_t* next, size_t step, size_t fram
       return fail(B2OF_E_BADARG, "frame_stride == 0 with batch > 1");
     }
     for (int l = 1; l < a.L.n; ++l) {
-      rc = pyrdown_dev(dst + a.L.off[l - 1], a.L.h[l - 1], a.L.w[l - 1], a.L.step[l - 1], a.L.pyr_bytes,
-                       dst + a.L.off[l], a.L.step[l], a.L.pyr_bytes, batch, st);
+      {
+        ProfScope ps(PT_PYRDOWN, st, batch * 1.25 * a.L.w[l - 1] * a.L.h[l - 1]);
+        rc = pyrdown_dev(dst + a.L.off[l - 1], a.L.h[l - 1], a.L.w[l - 1], a.L.step[l - 1], a.L.pyr_bytes,
+                         dst + a.L.off[l], a.L.step[l], a.L.pyr_bytes, batch, st);
+      }
       if (rc) return rc;
     }
   }
   for (int l = 0; l < a.L.n; ++l) {
     dim3 grid(cdiv(a.L.w[l], 256), a.L.h[l], batch);
-    lk_scharr<<<grid, 256, 0, st>>>(pi + a.L.off[l], a.L.step[l], a.L.pyr_bytes, a.L.w[l], a.L.h[l], dv + a.L.doff[l],
-                                    a.L.deriv_elems);
+    {
+      ProfScope ps(PT_LK_SCHARR, st, batch * 5.0 * a.L.w[l] * a.L.h[l]);
+      lk_scharr<<<grid, 256, 0, st>>>(pi + a.L.off[l], a.L.step[l], a.L.pyr_bytes, a.L.w[l], a.L.h[l], dv + a.L.doff[l],
+                                      a.L.deriv_elems);
+    }
     B2OF_LAUNCH_CHECK();
   }
   a.pyr_i = pi; a.pyr_j = pj; a.deriv = dv;

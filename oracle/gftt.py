@@ -27,14 +27,34 @@ def sobel3(img):
     return dx, dy
 
 
+def _fma(a, b, c):
+    return (a.astype(np.float64) * np.float64(b) + c.astype(np.float64)).astype(f32)
+
+
+def sobel3_f32(img, scale):
+    """cv2.Sobel(CV_32F, ksize=3, scale) as the SIMD body of opencv's separable filter rounds it (probed against
+    cv2 4.13 bit for bit): the scaled smoothing kernel [s, 2s, s] is applied with fused multiply-adds,
+        Dx = fma(t[y-1] + t[y+1], s, t[y] * 2s),        t = I[x+1] - I[x-1]   (exact)
+        Dy = r[y+1] - r[y-1],   r = fma(I[x+1], s, fma(I[x], 2s, I[x-1] * s))
+    (cv2's scalar tail columns -- width mod SIMD width -- round differently; that is machine dependent)."""
+    h, w = img.shape
+    s = img.astype(f32)
+    ym, yp = reflect101(np.arange(h) - 1, h), reflect101(np.arange(h) + 1, h)
+    xm, xp = reflect101(np.arange(w) - 1, w), reflect101(np.arange(w) + 1, w)
+    s2 = f32(2) * scale
+    t = s[:, xp] - s[:, xm]
+    dx = _fma(t[ym] + t[yp], scale, t * s2)
+    r = _fma(s[:, xp], scale, _fma(s, s2, s[:, xm] * scale))
+    dy = r[yp] - r[ym]
+    return dx, dy
+
+
 def min_eig_map(img, block_size=3, gradient_size=3, harris=False, k=0.04):
     """cornerMinEigenVal / cornerHarris response, float32 (H,W)."""
     assert gradient_size == 3
     h, w = img.shape
     scale = f32(1.0 / ((1 << (gradient_size - 1)) * block_size * 255.0))
-    dx, dy = sobel3(img)
-    Dx = dx.astype(f32) * scale
-    Dy = dy.astype(f32) * scale
+    Dx, Dy = sobel3_f32(img, scale)
     cov = np.stack([Dx * Dx, Dx * Dy, Dy * Dy], -1).astype(np.float64)
     r = block_size // 2
     ys, xs = np.arange(h), np.arange(w)

@@ -299,6 +299,43 @@ def test_lk_batched_shared_grid_matches_single(batch, seq1080):
     assert flow.norm(dim=-1).mean().item() > 1.0
 
 
+@pytest.mark.skipif(not have_cv2(), reason="cv2 wheel not importable on this box")
+@pytest.mark.parametrize("seed", [1000, 1001, 1002, 1003])
+def test_config1_sparse_720p_vs_live_cv2(b2, seed):
+    """BASELINE configs[1]: SparseOF goodFeaturesToTrack + pyramidal LK on synthetic 1280x720 pairs vs cv2
+    (reference params, all-255 mask and disc mask, dense stress case, forward+backward LK, viewer grid)."""
+    import cv2
+    from hackathonopticalflow_b200 import pathfinder, synth
+    from oracle import cv2_reference as ref
+    fr = synth.sequence(720, 1280, 2, seed=seed)
+    g0, g1 = fr[0], fr[1]
+    full = np.full_like(g0, 255)
+    p0 = cv2.goodFeaturesToTrack(g0, mask=full, **GFTT)
+    m0 = b2.goodFeaturesToTrack(g0, mask=full, **GFTT)
+    assert p0 is not None and np.array_equal(p0, m0)
+    disc = ref.track_mask(g1.shape, p0.reshape(-1, 2))                       # SparseOF.py:61-66
+    a, c = cv2.goodFeaturesToTrack(g1, mask=disc, **GFTT), b2.goodFeaturesToTrack(g1, mask=disc, **GFTT)
+    assert (a is None and c is None) or np.array_equal(a, c)
+    a = cv2.goodFeaturesToTrack(g0, 500, 0.01, 5, blockSize=3)
+    c = b2.goodFeaturesToTrack(g0, 500, 0.01, 5, blockSize=3)
+    common = len(set(map(tuple, a.reshape(-1, 2))) & set(map(tuple, c.reshape(-1, 2))))
+    assert common >= 0.995 * len(a)                                          # near-tie order may differ (DESIGN.md)
+    # forward + backward LK with SparseOF.py:6-8 parameters on the detected corners
+    r1 = cv2.calcOpticalFlowPyrLK(g0, g1, p0, None, **LK_TRACK)
+    m1 = b2.calcOpticalFlowPyrLK(g0, g1, p0, None, **LK_TRACK)
+    _lk_check(m1, r1[0], r1[1], r1[2])
+    r0 = cv2.calcOpticalFlowPyrLK(g1, g0, r1[0], None, **LK_TRACK)
+    m0r = b2.calcOpticalFlowPyrLK(g1, g0, m1[0], None, **LK_TRACK)
+    good_r = np.abs(p0 - r0[0]).reshape(-1, 2).max(-1) < 1
+    good_m = np.abs(p0 - m0r[0]).reshape(-1, 2).max(-1) < 1
+    assert (good_r == good_m).mean() >= LK_STATUS_TOL
+    # the viewer's 45x45 LK on the 1008-point grid
+    pts = pathfinder.grid_points(1280, 720, 30)
+    assert len(pts) == 1008
+    rg = cv2.calcOpticalFlowPyrLK(g1, g0, pts, None, **LK_GRID)
+    _lk_check(b2.calcOpticalFlowPyrLK(g1, g0, pts, None, **LK_GRID), rg[0], rg[1], rg[2])
+
+
 # ------------------------------------------------------------------ K7-K9 GFTT
 @pytest.mark.parametrize("i", range(4))
 def test_gftt_golden_exact(b2, crops, i):
