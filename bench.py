@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 H, W = 1080, 1920
 PAIRS_PER_GPU = 64          # pairs per step per GPU (65 frames = 135 MB of input, > L2)
 CHUNK_PAIRS = 64            # pairs in flight per pass inside the engine (13 GB of scratch)
-E2E_PAIRS = 32              # pairs per end-to-end step (68 MB H2D, 531 MB D2H)
+E2E_PAIRS = 64              # pairs per end-to-end step (135 MB H2D, 1062 MB D2H)
 PARAMS = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)  # DenseOF.py:127-128
 WORKLOAD = "configs[2]: DenseOF Farneback on synthetic 1920x1080 frame-pair batches, reference parameters"
 

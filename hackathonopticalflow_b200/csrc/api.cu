@@ -1,6 +1,7 @@
 // extern "C" surface of libb2of.so (see include/b2of.h) plus the host-buffer entry points that give the
 // cv2-call contract (host arrays in, host arrays out).
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -266,7 +267,8 @@ static int farneback_host_pipeline(const uint8_t* prev, const uint8_t* next, siz
   std::lock_guard<std::mutex> lock(c->mu);
   if ((rc = c->init())) return rc;
   const size_t frame = (size_t)rows * cols, flow_pair = frame * 2 * sizeof(float);
-  int chunk = n_pairs < 8 ? n_pairs : 8;
+  static const int host_chunk = [] { const char* e = getenv("B2OF_HOST_CHUNK"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : v; }();
+  int chunk = n_pairs < host_chunk ? n_pairs : host_chunk;
   const int fpc = shared ? chunk + 1 : 2 * chunk;   // device frames per chunk
   size_t ws_bytes = b2of_farneback_workspace_bytes(rows, cols, p, chunk, shared);
   if ((rc = c->ws.ensure(ws_bytes))) return rc;
