@@ -821,7 +821,8 @@ __global__ void __launch_bounds__(NT, CT == 0 ? 1 : (NT == 256 ? 4 : NT == 320 ?
   const int ty = t / E, ix = t - ty * E;
   const int x = clampi(x0 - m + ix, 0, w - 1);
   const float xf = (float)x;
-  const bool xb_border = x < 5 || x >= w - 5;
+  // cv2's own test, unsigned wrap-around included (it misfires when a dimension is below 10 px; kept for parity)
+  const bool xb_border = (unsigned)(x - 5) >= (unsigned)(w - 10);
   const float bwx = border_w(x, w);
   int uxa = 0, uxb = 0;
   float ufx = 0.f;
@@ -913,7 +914,7 @@ __global__ void __launch_bounds__(NT, CT == 0 ? 1 : (NT == 256 ? 4 : NT == 320 ?
           r3 = (q.y - r3) * 0.5f;
           r2 += r4 * d.y + r6 * d.x;
           r3 += r6 * d.y + r5 * d.x;
-          if (xb_border || y < 5 || y >= h - 5) {
+          if (xb_border || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
             float s = bwx * border_w(y, h);
             r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
           }

@@ -220,6 +220,10 @@ def update_matrices(R0, R1, flow):
         sy[i] *= BORDER[i]
         sy[h - 1 - i] *= BORDER[i]
     s = sy[:, None] * sx[None, :]
+    # optflowgf.cpp gates the attenuation with unsigned comparisons that wrap when a dimension is below 10 px
+    u32 = lambda v: np.asarray(v, np.int64) & 0xFFFFFFFF
+    gate = (u32(np.arange(w) - 5) >= u32(w - 10))[None, :] | (u32(np.arange(h) - 5) >= u32(h - 10))[:, None]
+    s = np.where(gate, s, f32(1))
     r2, r3, r4, r5, r6 = r2 * s, r3 * s, r4 * s, r5 * s, r6 * s
     M = np.empty((h, w, 5), f32)
     M[..., 0] = r4 * r4 + r6 * r6

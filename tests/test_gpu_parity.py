@@ -137,6 +137,19 @@ def test_farneback_parameter_sets_golden_and_oracle(b2, synth_small, name):
     assert mean <= 1e-4 and mx <= 1e-2, (name, "oracle", mean, mx)
 
 
+@pytest.mark.parametrize("h,w", [(8, 8), (6, 40), (9, 30), (20, 30), (33, 65), (57, 57), (113, 71)])
+def test_farneback_tiny_and_ragged_sizes_vs_oracle(b2, h, w):
+    """Edge sizes: below the 32-px pyramid cut-off, below the 10-px border band (cv2's unsigned gate), odd sizes."""
+    from oracle import farneback as ofb
+    rng = np.random.default_rng(h * 131 + w)
+    a = (np.kron(rng.random((h // 4 + 1, w // 4 + 1)), np.ones((4, 4)))[:h, :w] * 200 + 20).astype(np.uint8)
+    b = np.roll(a, 1, axis=1)
+    for args in [REF_FB, (0.5, 1, 5, 1, 7, 1.5, 0), (0.7, 4, 9, 2, 5, 1.1, 256)]:
+        got = b2.calcOpticalFlowFarneback(a, b, None, *args)
+        mean, mx = epe(got, ofb.farneback(a, b, None, *args))
+        assert mean <= 1e-4 and mx <= 1e-2, (h, w, args, mean, mx)
+
+
 def test_farneback_returns_passed_buffer(b2, synth_small):
     buf = np.zeros((135, 241, 2), np.float32)
     out = b2.calcOpticalFlowFarneback(synth_small["f0"], synth_small["f1"], buf, *REF_FB)
