@@ -200,6 +200,18 @@ def pathfinder_filter(pts, next_pts, width, height):
     return out
 
 
+def flow_sample(flow, pts):
+    """float32 (B,H,W,2) dense flow + grid float32 (N,2) or (B,N,2) -> next_pts float32 (B,N,2) = pts + flow at pts."""
+    b, h, w_, _ = flow.shape
+    shared = pts.dim() == 2
+    n = pts.shape[-2]
+    nxt = torch.empty((b, n, 2), dtype=torch.float32, device=flow.device)
+    with torch.cuda.device(flow.device):
+        _lib.check(_lib.lib().b2of_flow_sample_dev(_p(flow), b, h, w_, _p(pts), 0 if shared else n, n, _p(nxt),
+                                                   _stream()))
+    return nxt
+
+
 def flow_stats(flow):
     """float32 (B,H,W,2) -> float32 (B,8): mean|flow|, max|flow|, mean dx, mean dy, 0, 0, 0, 0 (deterministic)."""
     b, h, w, _ = flow.shape

@@ -63,6 +63,7 @@ int gftt_dev(const uint8_t*, const uint8_t*, size_t, size_t, int, int, int, cons
 int pathfinder_filter_dev(const float*, size_t, const float*, int, int, int, int, int32_t*, int32_t*, uint8_t*,
                           uint8_t*, int32_t*, float*, cudaStream_t);
 int flow_stats_dev(const float*, int, int, int, float*, cudaStream_t);
+int flow_sample_dev(const float*, int, int, int, const float*, size_t, int, float*, cudaStream_t);
 
 // ----------------------------------------------------------------------------------------------
 // host-call context: one per device, grow-only device buffers + non-blocking streams.
@@ -305,6 +306,12 @@ static int farneback_host_pipeline(const uint8_t* prev, const uint8_t* next, siz
           return rc;
       }
     }
+    if (p->flags & B2OF_OPTFLOW_USE_INITIAL_FLOW) {
+      // the caller's flow array is the initial estimate: it must be on the device before the pass, and the
+      // previous D2H out of this slot must have drained
+      if (ci >= 2) B2OF_CUDA(cudaStreamWaitEvent(s_in, c->ev[4 + b], 0));
+      B2OF_CUDA(cudaMemcpyAsync(dout, flow + (size_t)p0 * frame * 2, flow_pair * np, cudaMemcpyHostToDevice, s_in));
+    }
     B2OF_CUDA(cudaEventRecord(c->ev[b], s_in));
     B2OF_CUDA(cudaStreamWaitEvent(s_c, c->ev[b], 0));
     if (ci >= 2) B2OF_CUDA(cudaStreamWaitEvent(s_c, c->ev[4 + b], 0));  // previous output in this slot drained
@@ -442,6 +449,11 @@ int b2of_pathfinder_filter_dev(const float* pts, size_t pts_batch_stride, const 
                                uint8_t* mask, int32_t* n_kept, float* stats, void* stream) {
   return pathfinder_filter_dev(pts, pts_batch_stride, next_pts, n_pts, batch, width, height, kept_pts, kept_flow,
                                danger_v, mask, n_kept, stats, (cudaStream_t)stream);
+}
+
+int b2of_flow_sample_dev(const float* flow, int n_pairs, int rows, int cols, const float* pts, size_t pts_batch_stride,
+                         int n_pts, float* next_pts, void* stream) {
+  return flow_sample_dev(flow, n_pairs, rows, cols, pts, pts_batch_stride, n_pts, next_pts, (cudaStream_t)stream);
 }
 
 int b2of_flow_stats_dev(const float* flow, int n_pairs, int rows, int cols, float* stats, void* stream) {

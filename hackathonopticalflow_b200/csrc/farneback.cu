@@ -52,6 +52,10 @@ struct FbPlan {
   std::vector<FbLevel> lv;  // coarsest first
   PolyConst pc;
   float* gauss_taps;  // winsize/2+1 taps for the FARNEBACK_GAUSSIAN window (device)
+  // OPTFLOW_USE_INITIAL_FLOW: INTER_AREA decimation tables full-res -> coarsest level (device, CSR form)
+  int *ax_start, *ax_src, *ay_start, *ay_src;
+  float *ax_alpha, *ay_alpha;
+  int area_fast, area_sx, area_sy;   // exact integer factors: plain block average
   void* table_block;
   size_t S;  // sum of h*pitch over levels (floats per plane per frame)
 };
@@ -290,6 +294,35 @@ static int build_plan(int rows, int cols, const b2of_farneback_params& p, FbPlan
     for (int i = 0; i <= m; ++i) gk[i] = gk[i] * s;
   }
   size_t gk_off = put(gk.data(), gk.size() * 4);
+  // INTER_AREA tables (cv::computeResizeAreaTab) from the full-resolution flow to the coarsest level
+  auto area_tab = [](int ssize, int dsize, std::vector<int>& start, std::vector<int>& src, std::vector<float>& alpha) {
+    double scale = (double)ssize / dsize;
+    start.assign(1, 0); src.clear(); alpha.clear();
+    for (int dx = 0; dx < dsize; ++dx) {
+      double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+      double cell = std::min(scale, ssize - fsx1);
+      int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+      sx2 = std::min(sx2, ssize - 1);
+      sx1 = std::min(sx1, sx2);
+      if (sx1 - fsx1 > 1e-3) { src.push_back(sx1 - 1); alpha.push_back((float)((sx1 - fsx1) / cell)); }
+      for (int sx = sx1; sx < sx2; ++sx) { src.push_back(sx); alpha.push_back((float)(1.0 / cell)); }
+      if (fsx2 - sx2 > 1e-3) { src.push_back(sx2); alpha.push_back((float)(std::min(std::min(fsx2 - sx2, 1.), cell) / cell)); }
+      start.push_back((int)src.size());
+    }
+  };
+  std::vector<int> axs, axi, ays, ayi;
+  std::vector<float> axa, aya;
+  const FbLevel& C0 = pl->lv[0];
+  area_tab(cols, C0.w, axs, axi, axa);
+  area_tab(rows, C0.h, ays, ayi, aya);
+  {
+    double scx = (double)cols / C0.w, scy = (double)rows / C0.h;
+    int ix = (int)nearbyint(scx), iy = (int)nearbyint(scy);
+    pl->area_fast = fabs(scx - ix) < 2.220446049250313e-16 && fabs(scy - iy) < 2.220446049250313e-16;
+    pl->area_sx = ix; pl->area_sy = iy;
+  }
+  size_t o_axs = put(axs.data(), axs.size() * 4), o_axi = put(axi.data(), axi.size() * 4 + 4), o_axa = put(axa.data(), axa.size() * 4 + 4);
+  size_t o_ays = put(ays.data(), ays.size() * 4), o_ayi = put(ayi.data(), ayi.size() * 4 + 4), o_aya = put(aya.data(), aya.size() * 4 + 4);
   cudaError_t e = cudaMalloc(&pl->table_block, host.size());
   if (e != cudaSuccess) { delete pl; return fail(B2OF_E_NOMEM, "cudaMalloc(plan tables) failed: %s", cudaGetErrorString(e)); }
   e = cudaMemcpy(pl->table_block, host.data(), host.size(), cudaMemcpyHostToDevice);
@@ -306,6 +339,8 @@ static int build_plan(int rows, int cols, const b2of_farneback_params& p, FbPlan
     }
   }
   pl->gauss_taps = (float*)(base + gk_off);
+  pl->ax_start = (int*)(base + o_axs); pl->ax_src = (int*)(base + o_axi); pl->ax_alpha = (float*)(base + o_axa);
+  pl->ay_start = (int*)(base + o_ays); pl->ay_src = (int*)(base + o_ayi); pl->ay_alpha = (float*)(base + o_aya);
   poly_constants(p.poly_n, p.poly_sigma, pl->pc);
   *out = pl;
   return B2OF_OK;
@@ -1071,6 +1106,42 @@ __global__ void __launch_bounds__(NT, CT == 0 ? 1 : (NT == 256 ? 4 : NT == 320 ?
 }
 
 // ----------------------------------------------------------------------------------------------
+// OPTFLOW_USE_INITIAL_FLOW: flow_coarsest = resize(flow0, INTER_AREA) * scale   (optflowgf.cpp, first level)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fb_initflow_area(const float2* __restrict__ flow0, int W, size_t pair_stride,
+                                                         float2* __restrict__ out, int w, int h, int pitch,
+                                                         size_t out_pair_stride, const int* __restrict__ xs,
+                                                         const int* __restrict__ xi, const float* __restrict__ xa,
+                                                         const int* __restrict__ ys, const int* __restrict__ yi,
+                                                         const float* __restrict__ ya, int fast, int sx, int sy,
+                                                         float mult) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  const float2* f = flow0 + blockIdx.z * pair_stride;
+  float ax = 0.f, ay = 0.f;
+  if (fast) {   // ResizeAreaFast: plain sum of the sx*sy block in row-major order, then * 1/area
+    for (int j = 0; j < sy; ++j)
+      for (int i = 0; i < sx; ++i) {
+        float2 v = f[(size_t)(y * sy + j) * W + x * sx + i];
+        ax += v.x; ay += v.y;
+      }
+    float sc = 1.f / (float)(sx * sy);
+    ax *= sc; ay *= sc;
+  } else {      // ResizeArea: rows weighted by beta, columns by alpha, float accumulation
+    for (int j = ys[y]; j < ys[y + 1]; ++j) {
+      const float2* row = f + (size_t)yi[j] * W;
+      float rx = 0.f, ry = 0.f;
+      for (int i = xs[x]; i < xs[x + 1]; ++i) {
+        float2 v = row[xi[i]];
+        rx = fmaf(v.x, xa[i], rx); ry = fmaf(v.y, xa[i], ry);
+      }
+      ax = fmaf(ya[j], rx, ax); ay = fmaf(ya[j], ry, ay);
+    }
+  }
+  out[blockIdx.z * out_pair_stride + (size_t)y * pitch + x] = make_float2(ax * mult, ay * mult);
+}
+
+// ----------------------------------------------------------------------------------------------
 // host driver
 // ----------------------------------------------------------------------------------------------
 struct FbWorkspace {
@@ -1104,8 +1175,6 @@ static int check_params(int rows, int cols, const b2of_farneback_params* p) {
   B2OF_ASSERT(p->iterations >= 0, fn);
   B2OF_ASSERT(p->poly_n >= 1, fn);
   if (p->poly_n > FB_MAX_POLY_N) return fail(B2OF_E_UNSUPPORTED, "poly_n > %d is not supported", FB_MAX_POLY_N);
-  if (p->flags & B2OF_OPTFLOW_USE_INITIAL_FLOW)
-    return fail(B2OF_E_UNSUPPORTED, "OPTFLOW_USE_INITIAL_FLOW is not supported yet (not used by the reference)");
   if (p->winsize / 2 > 45) return fail(B2OF_E_UNSUPPORTED, "winsize > 91 is not supported");
   return B2OF_OK;
 }
@@ -1214,8 +1283,9 @@ static void set_func_attrs() {
 
 // iterations for `pairs` pairs whose frames sit in workspace slots (pair p -> slots p*fstep, p*fstep+1)
 static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fstep, int total_slots, float* flow_out,
-                    cudaStream_t st) {
-  const b2of_farneback_params& p = pl->p;
+                    const b2of_farneback_params& p, cudaStream_t st) {
+  // `p` is THIS call's parameter block: the cached plan only fixes what its key holds (sizes, windows, taps)
+  const int call_flags = p.flags;
   const int m = p.winsize / 2;
   const bool gauss = (p.flags & B2OF_OPTFLOW_FARNEBACK_GAUSSIAN) != 0;
   // tile: the specialised kernel for the reference's window, else the largest tile whose halo fits one SM
@@ -1276,7 +1346,18 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
     }
     for (int it = 0; it < iters; ++it) {
       if (it == 0) {
-        if (coarse) {
+        if (!coarse && (call_flags & B2OF_OPTFLOW_USE_INITIAL_FLOW)) {   // per call: the plan is shared
+          // initial flow of every pair sits in the caller's output buffer: area-resize it into the pong buffer
+          dim3 gi(cdiv(L.w, 256), L.h, pairs);
+          fb_initflow_area<<<gi, 256, 0, st>>>((const float2*)flow_out, pl->cols, (size_t)pl->cols * pl->rows, B, L.w,
+                                               L.h, L.pitch, plane, pl->ax_start, pl->ax_src, pl->ax_alpha,
+                                               pl->ay_start, pl->ay_src, pl->ay_alpha,
+                                               (L.w == pl->cols && L.h == pl->rows) ? 1 : pl->area_fast,
+                                               (L.w == pl->cols && L.h == pl->rows) ? 1 : pl->area_sx,
+                                               (L.w == pl->cols && L.h == pl->rows) ? 1 : pl->area_sy, (float)L.scale);
+          B2OF_LAUNCH_CHECK();
+          a.mode = 1; a.flow_in = B; a.flow_in_pair_stride = plane; a.in_pitch = L.pitch;
+        } else if (coarse) {
           a.mode = 2; a.flow_in = coarse; a.flow_in_pair_stride = cstride; a.in_pitch = cpitch; a.cw = cw; a.ch = ch;
         } else {
           a.mode = 0; a.flow_in = nullptr;
@@ -1364,7 +1445,7 @@ int farneback_dev(const uint8_t* prev, const uint8_t* next, size_t step, size_t 
       rc = fb_frames(pl, ws, next + (size_t)p0 * frame_stride, step, frame_stride, np, 1, 2, frames, st);
       if (rc) return rc;
     }
-    rc = fb_pairs(pl, ws, np, shared ? 1 : 2, frames, flow + (size_t)p0 * flow_pair, st);
+    rc = fb_pairs(pl, ws, np, shared ? 1 : 2, frames, flow + (size_t)p0 * flow_pair, *p, st);
     if (rc) return rc;
   }
   return B2OF_OK;

@@ -176,6 +176,33 @@ int pathfinder_filter_dev(const float* pts, size_t pts_bstride, const float* nex
   return B2OF_OK;
 }
 
+// ---- dense flow sampled on the measurement grid (what draw_flow does on its 14-px grid,
+// DenseOF.py:44-50): next_pts = pts + flow[int(y), int(x)], ready for pathfinder_filter in place of the LK result ----
+__global__ void __launch_bounds__(256) flow_sample_grid(const float2* __restrict__ flow, int rows, int cols,
+                                                         const float* __restrict__ pts, size_t pts_bstride, int n,
+                                                         float* __restrict__ next_pts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i >= n) return;
+  const float* P = pts + (size_t)b * pts_bstride * 2;
+  float x = P[2 * i], y = P[2 * i + 1];
+  int xi = clampi((int)x, 0, cols - 1), yi = clampi((int)y, 0, rows - 1);
+  float2 f = flow[(size_t)b * rows * cols + (size_t)yi * cols + xi];
+  next_pts[((size_t)b * n + i) * 2] = x + f.x;
+  next_pts[((size_t)b * n + i) * 2 + 1] = y + f.y;
+}
+
+int flow_sample_dev(const float* flow, int n_pairs, int rows, int cols, const float* pts, size_t pts_bstride, int n_pts,
+                    float* next_pts, cudaStream_t st) {
+  const char* fn = "flow_sample";
+  B2OF_ASSERT(n_pairs >= 0 && rows > 0 && cols > 0 && n_pts >= 0, fn);
+  if (n_pairs == 0 || n_pts == 0) return B2OF_OK;
+  B2OF_ASSERT(flow != nullptr && pts != nullptr && next_pts != nullptr, fn);
+  flow_sample_grid<<<dim3(cdiv(n_pts, 256), n_pairs), 256, 0, st>>>((const float2*)flow, rows, cols, pts, pts_bstride,
+                                                                   n_pts, next_pts);
+  B2OF_LAUNCH_CHECK();
+  return B2OF_OK;
+}
+
 // ---- dense flow statistics: deterministic fixed-point accumulation, then finalize in place ----
 // scratch layout inside the 8-float stats row: [0:2) u64 sum|f| (Q20), [2:4) i64 sum dx, [4:6) i64 sum dy, [6] max bits
 __global__ void __launch_bounds__(256) flow_stats_accum(const float2* __restrict__ flow, size_t n_px,

@@ -68,4 +68,9 @@ class PathfinderPipeline:
         if self.dense is not None:
             out["flow"] = self.dense.flow_sequence(gray)
             out["flow_stats"] = batch.flow_stats(out["flow"])
+            # the same vector filter / danger points driven by the dense field sampled on the grid.
+            # The viewer tracks current -> previous; the dense field is previous -> current, hence the sign.
+            back = self.points[None] - (batch.flow_sample(out["flow"], self.points) - self.points[None])
+            dense_out = batch.pathfinder_filter(self.points, back.contiguous(), self.w, self.h)
+            out.update({"dense_" + k: v for k, v in dense_out.items()})
         return out

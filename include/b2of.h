@@ -178,6 +178,12 @@ int b2of_pathfinder_filter_dev(const float* pts_dev, size_t pts_batch_stride, co
                                uint8_t* danger_v_dev, uint8_t* mask_dev, int32_t* n_kept_dev, float* stats_dev,
                                void* stream);
 
+/* dense flow sampled on a point set (the grid): next_pts[b][i] = pts[i] + flow[b][int(y_i)][int(x_i)], float32
+ * (batch, n_pts, 2) -- feeds b2of_pathfinder_filter_dev with the dense field instead of LK (what draw_flow samples,
+ * DenseOF.py:44-50).  pts_batch_stride (in points) may be 0 for one shared grid. */
+int b2of_flow_sample_dev(const float* flow_dev, int n_pairs, int rows, int cols, const float* pts_dev,
+                         size_t pts_batch_stride, int n_pts, float* next_pts_dev, void* stream);
+
 /* dense-flow statistics (what draw_flow / draw_hsv consume, DenseOF.py:44-50, :113-121):
  * per pair float32[8]: mean|flow|, max|flow|, mean dx, mean dy, 0, 0, 0, 0 */
 int b2of_flow_stats_dev(const float* flow_dev, int n_pairs, int rows, int cols, float* stats_dev, void* stream);

@@ -150,17 +150,47 @@ def test_farneback_tiny_and_ragged_sizes_vs_oracle(b2, h, w):
         assert mean <= 1e-4 and mx <= 1e-2, (h, w, args, mean, mx)
 
 
+def test_farneback_iterations_are_per_call_not_cached(b2, synth_small):
+    """Same image size and windows, different `iterations` back to back (the level plan is cached per size)."""
+    from oracle import farneback as ofb
+    f0, f1 = synth_small["f0"], synth_small["f1"]
+    for iters in (3, 1, 2, 3):
+        got = b2.calcOpticalFlowFarneback(f0, f1, None, 0.5, 3, 15, iters, 5, 1.2, 0)
+        mean, mx = epe(got, ofb.farneback(f0, f1, None, 0.5, 3, 15, iters, 5, 1.2, 0))
+        assert mean <= 1e-4 and mx <= 1e-2, (iters, mean, mx)
+
+
 def test_farneback_returns_passed_buffer(b2, synth_small):
     buf = np.zeros((135, 241, 2), np.float32)
     out = b2.calcOpticalFlowFarneback(synth_small["f0"], synth_small["f1"], buf, *REF_FB)
     assert out is buf and np.abs(buf).max() > 0
 
 
+@pytest.mark.skipif(not have_cv2(), reason="cv2 wheel not importable on this box")
+def test_farneback_use_initial_flow_vs_cv2(b2, synth_small, crops):
+    """OPTFLOW_USE_INITIAL_FLOW: the passed flow is area-resized to the coarsest level as the start.
+    135x241 -> 17x30 is a non-integer factor (general INTER_AREA), 360x640 -> 45x80 an exact factor 8 (fast path)."""
+    import cv2
+    for a, b_ in ((synth_small["f0"], synth_small["f1"]), (crops["gray0_1"], crops["gray1_1"])):
+        start = cv2.calcOpticalFlowFarneback(a, b_, None, 0.5, 3, 15, 1, 5, 1.2, 0)
+        for levels in (3, 0):
+            ref = cv2.calcOpticalFlowFarneback(a, b_, start.copy(), 0.5, levels, 15, 2, 5, 1.2, 4)
+            buf = start.copy()
+            got = b2.calcOpticalFlowFarneback(a, b_, buf, 0.5, levels, 15, 2, 5, 1.2, b2.OPTFLOW_USE_INITIAL_FLOW)
+            assert got is buf
+            mean, mx = epe(got, ref)
+            assert mean <= 1e-3 and mx <= 0.1, (a.shape, levels, mean, mx)
+        # and it must differ from a cold start (the flag is not silently ignored)
+        cold = b2.calcOpticalFlowFarneback(a, b_, None, 0.5, 3, 15, 2, 5, 1.2, 0)
+        assert epe(got, cold)[1] > 1e-4
+
+
 def test_farneback_loud_on_unsupported(b2, synth_small):
     from hackathonopticalflow_b200 import error
     with pytest.raises(error):
-        b2.calcOpticalFlowFarneback(synth_small["f0"], synth_small["f1"],
-                                    np.zeros((135, 241, 2), np.float32), 0.5, 3, 15, 3, 5, 1.2, 4)
+        b2.calcOpticalFlowFarneback(synth_small["f0"], synth_small["f1"], None, 0.5, 3, 15, 3, 40, 1.2, 0)  # poly_n > 16
+    with pytest.raises(error):
+        b2.calcOpticalFlowFarneback(synth_small["f0"], synth_small["f1"], None, 0.5, 3, 15, 3, 5, 1.2, 4)   # no flow0
 
 
 @pytest.fixture(scope="module")
@@ -435,6 +465,32 @@ def test_full_pipeline_4k_config5(batch):
     # gray is the bit-exact luma
     want = synth.to_gray(bgr[1].cpu().numpy())
     assert np.array_equal(out["gray"][1].cpu().numpy(), want)
+
+
+def test_dense_flow_sampled_on_grid_feeds_the_filter(batch, seq1080):
+    """the dense field sampled on the viewer's grid drives the same filter; on the synthetic flight it
+    must pick (almost) the same danger points as the LK path."""
+    import torch
+    from hackathonopticalflow_b200 import pathfinder
+    from oracle import pathfinder as opf
+    frames = torch.from_numpy(seq1080[:3]).cuda()
+    eng = batch.FarnebackEngine(1080, 1920, chunk_pairs=2)
+    flow = eng.flow_sequence(frames)
+    pts_np = pathfinder.grid_points(1920, 1080, 30)
+    pts = torch.from_numpy(pts_np).cuda()
+    nxt = batch.flow_sample(flow, pts)
+    f = flow.cpu().numpy()
+    want = pts_np + f[0][pts_np[:, 1].astype(int), pts_np[:, 0].astype(int)]
+    assert np.array_equal(nxt[0].cpu().numpy(), want)
+    # filter on the sampled dense flow == reference restatement of the filter on the same vectors
+    out = batch.pathfinder_filter(pts, nxt, 1920, 1080)
+    flow_o, pts_o, mask_o, _ = opf.vector_filter(want, pts_np, 1920, 1080)
+    assert (out["mask"][0].cpu().numpy().astype(bool) == mask_o).mean() >= MASK_TOL
+    # and it selects nearly the same grid points as the LK-driven filter (both see the same motion)
+    lk, _, _ = batch.pyrlk(frames[:2].contiguous(), frames[1:3].contiguous(), pts, **batch.LK_GRID_DEFAULTS)
+    lk_mask = batch.pathfinder_filter(pts, lk, 1920, 1080)["mask"][0]
+    agree = (lk_mask == out["mask"][0]).float().mean().item()
+    assert agree > 0.9, agree
 
 
 def test_flow_stats_deterministic_and_correct(batch):
