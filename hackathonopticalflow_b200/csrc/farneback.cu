@@ -851,9 +851,14 @@ __global__ void __launch_bounds__(NT, CT == 0 ? 1 : (NT == 256 ? 4 : NT == 320 ?
   float2* __restrict__ fo = a.flow_out + (size_t)pair * a.flow_out_pair_stride;
   const int t = threadIdx.x;
 
-  // per-thread constants of step A: one halo column per thread
-  const int RP = NT / E;                      // row runs per tile (7 for E = 70)
-  const int ty = t / E, ix = t - ty * E;
+  // per-thread constants of step A: one halo column per thread.  The column -> lane map is padded on the left so
+  // that lane 0 of every warp sits on an 8-pixel boundary of the image (x0 is a multiple of 8 for T % 8 == 0):
+  // the streamed float4 / float2 / float row loads then fall on whole 128-byte lines (4 wavefronts instead of ~7.5).
+  const int PADL = (8 - (m & 7)) & 7;         // 1 for m = 7
+  const int EW = (E + PADL + 7) & ~7;         // padded columns per row run (72 for E = 70)
+  const int RP = NT / EW;                     // row runs per tile (7)
+  const int ty0 = t / EW, ix = t - ty0 * EW - PADL;
+  const int ty = (ix >= 0 && ix < E) ? ty0 : RP;   // padding lanes sit step A out
   const int x = clampi(x0 - m + ix, 0, w - 1);
   const float xf = (float)x;
   // cv2's own test, unsigned wrap-around included (it misfires when a dimension is below 10 px; kept for parity)
