@@ -830,7 +830,7 @@ __device__ __forceinline__ float2 fetch_flow_m(const IterArgs& a, const float2* 
 }
 
 template <int NT, int CT, int CM, bool GAUSS, int MODE>
-__global__ void __launch_bounds__(NT, CT == 0 ? 1 : (NT == 256 ? 4 : NT == 320 ? 3 : NT == 512 ? 2 : 1)) fb_iter(IterArgs a) {
+__global__ void __launch_bounds__(NT, CT ? 2 : 1) fb_iter(IterArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int T = CT ? CT : a.tile;
   const int m = CT ? CM : a.m;
@@ -1273,12 +1273,7 @@ static void set_func_attrs() {
   cudaFuncSetAttribute(fb_iter<NT_, CT_, CM_, G_, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);    \
   cudaFuncSetAttribute(fb_iter<NT_, CT_, CM_, G_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);    \
   cudaFuncSetAttribute(fb_iter<NT_, CT_, CM_, G_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  B2OF_ATTR(512, 56, 7, false)
-  B2OF_ATTR(1024, 88, 7, false)
-  B2OF_ATTR(512, 48, 7, false)
-  B2OF_ATTR(256, 32, 7, false)
-  B2OF_ATTR(320, 40, 7, false)
-  B2OF_ATTR(512, 64, 7, false)
+  B2OF_ATTR(512, IT_T_FAST, 7, false)
   B2OF_ATTR(512, 0, 0, false)
   B2OF_ATTR(512, 0, 0, true)
 #undef B2OF_ATTR
@@ -1295,13 +1290,7 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
   const bool gauss = (p.flags & B2OF_OPTFLOW_FARNEBACK_GAUSSIAN) != 0;
   // tile: the specialised kernel for the reference's window, else the largest tile whose halo fits one SM
   const bool fast = !gauss && m == 7;
-  static const int fast_tile = [] {
-    const char* e = getenv("B2OF_ITER_TILE");   // 56 (2 CTAs/SM x 512 threads) or 88 (1 CTA/SM x 1024 threads)
-    int v = e ? atoi(e) : 56;
-    return (v == 88 || v == 48 || v == 64 || v == 32 || v == 40) ? v : 56;
-  }();
-  int tile = fast_tile;
-  const int nthreads = (fast && fast_tile == 88) ? 1024 : IT_THREADS;
+  int tile = IT_T_FAST;
   if (!fast) {
     tile = 64;
     while (tile > 16 && (size_t)5 * (tile + 2 * m) * ((tile + 2 * m) | 1) * sizeof(float) > 200 * 1024) tile -= 8;
@@ -1338,7 +1327,7 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
     // vertical streaming: as many tiles per CTA as still leaves >= ~4 waves of CTAs
     const int cx = cdiv(L.w, tile), cy = cdiv(L.h, tile);
     int nb = (int)(((long long)cx * cy * pairs) / (4 * 296));
-    static const int nb_cap = [] { const char* e = getenv("B2OF_ITER_NB"); return e ? atoi(e) : 8; }();
+    const int nb_cap = 8;
     nb = nb < 1 ? 1 : (nb > nb_cap ? nb_cap : nb);
     nb = cdiv(cy, cdiv(cy, nb));                 // balance the row groups
     a.nb = nb;
@@ -1392,12 +1381,7 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
     else if (a.mode == 1) fb_iter<NT_, CT_, CM_, G_, 1><<<grid, NT_, smem, st>>>(a);        \
     else fb_iter<NT_, CT_, CM_, G_, 2><<<grid, NT_, smem, st>>>(a);                         \
   } while (0)
-        if (fast && nthreads == 1024) B2OF_ITER_LAUNCH(1024, 88, 7, false);
-        else if (fast && tile == 48) B2OF_ITER_LAUNCH(512, 48, 7, false);
-        else if (fast && tile == 32) B2OF_ITER_LAUNCH(256, 32, 7, false);
-        else if (fast && tile == 40) B2OF_ITER_LAUNCH(320, 40, 7, false);
-        else if (fast && tile == 64) B2OF_ITER_LAUNCH(512, 64, 7, false);
-        else if (fast) B2OF_ITER_LAUNCH(512, 56, 7, false);
+        if (fast) B2OF_ITER_LAUNCH(512, IT_T_FAST, 7, false);
         else if (gauss) B2OF_ITER_LAUNCH(512, 0, 0, true);
         else B2OF_ITER_LAUNCH(512, 0, 0, false);
 #undef B2OF_ITER_LAUNCH
