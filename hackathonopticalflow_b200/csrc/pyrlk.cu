@@ -98,37 +98,79 @@ __device__ __forceinline__ int img_px(const uint8_t* img, size_t step, int w, in
   return img[(size_t)y * step + x];
 }
 
-// sum over the window of (bilinear(J) >> 9 - Iw) * {Ixw, Iyw}  (or |diff| when ABS)
+// Window walk shared by the passes below: element p = lane + 32*i of the ww x wh window sits at (x, y);
+// advancing by 32 elements is (dq rows, dr columns) with one carry.
+struct LkWalk {
+  int x, y, dq, dr, ww;
+  __device__ __forceinline__ LkWalk(int lane, int ww_) : ww(ww_) {
+    dq = 32 / ww_; dr = 32 - dq * ww_;
+    y = lane / ww_; x = lane - y * ww_;
+  }
+  __device__ __forceinline__ void next() {
+    x += dr; y += dq;
+    if (x >= ww) { x -= ww; ++y; }
+  }
+};
+
+// sum over the window of (bilinear(J) >> 9 - Iw) * {Ixw, Iyw}  (or |diff| when ABS).
+// Four window elements per lane are in flight at a time (16 independent byte loads), so the L1 latency of the
+// gathers overlaps instead of serialising one pixel after the other.
 template <bool ABS>
-__device__ __forceinline__ void lk_window_pass(const uint8_t* J, size_t step, int w, int h, int ix, int iy, int w00,
-                                               int w01, int w10, int w11, const short* sI, const short2* sD, int ww,
-                                               int wh, int lane, long long& o1, long long& o2) {
+__device__ __forceinline__ void lk_window_pass(const uint8_t* __restrict__ J, size_t step, int w, int h, int ix,
+                                               int iy, int w00, int w01, int w10, int w11, const short* sI,
+                                               const short2* sD, int ww, int wh, int lane, long long& o1,
+                                               long long& o2) {
   const bool inside = ix >= 0 && iy >= 0 && ix + ww < w && iy + wh < h;
   const int n = ww * wh;
   long long s1 = 0, s2 = 0;
   int a1 = 0, a2 = 0, cnt = 0;
-  int x = lane % ww, y = lane / ww;
-  for (int p = lane; p < n; p += 32) {
-    int gx = ix + x, gy = iy + y;
-    int v;
-    if (inside) {
-      const uint8_t* q = J + (size_t)gy * step + gx;
-      v = q[0] * w00 + q[1] * w01 + q[step] * w10 + q[step + 1] * w11;
-    } else {
-      v = img_px(J, step, w, h, gx, gy, false) * w00 + img_px(J, step, w, h, gx + 1, gy, false) * w01 +
-          img_px(J, step, w, h, gx, gy + 1, false) * w10 + img_px(J, step, w, h, gx + 1, gy + 1, false) * w11;
+  LkWalk wk(lane, ww);
+  if (inside) {
+    const uint8_t* base = J + (size_t)iy * step + ix;
+    for (int p = lane; p < n; p += 128) {
+      int v[4];
+      int pp[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        pp[k] = p + 32 * k;
+        v[k] = 0;
+        if (pp[k] < n) {
+          const uint8_t* q = base + (size_t)wk.y * step + wk.x;
+          v[k] = q[0] * w00 + q[1] * w01 + q[step] * w10 + q[step + 1] * w11;
+        }
+        wk.next();
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (pp[k] < n) {
+          int diff = ((v[k] + 256) >> 9) - (int)sI[pp[k]];
+          if (ABS) {
+            a1 += diff < 0 ? -diff : diff;
+          } else {
+            short2 d = sD[pp[k]];
+            a1 += diff * (int)d.x;
+            a2 += diff * (int)d.y;
+          }
+        }
+      }
+      if (++cnt == 8) { s1 += a1; s2 += a2; a1 = a2 = 0; cnt = 0; }   // 32 products per lane fit an int32
     }
-    int diff = ((v + 256) >> 9) - (int)sI[p];
-    if (ABS) {
-      a1 += diff < 0 ? -diff : diff;
-    } else {
-      short2 d = sD[p];
-      a1 += diff * (int)d.x;
-      a2 += diff * (int)d.y;
+  } else {
+    for (int p = lane; p < n; p += 32) {
+      int gx = ix + wk.x, gy = iy + wk.y;
+      int v = img_px(J, step, w, h, gx, gy, false) * w00 + img_px(J, step, w, h, gx + 1, gy, false) * w01 +
+              img_px(J, step, w, h, gx, gy + 1, false) * w10 + img_px(J, step, w, h, gx + 1, gy + 1, false) * w11;
+      int diff = ((v + 256) >> 9) - (int)sI[p];
+      if (ABS) {
+        a1 += diff < 0 ? -diff : diff;
+      } else {
+        short2 d = sD[p];
+        a1 += diff * (int)d.x;
+        a2 += diff * (int)d.y;
+      }
+      if (++cnt == 32) { s1 += a1; s2 += a2; a1 = a2 = 0; cnt = 0; }
+      wk.next();
     }
-    if (++cnt == 32) { s1 += a1; s2 += a2; a1 = a2 = 0; cnt = 0; }
-    x += 32;
-    while (x >= ww) { x -= ww; ++y; }
   }
   s1 += a1; s2 += a2;
   o1 = warp_sum_ll(s1);
@@ -188,40 +230,62 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_track(LkArgs a) {
     {
       const bool inside = ipx >= 0 && ipy >= 0 && ipx + ww < W && ipy + wh < H;
       int c11 = 0, c12 = 0, c22 = 0, cnt = 0;
-      int x = lane % ww, y = lane / ww;
+      LkWalk wk(lane, ww);
       __syncwarp();
-      for (int p = lane; p < n; p += 32) {
-        int gx = ipx + x, gy = ipy + y;
-        int iv, dxv, dyv;
-        if (inside) {
-          const uint8_t* q = I + (size_t)gy * step + gx;
-          iv = q[0] * w00 + q[1] * w01 + q[step] * w10 + q[step + 1] * w11;
-          const short2* dq = D + (size_t)gy * W + gx;
-          short2 d00 = dq[0], d01 = dq[1], d10 = dq[W], d11 = dq[W + 1];
-          dxv = d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11;
-          dyv = d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11;
-        } else {
-          iv = img_px(I, step, W, H, gx, gy, false) * w00 + img_px(I, step, W, H, gx + 1, gy, false) * w01 +
-               img_px(I, step, W, H, gx, gy + 1, false) * w10 + img_px(I, step, W, H, gx + 1, gy + 1, false) * w11;
-          dxv = dyv = 0;
+      if (inside) {
+        const uint8_t* ibase = I + (size_t)ipy * step + ipx;
+        const short2* dbase = D + (size_t)ipy * W + ipx;
+        for (int p = lane; p < n; p += 128) {
+          int iv[4], dxv[4], dyv[4], pp[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            pp[k] = p + 32 * k;
+            iv[k] = dxv[k] = dyv[k] = 0;
+            if (pp[k] < n) {
+              const uint8_t* q = ibase + (size_t)wk.y * step + wk.x;
+              iv[k] = q[0] * w00 + q[1] * w01 + q[step] * w10 + q[step + 1] * w11;
+              const short2* dq = dbase + (size_t)wk.y * W + wk.x;
+              short2 d00 = dq[0], d01 = dq[1], d10 = dq[W], d11 = dq[W + 1];
+              dxv[k] = d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11;
+              dyv[k] = d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11;
+            }
+            wk.next();
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (pp[k] < n) {
+              int ival = (iv[k] + 256) >> 9;
+              int ixv = (dxv[k] + 8192) >> 14, iyv = (dyv[k] + 8192) >> 14;
+              sI[pp[k]] = (short)ival;
+              sD[pp[k]] = make_short2((short)ixv, (short)iyv);
+              c11 += ixv * ixv; c12 += ixv * iyv; c22 += iyv * iyv;
+            }
+          }
+          if (++cnt == 8) { sA11 += c11; sA12 += c12; sA22 += c22; c11 = c12 = c22 = 0; cnt = 0; }
+        }
+      } else {
+        for (int p = lane; p < n; p += 32) {
+          int gx = ipx + wk.x, gy = ipy + wk.y;
+          int iv = img_px(I, step, W, H, gx, gy, false) * w00 + img_px(I, step, W, H, gx + 1, gy, false) * w01 +
+                   img_px(I, step, W, H, gx, gy + 1, false) * w10 + img_px(I, step, W, H, gx + 1, gy + 1, false) * w11;
+          int dxv = 0, dyv = 0;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             int xx = gx + (k & 1), yy = gy + (k >> 1);
-            int wk = k == 0 ? w00 : k == 1 ? w01 : k == 2 ? w10 : w11;
+            int wgt = k == 0 ? w00 : k == 1 ? w01 : k == 2 ? w10 : w11;
             if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
               short2 d = D[(size_t)yy * W + xx];
-              dxv += d.x * wk; dyv += d.y * wk;
+              dxv += d.x * wgt; dyv += d.y * wgt;
             }
           }
+          int ival = (iv + 256) >> 9;
+          int ixv = (dxv + 8192) >> 14, iyv = (dyv + 8192) >> 14;
+          sI[p] = (short)ival;
+          sD[p] = make_short2((short)ixv, (short)iyv);
+          c11 += ixv * ixv; c12 += ixv * iyv; c22 += iyv * iyv;
+          if (++cnt == 32) { sA11 += c11; sA12 += c12; sA22 += c22; c11 = c12 = c22 = 0; cnt = 0; }
+          wk.next();
         }
-        int ival = (iv + 256) >> 9;
-        int ixv = (dxv + 8192) >> 14, iyv = (dyv + 8192) >> 14;
-        sI[p] = (short)ival;
-        sD[p] = make_short2((short)ixv, (short)iyv);
-        c11 += ixv * ixv; c12 += ixv * iyv; c22 += iyv * iyv;
-        if (++cnt == 32) { sA11 += c11; sA12 += c12; sA22 += c22; c11 = c12 = c22 = 0; cnt = 0; }
-        x += 32;
-        while (x >= ww) { x -= ww; ++y; }
       }
       sA11 += c11; sA12 += c12; sA22 += c22;
       sA11 = warp_sum_ll(sA11); sA12 = warp_sum_ll(sA12); sA22 = warp_sum_ll(sA22);
