@@ -493,6 +493,30 @@ def test_dense_flow_sampled_on_grid_feeds_the_filter(batch, seq1080):
     assert agree > 0.9, agree
 
 
+def test_calls_are_safe_from_several_python_threads(b2, synth_small, crops):
+    """cv2 releases the GIL and is re-entrant; the drop-in must give the same answers when several
+    Python threads call it at once (host calls queue on the library's per-device context)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from hackathonopticalflow_b200 import pathfinder
+    f0, f1 = synth_small["f0"], synth_small["f1"]
+    g0, g1 = crops["gray0_0"], crops["gray1_0"]
+    pts = pathfinder.grid_points(640, 360, 30)
+    want_flow = b2.calcOpticalFlowFarneback(f0, f1, None, *REF_FB)
+    want_lk = b2.calcOpticalFlowPyrLK(g1, g0, pts, None, **LK_GRID)
+    want_c = b2.goodFeaturesToTrack(g0, mask=None, **GFTT)
+
+    def job(i):
+        if i % 3 == 0:
+            return np.array_equal(b2.calcOpticalFlowFarneback(f0, f1, None, *REF_FB), want_flow)
+        if i % 3 == 1:
+            r = b2.calcOpticalFlowPyrLK(g1, g0, pts, None, **LK_GRID)
+            return np.array_equal(r[0], want_lk[0]) and np.array_equal(r[1], want_lk[1])
+        return np.array_equal(b2.goodFeaturesToTrack(g0, mask=None, **GFTT), want_c)
+
+    with ThreadPoolExecutor(6) as ex:
+        assert all(ex.map(job, range(36)))
+
+
 def test_flow_stats_deterministic_and_correct(batch):
     import torch
     g = torch.Generator(device="cuda").manual_seed(1)
