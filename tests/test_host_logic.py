@@ -92,3 +92,40 @@ assert m == 2.0
                          capture_output=True, text=True, env=env, timeout=240)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "GATHER_OK" in res.stdout
+
+
+def test_sharded_pairs_with_halo_equal_serial_two_ranks_gloo(tmp_path):
+    """world_size 2 on CPU: each rank takes its frame shard (one-frame halo), computes a per-pair record with the
+    numpy oracle standing in for the GPU engine, rank 0 gathers; the result must equal the serial pass."""
+    script = tmp_path / "w2.py"
+    script.write_text(f"""
+import os, sys
+sys.path.insert(0, {ROOT!r})
+import numpy as np, torch
+from hackathonopticalflow_b200 import dist as d
+from oracle import farneback as ofb
+rank, world, _ = d.init_from_env("gloo")
+rng = np.random.default_rng(0)
+base = (np.kron(rng.random((12, 16)), np.ones((4, 4))) * 200 + 20).astype(np.uint8)     # 48 x 64
+frames = np.stack([np.roll(base, (t, 2 * t), axis=(0, 1)) for t in range(6)])             # 6 frames, 5 pairs
+def record(a, b):
+    f = ofb.farneback(a, b, None, 0.5, 1, 9, 1, 5, 1.1, 0)
+    m = np.sqrt((f ** 2).sum(-1))
+    return [m.mean(), m.max(), f[..., 0].mean(), f[..., 1].mean(), 0, 0, 0, 0]
+lo, hi, flo, fhi = d.shard(len(frames), rank, world)
+mine = frames[flo:fhi]                                     # includes the halo frame
+assert len(mine) == (hi - lo) + 1
+local = torch.tensor([record(mine[i], mine[i + 1]) for i in range(hi - lo)], dtype=torch.float32).reshape(-1, 8)
+out = d.gather_stats(local, len(frames), rank, world)
+if rank == 0:
+    serial = torch.tensor([record(frames[i], frames[i + 1]) for i in range(len(frames) - 1)], dtype=torch.float32)
+    assert out.shape == serial.shape and torch.equal(out, serial), (out, serial)
+    print("SHARD_OK")
+""")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    port = 31500 + os.getpid() % 2000
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "SHARD_OK" in res.stdout
