@@ -30,6 +30,23 @@ def shard(n_frames, rank, world):
     return lo, hi, lo, hi + 1
 
 
+def bind_to_local_numa(local_rank):
+    """Best effort: pin this process to the CPUs next to its GPU, so pinned host buffers and the copy threads sit
+    on the GPU's own NUMA node (matters for the end-to-end path when several ranks stream flow fields to the host)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return sorted(allowed)
+    except Exception:
+        return None
+
+
 def init_from_env(backend=None):
     """Initialise torch.distributed from torchrun's environment; returns (rank, world, local_rank)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -41,6 +58,7 @@ def init_from_env(backend=None):
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
+            bind_to_local_numa(local_rank)
             torch.cuda.set_device(local_rank)
             dist.init_process_group(backend, rank=rank, world_size=world,
                                     device_id=torch.device("cuda", local_rank))
