@@ -10,7 +10,8 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libb2of.so")
+# B2OF_LIB: developer override used by scripts/ab_variants.py to A/B alternative builds of the same sources
+LIB_PATH = os.environ.get("B2OF_LIB") or os.path.join(CSRC, "libb2of.so")
 SOURCES = ["api.cu", "gray_pyr.cu", "farneback.cu", "pyrlk.cu", "gftt.cu", "pathfinder.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -79,8 +80,15 @@ _lib = None
 _lock = threading.Lock()
 
 
-def build(force=False, verbose=False):
-    """Compile csrc/*.cu into csrc/libb2of.so for sm_100a (cross-compiles without a GPU)."""
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile csrc/*.cu into csrc/libb2of.so for sm_100a (cross-compiles without a GPU).
+    `defines` / `out` build a variant (extra -D macros) to another path without touching the default library."""
+    if out is not None:
+        cmd = ["nvcc"] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        return out
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(_HERE, "..", "include", "b2of.h")]
     if not force and os.path.exists(LIB_PATH):

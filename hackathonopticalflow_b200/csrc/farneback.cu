@@ -757,6 +757,9 @@ __global__ void __launch_bounds__(320) fb_polyexp_n(const float* __restrict__ I,
 // ----------------------------------------------------------------------------------------------
 constexpr int IT_THREADS = 512;
 constexpr int IT_T_FAST = 56;
+#ifndef IT_NT_FAST
+#define IT_NT_FAST 512
+#endif
 
 struct IterArgs {
   const float* R;          // level base, [frame]{float4 plane ch0..3, float plane ch4}
@@ -815,11 +818,63 @@ __device__ __forceinline__ float2 solve2x2(float g11, float g12, float g22, floa
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+__device__ __forceinline__ void touch_l2(const void* p) {
+  unsigned v;
+  asm volatile("ld.global.cg.b32 %0, [%1];" : "=r"(v) : "l"(p));
+}
+struct FbCorner { float4 a0, a1; float e0, e1; };   // two horizontally adjacent R1 records (ch0..3, ch4)
+
+#ifndef FB_L2_PREFETCH
+#define FB_L2_PREFETCH 1
+#endif
+#ifndef FB_PAIR_FASTEST
+#define FB_PAIR_FASTEST 1
+#endif
+#ifndef FB_EXP
+#define FB_EXP 0
+#endif
+#ifndef FB_PF_DIST
+#define FB_PF_DIST 4
+#endif
+
+__device__ __forceinline__ void pin(int& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void pin(float& v) { asm volatile("" : "+f"(v)); }
+template <typename T>
+__device__ __forceinline__ void pin(T*& v) { asm volatile("" : "+l"(v)); }
+
+// explicit state-space loads / stores: pinned pointers lose their address space, and 32-bit shared addresses
+// save the generic -> shared conversion per access
+template <int OFF>
+__device__ __forceinline__ float4 ldg_f4(const float4* p) {
+  float4 v;
+  asm("ld.global.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "n"(OFF));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ float ldg_f1(const float* p) {
+  float v;
+  asm("ld.global.f32 %0, [%1+%2];" : "=f"(v) : "l"(p), "n"(OFF));
+  return v;
+}
+__device__ __forceinline__ float2 ldg_f2(const float2* p) {
+  float2 v;
+  asm("ld.global.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sts_f4(unsigned addr, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void sts_f1(unsigned addr, float x) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(x) : "memory");
+}
+
+// flow vector of pixel (x, y) of this level: o = y * pitch + x (MODE 1: the flow buffers share the level's pitch)
 template <int MODE>
-__device__ __forceinline__ float2 fetch_flow_m(const IterArgs& a, const float2* fin, int x, int y, int xa, int xb,
+__device__ __forceinline__ float2 fetch_flow_m(const IterArgs& a, const float2* fin, int o, int y, int xa, int xb,
                                                float ufx) {
   if (MODE == 0) return make_float2(0.f, 0.f);
-  if (MODE == 1) return fin[y * a.in_pitch + x];
+  if (MODE == 1) return FB_EXP == 1 ? make_float2(0.3f, 0.4f) : ldg_f2(fin + o);
   int ya = a.uy0[y], yb = a.uy1[y];
   float fy = a.ufy[y];
   float2 p00 = fin[ya * a.in_pitch + xa], p01 = fin[ya * a.in_pitch + xb];
@@ -839,8 +894,11 @@ __global__ void __launch_bounds__(NT, CT ? 2 : 1) fb_iter(IterArgs a) {
   const int HL = T >> 1;            // outputs [0,HL) are summed left->right, [HL,T) right->left (see step B)
   float4* sM4 = (float4*)smem;      // [E][ES]  (M0..M3)   rows form a ring (see `off`)
   float* sM1 = smem + 4 * E * ES;   // [E][ES]  (M4)
-  const int pair = blockIdx.z;
-  const int x0 = blockIdx.x * T;
+  // launch order: pair index fastest, so the CTAs of pairs p and p + 1 on the same tile run together and the
+  // expansion of frame p + 1 (R1 of pair p, R0 of pair p + 1) comes from HBM once and from L2 the second time
+  const int pair = FB_PAIR_FASTEST ? blockIdx.x : blockIdx.z;
+  const int bx = FB_PAIR_FASTEST ? blockIdx.y : blockIdx.x, by = FB_PAIR_FASTEST ? blockIdx.z : blockIdx.y;
+  const int x0 = bx * T;
   const int w = a.w, h = a.h, pitch = a.pitch;
   const float* base0 = a.R + (size_t)pair * a.pair_frame_step * a.r_frame_stride;
   const float4* __restrict__ R0a = (const float4*)base0;
@@ -874,7 +932,7 @@ __global__ void __launch_bounds__(NT, CT ? 2 : 1) fb_iter(IterArgs a) {
   // from E*E/(T*T) to E/T per tile after the first.
   int off = 0;
   for (int c = 0; c < a.nb; ++c) {
-    const int y0 = (blockIdx.y * a.nb + c) * T;
+    const int y0 = (by * a.nb + c) * T;
     if (y0 >= h) break;
     const int lstart = c == 0 ? 0 : 2 * m;    // first logical row that is new in this tile
     const int nrows = E - lstart;
@@ -882,88 +940,144 @@ __global__ void __launch_bounds__(NT, CT ? 2 : 1) fb_iter(IterArgs a) {
     // ---- step A: M on the new halo rows (positions clamped to the image = BORDER_REPLICATE of M) ----
     // thread = one halo column and a run of RS consecutive rows.  Walking down a column, the bottom corners of
     // one pixel's bilinear gather are the top corners of the next one whenever the integer part of the warp
-    // did not jump (almost always: the flow is smooth), so they are carried in registers and only the two new
-    // corners are loaded.  Flow vector and R0 record of the NEXT row are fetched before the current gathers are
-    // consumed (software pipeline); gathers are branch-free (clamped address + select).
-    if (ty < RP) {
+    // advanced by exactly one row (almost always: the flow is smooth), so they are carried in registers and only
+    // the two new corners are loaded.  The loop is unrolled by two with the carried / new corner sets swapping
+    // roles (no register moves); the flow vector of the next row is fetched one row ahead.
+    if (FB_EXP != 4 && ty < RP) {
       const int RS = (nrows + RP - 1) / RP;
       int l = lstart + ty * RS;
       const int l_end = min(l + RS, E);
-      // first touches from HBM (flow, R0, most of the R1 neighbourhood): pull the run into L2 now
-      for (int r = l; r < l_end; ++r) {
-        const int yy = clampi(y0 - m + r, 0, h - 1);
-        const int o = yy * pitch + x;
-        if (MODE == 1) prefetch_l2(fin + yy * a.in_pitch + x);
-        prefetch_l2(R0a + o);
-        prefetch_l2(R0b + o);
-        prefetch_l2(R1a + o);
-        prefetch_l2(R1b + o);
-      }
+      // first touches come from HBM (flow, R0, most of the R1 neighbourhood).  The rows of a tile are pulled into
+      // L2 one tile ahead: the first tile of a CTA prefetches its own rows up front, every tile prefetches the new
+      // rows of the next one (FB_L2_PREFETCH 2: after its own gathers are issued, 3: before them; 1: own rows only)
+      auto prefetch_rows = [&](int ytop, int r0, int r1) {
+        for (int r = r0; r < r1; ++r) {
+          const int yy = clampi(ytop - m + r, 0, h - 1);
+          const int o = yy * pitch + x;
+          if (MODE == 1) prefetch_l2(fin + o);
+          prefetch_l2(R0a + o);
+          prefetch_l2(R0b + o);
+          prefetch_l2(R1a + o);
+          prefetch_l2(R1b + o);
+        }
+      };
+      const bool pf_next = FB_L2_PREFETCH >= 2 && c + 1 < a.nb && y0 + T < h;
+      const int rs_next = (T + RP - 1) / RP;
+      if (FB_L2_PREFETCH == 1 || ((FB_L2_PREFETCH == 2 || FB_L2_PREFETCH == 3) && c == 0)) prefetch_rows(y0, l, l_end);
+      // FB_L2_PREFETCH 4: rolling prefetch FB_PF_DIST rows ahead in this thread's own row sequence (its run in this
+      // tile, then its run in the next tile): a small L2 footprint per CTA instead of a whole tile at once
+      if ((FB_L2_PREFETCH == 4 || FB_L2_PREFETCH == 5) && c == 0) prefetch_rows(y0, l, min(l + FB_PF_DIST, l_end));
+      const int nl0 = 2 * m + ty * rs_next, nl1 = min(nl0 + rs_next, E);   // this thread's run in the next tile
+      if (FB_L2_PREFETCH == 3 && pf_next)
+        prefetch_rows(y0 + T, 2 * m + ty * rs_next, min(2 * m + (ty + 1) * rs_next, E));
       if (l < l_end) {
-        int y_n = clampi(y0 - m + l, 0, h - 1);
-        float2 d_n = fetch_flow_m<MODE>(a, fin, x, y_n, uxa, uxb, ufx);
-        float4 q_n = R0a[y_n * pitch + x];
-        float q4_n = R0b[y_n * pitch + x];
-        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;   // carried bottom corners of the previous row
-        float e0 = 0.f, e1 = 0.f;
-        int ox_prev = -1 << 30;                                   // R1 offset they were loaded from
         int pr = l + off;
         if (pr >= E) pr -= E;
-        for (; l < l_end; ++l) {
-          const float2 d = d_n;
-          const float4 q = q_n;
-          const float q4 = q4_n;
-          const int y = y_n;
+        // shared-memory byte addresses of this thread's M record (float4 plane, float plane), kept incrementally
+        unsigned sa4 = smem_u32(sM4 + pr * ES + ix), sa1 = smem_u32(sM1 + pr * ES + ix);
+        const unsigned sa4_end = smem_u32(sM4 + E * ES + ix);
+        int yu = y0 - m + l;                                       // unclamped image row of logical row l
+        // loop invariants pinned in registers (ptxas otherwise re-derives them from the constant bank every row)
+        const float4* r0a = R0a; const float* r0b = R0b; const float4* r1a = R1a; const float* r1b = R1b;
+        const float2* fi = fin;
+        int wm1 = w - 1, hm1 = h - 1, pit = pitch;
+        int pitb = h > 1 ? pitch : 0;                              // keeps the unused bottom-corner loads in bounds
+        int thr = xb_border ? 0 : h - 10;                          // (unsigned)(y - 5) >= thr  <=>  border pixel
+        pin(r0a); pin(r0b); pin(r1a); pin(r1b); pin(fi); pin(wm1); pin(hm1); pin(pit); pin(pitb); pin(thr);
+        FbCorner cA, cB;
+        cA.a0 = cA.a1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        cA.e0 = cA.e1 = 0.f;
+        cB = cA;
+        int o_carry = -1 << 30;                                    // R1 offset the carried corners came from
+        int yA = min(max(yu, 0), hm1), yB = yA;
+        int oA = yA * pit + x, oB = oA;
+        float2 dA = fetch_flow_m<MODE>(a, fi, oA, yA, uxa, uxb, ufx), dB = dA;
+        auto row = [&](const float2 d, float2& dn, const int y, int& yn, const int o, int& on, bool has_next,
+                       FbCorner& top, FbCorner& bot, int lcur) {
+#if FB_EXP == 1   // timing experiment: no streamed loads (R0, flow)
+          const float4 q = make_float4(xf, (float)y, 1.f, 2.f);
+          const float q4 = xf * 0.001f;
+#else
+          const float4 q = ldg_f4<0>(r0a + o);
+          const float q4 = ldg_f1<0>(r0b + o);
+#endif
+          if (FB_L2_PREFETCH == 4 || FB_L2_PREFETCH == 5) {
+            int lt = lcur + FB_PF_DIST, yt = -1;
+            if (lt < l_end) yt = y0 - m + lt;
+            else if (pf_next && nl0 + (lt - l_end) < nl1) yt = y0 + T - m + nl0 + (lt - l_end);
+            if (yt >= 0) {
+              const int op = min(yt, hm1) * pit + x;
+              if (FB_L2_PREFETCH == 5) {          // experiment: real (discarded) L2-only loads instead of prefetch hints
+                if (MODE == 1) touch_l2(fi + op);
+                touch_l2(r0a + op); touch_l2(r0b + op); touch_l2(r1a + op); touch_l2(r1b + op);
+              } else {
+                if (MODE == 1) prefetch_l2(fi + op);
+                prefetch_l2(r0a + op);
+                prefetch_l2(r0b + op);
+                prefetch_l2(r1a + op);
+                prefetch_l2(r1b + op);
+              }
+            }
+          }
+          ++yu;
+          if (has_next) {
+            yn = min(max(yu, 0), hm1);
+            on = yn * pit + x;
+            dn = fetch_flow_m<MODE>(a, fi, on, yn, uxa, uxb, ufx);
+          }
           float fx = xf + d.x, fy = (float)y + d.y;
-          float flx = floorf(fx), fly = floorf(fy);
-          int x1 = (int)flx, y1 = (int)fly;
-          fx -= flx; fy -= fly;
-          const bool inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
-          const int o1 = inside ? y1 * pitch + x1 : 0;
-          const float4* g4 = R1a + o1;
-          const float* g1 = R1b + o1;
-          float4 p00, p01;
-          float s00, s01;
-          if (o1 == ox_prev) {                  // top corners = carried bottom corners
-            p00 = c0; p01 = c1; s00 = e0; s01 = e1;
-          } else {
-            p00 = g4[0]; p01 = g4[1]; s00 = g1[0]; s01 = g1[1];
+          const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
+          fx -= (float)x1; fy -= (float)y1;
+          const bool inside = (unsigned)x1 < (unsigned)wm1 && (unsigned)y1 < (unsigned)hm1;
+          const int ot = inside ? y1 * pit + x1 : 0;
+          if (FB_EXP != 2 && ot != o_carry) {   // top corners are not the carried bottom corners: load them
+            top.a0 = ldg_f4<0>(r1a + ot); top.a1 = ldg_f4<16>(r1a + ot);
+            top.e0 = ldg_f1<0>(r1b + ot); top.e1 = ldg_f1<4>(r1b + ot);
           }
-          const float4 p10 = g4[pitch], p11 = g4[pitch + 1];
-          const float s10 = g1[pitch], s11 = g1[pitch + 1];
-          if (l + 1 < l_end) {                  // prefetch the next row of this thread
-            y_n = clampi(y0 - m + l + 1, 0, h - 1);
-            d_n = fetch_flow_m<MODE>(a, fin, x, y_n, uxa, uxb, ufx);
-            q_n = R0a[y_n * pitch + x];
-            q4_n = R0b[y_n * pitch + x];
-          }
-          const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-          float r2 = a00 * p00.x + a01 * p01.x + a10 * p10.x + a11 * p11.x;
-          float r3 = a00 * p00.y + a01 * p01.y + a10 * p10.y + a11 * p11.y;
-          float r4 = a00 * p00.z + a01 * p01.z + a10 * p10.z + a11 * p11.z;
-          float r5 = a00 * p00.w + a01 * p01.w + a10 * p10.w + a11 * p11.w;
-          float r6 = a00 * s00 + a01 * s01 + a10 * s10 + a11 * s11;
-          c0 = p10; c1 = p11; e0 = s10; e1 = s11;
-          ox_prev = o1 + pitch;
+          const int ob = ot + pitb;
+#if FB_EXP == 2   // timing experiment: no gathers
+          bot.a0 = q; bot.a1 = q; bot.e0 = q4; bot.e1 = q4;
+#else
+          bot.a0 = ldg_f4<0>(r1a + ob); bot.a1 = ldg_f4<16>(r1a + ob);
+          bot.e0 = ldg_f1<0>(r1b + ob); bot.e1 = ldg_f1<4>(r1b + ob);
+#endif
+          o_carry = ob;
+          const float gx = 1.f - fx, gy = 1.f - fy;
+          const float a00 = gx * gy, a01 = fx * gy, a10 = gx * fy, a11 = fx * fy;
+          float r2 = a00 * top.a0.x + a01 * top.a1.x + a10 * bot.a0.x + a11 * bot.a1.x;
+          float r3 = a00 * top.a0.y + a01 * top.a1.y + a10 * bot.a0.y + a11 * bot.a1.y;
+          float r4 = a00 * top.a0.z + a01 * top.a1.z + a10 * bot.a0.z + a11 * bot.a1.z;
+          float r5 = a00 * top.a0.w + a01 * top.a1.w + a10 * bot.a0.w + a11 * bot.a1.w;
+          float r6 = a00 * top.e0 + a01 * top.e1 + a10 * bot.e0 + a11 * bot.e1;
           r2 = inside ? r2 : 0.f;
           r3 = inside ? r3 : 0.f;
-          r4 = inside ? (q.z + r4) * 0.5f : q.z;
-          r5 = inside ? (q.w + r5) * 0.5f : q.w;
-          r6 = inside ? (q4 + r6) * 0.25f : q4 * 0.5f;
+          r4 = inside ? r4 : q.z;               // (q + q) * 0.5 = q, (q4 + q4) * 0.25 = q4 * 0.5: exact
+          r5 = inside ? r5 : q.w;
+          r6 = inside ? r6 : q4;
+          r4 = (q.z + r4) * 0.5f;
+          r5 = (q.w + r5) * 0.5f;
+          r6 = (q4 + r6) * 0.25f;
           r2 = (q.x - r2) * 0.5f;
           r3 = (q.y - r3) * 0.5f;
           r2 += r4 * d.y + r6 * d.x;
           r3 += r6 * d.y + r5 * d.x;
-          if (xb_border || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
-            float s = bwx * border_w(y, h);
+          if ((unsigned)(y - 5) >= (unsigned)thr) {
+            const float s = bwx * border_w(y, h);
             r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
           }
-          const int so = pr * ES + ix;
-          sM4[so] = make_float4(r4 * r4 + r6 * r6, (r4 + r5) * r6, r5 * r5 + r6 * r6, r4 * r2 + r6 * r3);
-          sM1[so] = r6 * r2 + r5 * r3;
-          if (++pr == E) pr = 0;
+          sts_f4(sa4, r4 * r4 + r6 * r6, (r4 + r5) * r6, r5 * r5 + r6 * r6, r4 * r2 + r6 * r3);
+          sts_f1(sa1, r6 * r2 + r5 * r3);
+          sa4 += ES * 16; sa1 += ES * 4;
+          if (sa4 == sa4_end) { sa4 -= E * ES * 16; sa1 -= E * ES * 4; }   // ring wrap
+        };
+        for (; l + 1 < l_end; l += 2) {
+          row(dA, dB, yA, yB, oA, oB, true, cA, cB, l);
+          row(dB, dA, yB, yA, oB, oA, l + 2 < l_end, cB, cA, l + 1);
         }
+        if (l < l_end) row(dA, dB, yA, yB, oA, oB, false, cA, cB, l);
       }
+      if (FB_L2_PREFETCH == 2 && pf_next)
+        prefetch_rows(y0 + T, 2 * m + ty * rs_next, min(2 * m + (ty + 1) * rs_next, E));
     }
     __syncthreads();
 
@@ -974,7 +1088,7 @@ __global__ void __launch_bounds__(NT, CT ? 2 : 1) fb_iter(IterArgs a) {
     {
       const int gs = (E + 31) & ~31;            // group stride: each group starts on a warp boundary
       const int g = t / gs, r = t - g * gs;
-      if (g < 4 && r < nrows) {
+      if (FB_EXP != 3 && g < 4 && r < nrows) {
         int pr = lstart + r + off;
         if (pr >= E) pr -= E;
         const bool right = g & 1;
@@ -1060,7 +1174,7 @@ __global__ void __launch_bounds__(NT, CT ? 2 : 1) fb_iter(IterArgs a) {
       const int seg = t / T, xo = t - seg * T;
       const int gx = x0 + xo;
       const int xs = xo < HL ? xo : xo + 2 * m;   // where step B left this column's sums
-      if (seg < nseg && gx < w) {
+      if (FB_EXP != 3 && seg < nseg && gx < w) {
         const int r0 = seg * segr;
         const int r1 = min(r0 + segr, T);
         if (GAUSS) {
@@ -1273,7 +1387,7 @@ static void set_func_attrs() {
   cudaFuncSetAttribute(fb_iter<NT_, CT_, CM_, G_, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);    \
   cudaFuncSetAttribute(fb_iter<NT_, CT_, CM_, G_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);    \
   cudaFuncSetAttribute(fb_iter<NT_, CT_, CM_, G_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  B2OF_ATTR(512, IT_T_FAST, 7, false)
+  B2OF_ATTR(IT_NT_FAST, IT_T_FAST, 7, false)
   B2OF_ATTR(512, 0, 0, false)
   B2OF_ATTR(512, 0, 0, true)
 #undef B2OF_ATTR
@@ -1327,11 +1441,14 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
     // vertical streaming: as many tiles per CTA as still leaves >= ~4 waves of CTAs
     const int cx = cdiv(L.w, tile), cy = cdiv(L.h, tile);
     int nb = (int)(((long long)cx * cy * pairs) / (4 * 296));
-    const int nb_cap = 8;
+#ifndef FB_NB_CAP
+#define FB_NB_CAP 8
+#endif
+    const int nb_cap = FB_NB_CAP;
     nb = nb < 1 ? 1 : (nb > nb_cap ? nb_cap : nb);
     nb = cdiv(cy, cdiv(cy, nb));                 // balance the row groups
     a.nb = nb;
-    dim3 grid(cx, cdiv(cy, nb), pairs);
+    dim3 grid = FB_PAIR_FASTEST ? dim3(pairs, cx, cdiv(cy, nb)) : dim3(cx, cdiv(cy, nb), pairs);
     int iters = p.iterations;
     if (iters == 0) {
       // cv2 with iterations == 0 returns the (upsampled) initial flow of the finest level untouched;
@@ -1381,7 +1498,7 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
     else if (a.mode == 1) fb_iter<NT_, CT_, CM_, G_, 1><<<grid, NT_, smem, st>>>(a);        \
     else fb_iter<NT_, CT_, CM_, G_, 2><<<grid, NT_, smem, st>>>(a);                         \
   } while (0)
-        if (fast) B2OF_ITER_LAUNCH(512, IT_T_FAST, 7, false);
+        if (fast) B2OF_ITER_LAUNCH(IT_NT_FAST, IT_T_FAST, 7, false);
         else if (gauss) B2OF_ITER_LAUNCH(512, 0, 0, true);
         else B2OF_ITER_LAUNCH(512, 0, 0, false);
 #undef B2OF_ITER_LAUNCH
