@@ -833,6 +833,9 @@ struct FbCorner { float4 a0, a1; float e0, e1; };   // two horizontally adjacent
 #ifndef FB_EXP
 #define FB_EXP 0
 #endif
+#ifndef FB_STRIP
+#define FB_STRIP 1
+#endif
 #ifndef FB_PF_DIST
 #define FB_PF_DIST 4
 #endif
@@ -1224,6 +1227,8 @@ __global__ void __launch_bounds__(NT, CT ? 2 : 1) fb_iter(IterArgs a) {
   }
 }
 
+#include "fb_strip.cuh"
+
 // ----------------------------------------------------------------------------------------------
 // OPTFLOW_USE_INITIAL_FLOW: flow_coarsest = resize(flow0, INTER_AREA) * scale   (optflowgf.cpp, first level)
 // ----------------------------------------------------------------------------------------------
@@ -1391,6 +1396,9 @@ static void set_func_attrs() {
   B2OF_ATTR(512, 0, 0, false)
   B2OF_ATTR(512, 0, 0, true)
 #undef B2OF_ATTR
+  cudaFuncSetAttribute(fb_iter_strip<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBS_SMEM);
+  cudaFuncSetAttribute(fb_iter_strip<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBS_SMEM);
+  cudaFuncSetAttribute(fb_iter_strip<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBS_SMEM);
   cudaFuncSetAttribute(fb_polyexp, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   cudaFuncSetAttribute(fb_level_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 }
@@ -1498,7 +1506,19 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
     else if (a.mode == 1) fb_iter<NT_, CT_, CM_, G_, 1><<<grid, NT_, smem, st>>>(a);        \
     else fb_iter<NT_, CT_, CM_, G_, 2><<<grid, NT_, smem, st>>>(a);                         \
   } while (0)
-        if (fast) B2OF_ITER_LAUNCH(IT_NT_FAST, IT_T_FAST, 7, false);
+        if (fast && FB_STRIP) {
+          // strip kernel: 112-column strips, nseg row segments of nblk 16-row blocks each (>= ~4 waves of CTAs)
+          IterArgs b = a;
+          const int nstrips = cdiv(L.w, FBS_TW), blocks = cdiv(L.h, FBS_RB);
+          int nseg = cdiv(4 * 296, pairs * nstrips);
+          nseg = nseg < 1 ? 1 : (nseg > blocks ? blocks : nseg);
+          b.nb = cdiv(cdiv(blocks, nseg), FBS_REFRESH) * FBS_REFRESH;   // segments start on refresh blocks: results
+                                                                        // are independent of the batch size
+          dim3 gs(pairs, nstrips, cdiv(blocks, b.nb));
+          if (b.mode == 0) fb_iter_strip<0><<<gs, FBS_NT, FBS_SMEM, st>>>(b);
+          else if (b.mode == 1) fb_iter_strip<1><<<gs, FBS_NT, FBS_SMEM, st>>>(b);
+          else fb_iter_strip<2><<<gs, FBS_NT, FBS_SMEM, st>>>(b);
+        } else if (fast) B2OF_ITER_LAUNCH(IT_NT_FAST, IT_T_FAST, 7, false);
         else if (gauss) B2OF_ITER_LAUNCH(512, 0, 0, true);
         else B2OF_ITER_LAUNCH(512, 0, 0, false);
 #undef B2OF_ITER_LAUNCH
