@@ -834,7 +834,7 @@ struct FbCorner { float4 a0, a1; float e0, e1; };   // two horizontally adjacent
 #define FB_EXP 0
 #endif
 #ifndef FB_STRIP
-#define FB_STRIP 1
+#define FB_STRIP 2
 #endif
 #ifndef FB_PF_DIST
 #define FB_PF_DIST 4
@@ -1228,6 +1228,7 @@ __global__ void __launch_bounds__(NT, CT ? 2 : 1) fb_iter(IterArgs a) {
 }
 
 #include "fb_strip.cuh"
+#include "fb_ws.cuh"
 
 // ----------------------------------------------------------------------------------------------
 // OPTFLOW_USE_INITIAL_FLOW: flow_coarsest = resize(flow0, INTER_AREA) * scale   (optflowgf.cpp, first level)
@@ -1396,6 +1397,9 @@ static void set_func_attrs() {
   B2OF_ATTR(512, 0, 0, false)
   B2OF_ATTR(512, 0, 0, true)
 #undef B2OF_ATTR
+  cudaFuncSetAttribute(fb_iter_ws<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
+  cudaFuncSetAttribute(fb_iter_ws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
+  cudaFuncSetAttribute(fb_iter_ws<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
   cudaFuncSetAttribute(fb_iter_strip<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBS_SMEM);
   cudaFuncSetAttribute(fb_iter_strip<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBS_SMEM);
   cudaFuncSetAttribute(fb_iter_strip<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBS_SMEM);
@@ -1506,8 +1510,20 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
     else if (a.mode == 1) fb_iter<NT_, CT_, CM_, G_, 1><<<grid, NT_, smem, st>>>(a);        \
     else fb_iter<NT_, CT_, CM_, G_, 2><<<grid, NT_, smem, st>>>(a);                         \
   } while (0)
-        if (fast && FB_STRIP) {
-          // strip kernel: 112-column strips, nseg row segments of nblk 16-row blocks each (>= ~4 waves of CTAs)
+        if (fast && FB_STRIP == 2) {
+          // warp-specialised strip kernel: one CTA per SM, 112-column strips, nseg row segments of nb 20-row blocks
+          IterArgs b = a;
+          const int nstrips = cdiv(L.w, FBS_TW), blocks = cdiv(L.h, FBW_RB);
+          int nseg = cdiv(2 * 148, pairs * nstrips);
+          nseg = nseg < 1 ? 1 : (nseg > blocks ? blocks : nseg);
+          b.nb = cdiv(cdiv(blocks, nseg), FBS_REFRESH) * FBS_REFRESH;   // segments start on refresh blocks: results
+                                                                        // are independent of the batch size
+          dim3 gs(pairs, nstrips, cdiv(blocks, b.nb));
+          if (b.mode == 0) fb_iter_ws<0><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
+          else if (b.mode == 1) fb_iter_ws<1><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
+          else fb_iter_ws<2><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
+        } else if (fast && FB_STRIP) {
+          // strip kernel: 112-column strips, nseg row segments of nblk 15-row blocks each (>= ~4 waves of CTAs)
           IterArgs b = a;
           const int nstrips = cdiv(L.w, FBS_TW), blocks = cdiv(L.h, FBS_RB);
           int nseg = cdiv(4 * 296, pairs * nstrips);

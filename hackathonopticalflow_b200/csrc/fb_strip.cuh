@@ -15,16 +15,22 @@
 // Wavefronts per output pixel: about 1.9 (A 1.0, B 0.6, C 0.3) against 3.6 for the square-tile kernel.
 #pragma once
 
-constexpr int FBS_NT = 512;               // threads per CTA
+constexpr int FBS_NT = 384;               // threads per CTA
 constexpr int FBS_EW = 128;               // halo columns per strip
 constexpr int FBS_TW = 112;               // output columns per strip
 constexpr int FBS_M = 7;                  // window radius
 constexpr int FBS_PADL = 8;               // halo column 0 sits at image column x0 - 8 (8-pixel aligned)
-constexpr int FBS_RB = 16;                // rows per block
+constexpr int FBS_RB = 15;                // rows per block
 constexpr int FBS_NR = FBS_RB + 2 * FBS_M;   // ring rows
 constexpr int FBS_ES = 129;               // plane row stride in elements (odd)
 constexpr int FBS_HL = FBS_TW / 2;        // outputs [0,HL) are summed left->right, [HL,TW) right->left
 constexpr int FBS_RUNS = FBS_NT / FBS_EW; // row runs per block in step A
+#ifndef FBS_BULK_PF
+#define FBS_BULK_PF 1
+#endif
+#ifndef FBS_EXP
+#define FBS_EXP 0
+#endif
 #ifndef FBS_REFRESH
 #define FBS_REFRESH 4
 #endif
@@ -35,6 +41,15 @@ __device__ __forceinline__ void sts_f2(unsigned addr, float x, float y) {
 }
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+
+struct FbRow {               // one row of a thread's run in flight through step A
+  float2 d;                  // flow vector
+  float4 q; float q4;        // R0 record
+  float fx, fy;              // fractional warp position
+  int y, ot;                 // image row; R1 element offset of the top-left corner
+  bool inside;
+  FbCorner bot;              // bottom corner pair
+};
 
 template <int MODE>
 __global__ void __launch_bounds__(FBS_NT, 2) fb_iter_strip(IterArgs a) {
@@ -61,7 +76,7 @@ __global__ void __launch_bounds__(FBS_NT, 2) fb_iter_strip(IterArgs a) {
   const int t = threadIdx.x;
 
   // ---- step A constants: thread = (halo column cx, run) ----
-  const int cx = t & (EW - 1), run = t >> 7;
+  const int cx = t & (EW - 1), run = t >> 7;            // 3 runs of 128 columns
   const int x = clampi(x0 - FBS_PADL + cx, 0, w - 1);
   const float xf = (float)x;
   const bool xb_border = (unsigned)(x - 5) >= (unsigned)(w - 10);   // cv2's own (unsigned) test
@@ -81,75 +96,106 @@ __global__ void __launch_bounds__(FBS_NT, 2) fb_iter_strip(IterArgs a) {
     const int lstart = s == 0 ? 0 : 2 * M;              // logical rows [lstart, NR) are new; row l = image row yb - M + l
     const int nrows = NR - lstart;
 
-    // ---- step A: M on the new rows (see fb_iter for the gather scheme) ----
+    // ---- L2 prefetch of the next block's new rows by the copy engine (no LSU wavefronts): one bulk prefetch per
+    // (row, stream), issued by one thread each; R1 is prefetched at the undisplaced position (the flow moves the
+    // gather by a few rows, which the neighbouring blocks' prefetches cover)
+    if (FBS_BULK_PF) {
+      const int nrow_pf = s == 0 ? NR + RB : RB;        // first block: its own rows too
+      const int np = nrow_pf * 5;
+      for (int u = t; u < np; u += FBS_NT) {
+        const int r = u / 5, k = u - r * 5;
+        const int yy = min(max(yb - M + (s == 0 ? r : NR + r), 0), h - 1);
+        if (yy >= ye + M + RB) continue;
+        const int xs = max(x0 - FBS_PADL, 0);
+        const int cols = min(EW, pitch - xs);
+        const size_t o = (size_t)yy * pitch + xs;
+        const void* p;
+        int bytes;
+        if (k == 0) { p = R0a + o; bytes = cols * 16; }
+        else if (k == 1) { p = R1a + o; bytes = cols * 16; }
+        else if (k == 2) { p = R0b + o; bytes = cols * 4; }
+        else if (k == 3) { p = R1b + o; bytes = cols * 4; }
+        else { if (MODE != 1) continue; p = fin + o; bytes = cols * 8; }
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+      }
+    }
+
+    // ---- step A: M on the new rows.  thread = (halo column, run of consecutive rows); software-pipelined one row
+    // deep: the gather and R0 loads of row k + 1 (and the flow vector of row k + 2) are in flight while row k is
+    // consumed, so memory latency overlaps the arithmetic of the same warp.  Walking down a column the bottom
+    // corners of row k are the top corners of row k + 1 whenever the integer part of the warp advanced by exactly
+    // one row (almost always); they are folded into a 5-value partial sum for row k + 1 as soon as they arrive, so
+    // only that partial sum is carried.
     {
       const int RS = (nrows + FBS_RUNS - 1) / FBS_RUNS;
-      int l = lstart + run * RS;
-      const int l_end = min(l + RS, NR);
-      if (l < l_end) {
-        int pr = l + off;
+      const int l0 = lstart + run * RS;
+      const int n = min(l0 + RS, NR) - l0;              // rows of this thread's run
+      if (FBS_EXP != 4 && n > 0) {
+        int pr = l0 + off;
         if (pr >= NR) pr -= NR;
         unsigned sa = (unsigned)(pr * ES + cx);         // element index into the planes
         const unsigned sa_end = (unsigned)(NR * ES + cx);
-        int yu = yb - M + l;
+        int yu = yb - M + l0;                           // unclamped image row of the row being set up
         const float4* r0a = R0a; const float* r0b = R0b; const float4* r1a = R1a; const float* r1b = R1b;
         const float2* fi = fin;
         int wm1 = w - 1, hm1 = h - 1, pit = pitch;
-        int pitb = h > 1 ? pitch : 0;
-        int thr = xb_border ? 0 : h - 10;
+        int pitb = h > 1 ? pitch : 0;                   // keeps the unused bottom-corner loads in bounds
+        int thr = xb_border ? 0 : h - 10;               // (unsigned)(y - 5) >= thr  <=>  border pixel
         pin(r0a); pin(r0b); pin(r1a); pin(r1b); pin(fi); pin(wm1); pin(hm1); pin(pit); pin(pitb); pin(thr);
-        FbCorner cA, cB;
-        cA.a0 = cA.a1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        cA.e0 = cA.e1 = 0.f;
-        cB = cA;
-        int o_carry = -1 << 30;
-        int yA = min(max(yu, 0), hm1), yB = yA;
-        int oA = yA * pit + x, oB = oA;
-        float2 dA = fetch_flow_m<MODE>(a, fi, oA, yA, uxa, uxb, ufx), dB = dA;
-        auto row = [&](const float2 d, float2& dn, const int y, int& yn, const int o, int& on, bool has_next,
-                       FbCorner& top, FbCorner& bot) {
-          const float4 q = ldg_f4<0>(r0a + o);
-          const float q4 = ldg_f1<0>(r0b + o);
-          ++yu;
-          if (has_next) {
-            yn = min(max(yu, 0), hm1);
-            on = yn * pit + x;
-            dn = fetch_flow_m<MODE>(a, fi, on, yn, uxa, uxb, ufx);
-          }
-          float fx = xf + d.x, fy = (float)y + d.y;
+
+        // stage 1: everything of a row that only needs its flow vector: addresses, weights, loads in flight
+        auto stage1 = [&](FbRow& R, int o) {
+          R.q = ldg_f4<0>(r0a + o);
+          R.q4 = ldg_f1<0>(r0b + o);
+          float fx = xf + R.d.x, fy = (float)R.y + R.d.y;
           const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
-          fx -= (float)x1; fy -= (float)y1;
-          const bool inside = (unsigned)x1 < (unsigned)wm1 && (unsigned)y1 < (unsigned)hm1;
-          const int ot = inside ? y1 * pit + x1 : 0;
-          if (ot != o_carry) {
-            top.a0 = ldg_f4<0>(r1a + ot); top.a1 = ldg_f4<16>(r1a + ot);
-            top.e0 = ldg_f1<0>(r1b + ot); top.e1 = ldg_f1<4>(r1b + ot);
-          }
-          const int ob = ot + pitb;
-          bot.a0 = ldg_f4<0>(r1a + ob); bot.a1 = ldg_f4<16>(r1a + ob);
-          bot.e0 = ldg_f1<0>(r1b + ob); bot.e1 = ldg_f1<4>(r1b + ob);
-          o_carry = ob;
-          const float gx = 1.f - fx, gy = 1.f - fy;
-          const float a00 = gx * gy, a01 = fx * gy, a10 = gx * fy, a11 = fx * fy;
-          float r2 = a00 * top.a0.x + a01 * top.a1.x + a10 * bot.a0.x + a11 * bot.a1.x;
-          float r3 = a00 * top.a0.y + a01 * top.a1.y + a10 * bot.a0.y + a11 * bot.a1.y;
-          float r4 = a00 * top.a0.z + a01 * top.a1.z + a10 * bot.a0.z + a11 * bot.a1.z;
-          float r5 = a00 * top.a0.w + a01 * top.a1.w + a10 * bot.a0.w + a11 * bot.a1.w;
-          float r6 = a00 * top.e0 + a01 * top.e1 + a10 * bot.e0 + a11 * bot.e1;
-          r2 = inside ? r2 : 0.f;
-          r3 = inside ? r3 : 0.f;
-          r4 = inside ? r4 : q.z;
-          r5 = inside ? r5 : q.w;
-          r6 = inside ? r6 : q4;
+          R.fx = fx - (float)x1; R.fy = fy - (float)y1;
+          R.inside = (unsigned)x1 < (unsigned)wm1 && (unsigned)y1 < (unsigned)hm1;
+          R.ot = R.inside ? y1 * pit + x1 : 0;
+          const int ob = R.ot + pitb;
+          R.bot.a0 = ldg_f4<0>(r1a + ob); R.bot.a1 = ldg_f4<16>(r1a + ob);
+          R.bot.e0 = ldg_f1<0>(r1b + ob); R.bot.e1 = ldg_f1<4>(r1b + ob);
+        };
+        // top half of the bilinear sum of row R from the corner pair c
+        auto top_partial = [&](const FbRow& R, const FbCorner& c, float (&tp)[5]) {
+          const float gy = 1.f - R.fy;
+          const float a00 = (1.f - R.fx) * gy, a01 = R.fx * gy;
+          tp[0] = fmaf(a01, c.a1.x, a00 * c.a0.x);
+          tp[1] = fmaf(a01, c.a1.y, a00 * c.a0.y);
+          tp[2] = fmaf(a01, c.a1.z, a00 * c.a0.z);
+          tp[3] = fmaf(a01, c.a1.w, a00 * c.a0.w);
+          tp[4] = fmaf(a01, c.e1, a00 * c.e0);
+        };
+        auto load_top = [&](const FbRow& R, float (&tp)[5]) {
+          FbCorner c;
+          c.a0 = ldg_f4<0>(r1a + R.ot); c.a1 = ldg_f4<16>(r1a + R.ot);
+          c.e0 = ldg_f1<0>(r1b + R.ot); c.e1 = ldg_f1<4>(r1b + R.ot);
+          top_partial(R, c, tp);
+        };
+        // stage 2: consume a row whose loads have landed
+        auto stage2 = [&](const FbRow& R, const float (&tp)[5]) {
+          const float a10 = (1.f - R.fx) * R.fy, a11 = R.fx * R.fy;
+          float r2 = fmaf(a11, R.bot.a1.x, fmaf(a10, R.bot.a0.x, tp[0]));
+          float r3 = fmaf(a11, R.bot.a1.y, fmaf(a10, R.bot.a0.y, tp[1]));
+          float r4 = fmaf(a11, R.bot.a1.z, fmaf(a10, R.bot.a0.z, tp[2]));
+          float r5 = fmaf(a11, R.bot.a1.w, fmaf(a10, R.bot.a0.w, tp[3]));
+          float r6 = fmaf(a11, R.bot.e1, fmaf(a10, R.bot.e0, tp[4]));
+          const float4 q = R.q;
+          const float q4 = R.q4;
+          r2 = R.inside ? r2 : 0.f;
+          r3 = R.inside ? r3 : 0.f;
+          r4 = R.inside ? r4 : q.z;               // (q + q) * 0.5 = q, (q4 + q4) * 0.25 = q4 * 0.5: exact
+          r5 = R.inside ? r5 : q.w;
+          r6 = R.inside ? r6 : q4;
           r4 = (q.z + r4) * 0.5f;
           r5 = (q.w + r5) * 0.5f;
           r6 = (q4 + r6) * 0.25f;
           r2 = (q.x - r2) * 0.5f;
           r3 = (q.y - r3) * 0.5f;
-          r2 += r4 * d.y + r6 * d.x;
-          r3 += r6 * d.y + r5 * d.x;
-          if ((unsigned)(y - 5) >= (unsigned)thr) {
-            const float sc = bwx * border_w(y, h);
+          r2 += r4 * R.d.y + r6 * R.d.x;
+          r3 += r6 * R.d.y + r5 * R.d.x;
+          if ((unsigned)(R.y - 5) >= (unsigned)thr) {
+            const float sc = bwx * border_w(R.y, h);
             r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
           }
           sts_f2(s_xy + sa * 8, r4 * r4 + r6 * r6, (r4 + r5) * r6);
@@ -158,11 +204,37 @@ __global__ void __launch_bounds__(FBS_NT, 2) fb_iter_strip(IterArgs a) {
           sa += ES;
           if (sa == sa_end) sa -= NR * ES;
         };
-        for (; l + 1 < l_end; l += 2) {
-          row(dA, dB, yA, yB, oA, oB, true, cA, cB);
-          row(dB, dA, yB, yA, oB, oA, l + 2 < l_end, cB, cA);
+        auto next_row = [&](int& y, int& o) {          // image row / element offset of the next row to set up
+          y = min(max(yu, 0), hm1);
+          o = y * pit + x;
+          ++yu;
+        };
+
+        FbRow A, B;
+        float tp[5];
+        int oA, oB = 0, yn, on;
+        float2 dn = make_float2(0.f, 0.f);
+        next_row(A.y, oA);
+        A.d = fetch_flow_m<MODE>(a, fi, oA, A.y, uxa, uxb, ufx);
+        B.y = A.y; B.d = A.d;
+        if (n > 1) { next_row(B.y, oB); B.d = fetch_flow_m<MODE>(a, fi, oB, B.y, uxa, uxb, ufx); }
+        stage1(A, oA);
+        load_top(A, tp);
+        int k = 0;
+        for (; k + 1 < n; k += 2) {
+          // rows k (in A, loads in flight) and k + 1 (in B, flow vector in flight)
+          stage1(B, oB);
+          if (k + 2 < n) { next_row(yn, on); dn = fetch_flow_m<MODE>(a, fi, on, yn, uxa, uxb, ufx); }
+          stage2(A, tp);
+          if (B.ot == A.ot + pitb) top_partial(B, A.bot, tp); else load_top(B, tp);
+          A.d = dn; A.y = yn; oA = on;
+          if (k + 2 < n) stage1(A, oA);
+          if (k + 3 < n) { next_row(yn, on); dn = fetch_flow_m<MODE>(a, fi, on, yn, uxa, uxb, ufx); }
+          stage2(B, tp);
+          if (k + 2 < n) { if (A.ot == B.ot + pitb) top_partial(A, B.bot, tp); else load_top(A, tp); }
+          B.d = dn; B.y = yn; oB = on;
         }
-        if (l < l_end) row(dA, dB, yA, yB, oA, oB, false, cA, cB);
+        if (k < n) stage2(A, tp);
       }
     }
     __syncthreads();
@@ -172,7 +244,7 @@ __global__ void __launch_bounds__(FBS_NT, 2) fb_iter_strip(IterArgs a) {
     //   right half: outputs [HL,TW) walked right->left, result stored at p = xo + 14  (reads p <= xo + 14)
     // positions [HL, HL + 14) are written by neither half.  thread = (plane, row, half); a warp holds 16 rows x 2
     // halves, which the odd row stride spreads over all banks.
-    if (t < 192) {
+    if (FBS_EXP != 3 && FBS_EXP != 5 && t < 192) {
       const int plane = t >> 6, rg = (t >> 5) & 1, lane = t & 31;
       const int r = rg * 16 + (lane & 15);
       const bool right = (lane >> 4) != 0;
@@ -235,7 +307,7 @@ __global__ void __launch_bounds__(FBS_NT, 2) fb_iter_strip(IterArgs a) {
     __syncthreads();
 
     // ---- step C: vertical running 15-sums + 2x2 solve; thread = output column ----
-    if (t < TW && x0 + t < w) {
+    if (FBS_EXP != 3 && FBS_EXP != 6 && t < TW && x0 + t < w) {
       const int col = 1 + (t < HL ? t : t + 2 * M);                      // where step B left this column's sums
       int pn = off;                                                      // physical row of logical row 0
       if (s == 0 || ((yb / RB) % FBS_REFRESH) == 0) {   // absolute block index: results do not depend on the segmentation

@@ -1,0 +1,332 @@
+// K5/K6, warp-specialised strip form (the reference's window: winsize 15, box): one fused kernel per
+// (level, iteration), one persistent-style CTA per SM walking down a strip of 112 output columns in blocks of
+// FBW_RB rows.  The three steps of a block run on DIFFERENT warps and on different blocks at the same time:
+//
+//   A warps (20): UpdateMatrices for block s + 2 -> ring rows          (memory-latency bound: gathers)
+//   B warps  (4): horizontal 15-sums in place on block s + 1           (shared-memory latency bound, serial in x)
+//   C warps  (4): vertical running 15-sums + 2x2 solve for block s     (shared-memory latency bound, serial in y)
+//
+// so the serial row / column walks of B and C hide behind the gathers of A instead of stalling the whole CTA at a
+// barrier (in the phase-structured kernels 44 % of all warp time was barrier wait).  Blocks are handed from
+// stage to stage through mbarriers (full_a[3], full_b[3], empty_c[3]; stage = block mod 3); the M ring holds
+// 14 + 3 * FBW_RB rows as three planes (float2 ch0/1, float2 ch2/3, float ch4) with an odd row stride.
+// Arithmetic is the same as fb_iter_strip (fb_strip.cuh), which documents steps A, B and C.
+#pragma once
+
+constexpr int FBW_A_WARPS = 20;
+constexpr int FBW_NT = (FBW_A_WARPS + 8) * 32;          // 896 threads: 20 A warps, 4 B warps, 4 C warps
+constexpr int FBW_RUNS = FBW_A_WARPS / 4;               // row runs per block in step A (128 columns = 4 warps each)
+constexpr int FBW_RB = 20;                              // rows per block
+constexpr int FBW_NR = 2 * FBS_M + 3 * FBW_RB;          // ring rows (74)
+constexpr size_t FBW_PLANES = (size_t)FBW_NR * FBS_ES * 20;
+constexpr size_t FBW_SMEM = FBW_PLANES + 16 * 8;        // + mbarriers
+static_assert(FBW_A_WARPS == FBW_RB, "one A warp issues the L2 prefetch of one row of the next block");
+
+__device__ __forceinline__ void mbar_init(unsigned addr, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned addr) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
+  asm volatile(
+      "{ .reg .pred p;\n"
+      "W_%=: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra W_%=;\n }" ::"r"(addr), "r"(parity) : "memory");
+}
+
+// horizontal 15-sums of one ring row of one plane, in place (see fb_iter_strip step B)
+template <typename T>
+__device__ __forceinline__ T hp_add(T a, T b);
+template <> __device__ __forceinline__ float2 hp_add<float2>(float2 a, float2 b) { return add2(a, b); }
+template <> __device__ __forceinline__ float hp_add<float>(float a, float b) { return a + b; }
+template <typename T>
+__device__ __forceinline__ T hp_sub(T a, T b);
+template <> __device__ __forceinline__ float2 hp_sub<float2>(float2 a, float2 b) { return sub2(a, b); }
+template <> __device__ __forceinline__ float hp_sub<float>(float a, float b) { return a - b; }
+
+template <typename T>
+__device__ __forceinline__ void hpass_half_row(T* rowp, bool right) {
+  constexpr int M = FBS_M, TW = FBS_TW, HL = FBS_HL;
+  if (!right) {
+    T sm = rowp[0];
+#pragma unroll
+    for (int k = 1; k < 2 * M; ++k) sm = hp_add(sm, rowp[k]);
+#pragma unroll 8
+    for (int xo = 0; xo < HL; ++xo) {
+      sm = hp_add(sm, rowp[xo + 2 * M]);
+      const T old = rowp[xo];
+      rowp[xo] = sm;
+      sm = hp_sub(sm, old);
+    }
+  } else {
+    T sm = rowp[TW];
+#pragma unroll
+    for (int k = 1; k < 2 * M; ++k) sm = hp_add(sm, rowp[TW + k]);
+#pragma unroll 8
+    for (int xo = TW - 1; xo >= HL; --xo) {
+      sm = hp_add(sm, rowp[xo]);
+      const T old = rowp[xo + 2 * M];
+      rowp[xo + 2 * M] = sm;
+      sm = hp_sub(sm, old);
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int EW = FBS_EW, TW = FBS_TW, M = FBS_M, RB = FBW_RB, NR = FBW_NR, ES = FBS_ES, HL = FBS_HL;
+  float2* Pxy = (float2*)smem;                          // float2 [NR][ES]  (M0, M1)
+  float2* Pzw = Pxy + NR * ES;                          // float2 [NR][ES]  (M2, M3)
+  float* Pe = (float*)(Pzw + NR * ES);                  // float  [NR][ES]  (M4)
+  const unsigned s_xy = smem_u32(smem);
+  const unsigned s_zw = s_xy + NR * ES * 8;
+  const unsigned s_e = s_zw + NR * ES * 8;
+  const unsigned s_bar = s_xy + (unsigned)FBW_PLANES;   // full_a[3], full_b[3], empty_c[3]
+  const int pair = blockIdx.x;                          // pair index fastest (frame p + 1 shared through L2)
+  const int x0 = blockIdx.y * TW;
+  const int w = a.w, h = a.h, pitch = a.pitch;
+  const int ys = blockIdx.z * a.nb * RB;                // rows [ys, ye) are this CTA's outputs
+  const int ye = min(ys + a.nb * RB, h);
+  const int nblk = (ye - ys + RB - 1) / RB;
+  const int t = threadIdx.x;
+
+  if (t == 0) {
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(s_bar + i * 8, FBW_A_WARPS * 32);       // full_a: every A thread arrives
+      mbar_init(s_bar + (3 + i) * 8, 128);              // full_b
+      mbar_init(s_bar + (6 + i) * 8, 128);              // empty_c
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (t < FBW_A_WARPS * 32) {
+    // =========================== A warps: UpdateMatrices ===========================
+    const float* base0 = a.R + (size_t)pair * a.pair_frame_step * a.r_frame_stride;
+    const float4* __restrict__ R0a = (const float4*)base0;
+    const float* __restrict__ R0b = base0 + 4 * a.plane_stride;
+    const float4* __restrict__ R1a = (const float4*)(base0 + a.r_frame_stride);
+    const float* __restrict__ R1b = base0 + a.r_frame_stride + 4 * a.plane_stride;
+    const float2* __restrict__ fin = MODE ? a.flow_in + (size_t)pair * a.flow_in_pair_stride : nullptr;
+    const int cx = t & (EW - 1), run = t >> 7;
+    const int x = clampi(x0 - FBS_PADL + cx, 0, w - 1);
+    const float xf = (float)x;
+    const bool xb_border = (unsigned)(x - 5) >= (unsigned)(w - 10);   // cv2's own (unsigned) test
+    const float bwx = border_w(x, w);
+    int uxa = 0, uxb = 0;
+    float ufx = 0.f;
+    if (MODE == 2) { uxa = a.ux0[x]; uxb = a.ux1[x]; ufx = a.ufx[x]; }
+    const float4* r0a = R0a; const float* r0b = R0b; const float4* r1a = R1a; const float* r1b = R1b;
+    const float2* fi = fin;
+    int wm1 = w - 1, hm1 = h - 1, pit = pitch;
+    int pitb = h > 1 ? pitch : 0;                       // keeps the unused bottom-corner loads in bounds
+    int thr = xb_border ? 0 : h - 10;                   // (unsigned)(y - 5) >= thr  <=>  border pixel
+    pin(r0a); pin(r0b); pin(r1a); pin(r1b); pin(fi); pin(wm1); pin(hm1); pin(pit); pin(pitb); pin(thr);
+
+    int j0 = 0;                                         // ring row (mod NR) of the first new M row of the block
+    for (int s = 0; s < nblk; ++s) {
+      const int yb = ys + s * RB;
+      const int nrows = s == 0 ? 2 * M + RB : RB;       // M rows [y_first, y_first + nrows), y_first below
+      const int y_first = s == 0 ? yb - M : yb + M;     // image row of the first new M row
+      if (s >= 3) mbar_wait(s_bar + (6 + s % 3) * 8, (unsigned)((s / 3 - 1) & 1));   // C is done with block s - 3
+
+      // L2 prefetch of the next block's new rows by the copy engine: one bulk prefetch per (row, stream)
+      if ((t & 31) == 0 && s + 1 < nblk) {
+        const int r = t >> 5;                            // warp = row of the next block (FBW_A_WARPS == FBW_RB)
+        const int yy = min(yb + RB + M + r, h - 1);
+        const int xs = max(x0 - FBS_PADL, 0);
+        const int cols = min(EW, pitch - xs);
+        const size_t o = (size_t)yy * pitch + xs;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(R0a + o), "r"(cols * 16) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(R1a + o), "r"(cols * 16) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(R0b + o), "r"(cols * 4) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(R1b + o), "r"(cols * 4) : "memory");
+        if (MODE == 1) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(fin + o), "r"(cols * 8) : "memory");
+      }
+
+      const int RS = (nrows + FBW_RUNS - 1) / FBW_RUNS;
+      const int l0 = run * RS;
+      const int n = min(l0 + RS, nrows) - l0;           // rows of this thread's run
+      if (n > 0) {
+        int pr = j0 + l0;
+        if (pr >= NR) pr -= NR;
+        unsigned sa = (unsigned)(pr * ES + cx);         // element index into the planes
+        const unsigned sa_end = (unsigned)(NR * ES + cx);
+        int yu = y_first + l0;                          // unclamped image row of the row being set up
+
+        auto stage1 = [&](FbRow& R, int o) {
+          R.q = ldg_f4<0>(r0a + o);
+          R.q4 = ldg_f1<0>(r0b + o);
+          float fx = xf + R.d.x, fy = (float)R.y + R.d.y;
+          const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
+          R.fx = fx - (float)x1; R.fy = fy - (float)y1;
+          R.inside = (unsigned)x1 < (unsigned)wm1 && (unsigned)y1 < (unsigned)hm1;
+          R.ot = R.inside ? y1 * pit + x1 : 0;
+          const int ob = R.ot + pitb;
+          R.bot.a0 = ldg_f4<0>(r1a + ob); R.bot.a1 = ldg_f4<16>(r1a + ob);
+          R.bot.e0 = ldg_f1<0>(r1b + ob); R.bot.e1 = ldg_f1<4>(r1b + ob);
+        };
+        auto top_partial = [&](const FbRow& R, const FbCorner& c, float (&tp)[5]) {
+          const float gy = 1.f - R.fy;
+          const float a00 = (1.f - R.fx) * gy, a01 = R.fx * gy;
+          tp[0] = fmaf(a01, c.a1.x, a00 * c.a0.x);
+          tp[1] = fmaf(a01, c.a1.y, a00 * c.a0.y);
+          tp[2] = fmaf(a01, c.a1.z, a00 * c.a0.z);
+          tp[3] = fmaf(a01, c.a1.w, a00 * c.a0.w);
+          tp[4] = fmaf(a01, c.e1, a00 * c.e0);
+        };
+        auto load_top = [&](const FbRow& R, float (&tp)[5]) {
+          FbCorner c;
+          c.a0 = ldg_f4<0>(r1a + R.ot); c.a1 = ldg_f4<16>(r1a + R.ot);
+          c.e0 = ldg_f1<0>(r1b + R.ot); c.e1 = ldg_f1<4>(r1b + R.ot);
+          top_partial(R, c, tp);
+        };
+        auto stage2 = [&](const FbRow& R, const float (&tp)[5]) {
+          const float a10 = (1.f - R.fx) * R.fy, a11 = R.fx * R.fy;
+          float r2 = fmaf(a11, R.bot.a1.x, fmaf(a10, R.bot.a0.x, tp[0]));
+          float r3 = fmaf(a11, R.bot.a1.y, fmaf(a10, R.bot.a0.y, tp[1]));
+          float r4 = fmaf(a11, R.bot.a1.z, fmaf(a10, R.bot.a0.z, tp[2]));
+          float r5 = fmaf(a11, R.bot.a1.w, fmaf(a10, R.bot.a0.w, tp[3]));
+          float r6 = fmaf(a11, R.bot.e1, fmaf(a10, R.bot.e0, tp[4]));
+          const float4 q = R.q;
+          const float q4 = R.q4;
+          r2 = R.inside ? r2 : 0.f;
+          r3 = R.inside ? r3 : 0.f;
+          r4 = R.inside ? r4 : q.z;               // (q + q) * 0.5 = q, (q4 + q4) * 0.25 = q4 * 0.5: exact
+          r5 = R.inside ? r5 : q.w;
+          r6 = R.inside ? r6 : q4;
+          r4 = (q.z + r4) * 0.5f;
+          r5 = (q.w + r5) * 0.5f;
+          r6 = (q4 + r6) * 0.25f;
+          r2 = (q.x - r2) * 0.5f;
+          r3 = (q.y - r3) * 0.5f;
+          r2 += r4 * R.d.y + r6 * R.d.x;
+          r3 += r6 * R.d.y + r5 * R.d.x;
+          if ((unsigned)(R.y - 5) >= (unsigned)thr) {
+            const float sc = bwx * border_w(R.y, h);
+            r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
+          }
+          sts_f2(s_xy + sa * 8, r4 * r4 + r6 * r6, (r4 + r5) * r6);
+          sts_f2(s_zw + sa * 8, r5 * r5 + r6 * r6, r4 * r2 + r6 * r3);
+          sts_f1(s_e + sa * 4, r6 * r2 + r5 * r3);
+          sa += ES;
+          if (sa == sa_end) sa -= NR * ES;
+        };
+        auto next_row = [&](int& y, int& o) {
+          y = min(max(yu, 0), hm1);
+          o = y * pit + x;
+          ++yu;
+        };
+
+        FbRow A, B;
+        float tp[5];
+        int oA, oB = 0, yn = 0, on = 0;
+        float2 dn = make_float2(0.f, 0.f);
+        next_row(A.y, oA);
+        A.d = fetch_flow_m<MODE>(a, fi, oA, A.y, uxa, uxb, ufx);
+        B.y = A.y; B.d = A.d;
+        if (n > 1) { next_row(B.y, oB); B.d = fetch_flow_m<MODE>(a, fi, oB, B.y, uxa, uxb, ufx); }
+        stage1(A, oA);
+        load_top(A, tp);
+        int k = 0;
+        for (; k + 1 < n; k += 2) {
+          stage1(B, oB);
+          if (k + 2 < n) { next_row(yn, on); dn = fetch_flow_m<MODE>(a, fi, on, yn, uxa, uxb, ufx); }
+          stage2(A, tp);
+          if (B.ot == A.ot + pitb) top_partial(B, A.bot, tp); else load_top(B, tp);
+          A.d = dn; A.y = yn; oA = on;
+          if (k + 2 < n) stage1(A, oA);
+          if (k + 3 < n) { next_row(yn, on); dn = fetch_flow_m<MODE>(a, fi, on, yn, uxa, uxb, ufx); }
+          stage2(B, tp);
+          if (k + 2 < n) { if (A.ot == B.ot + pitb) top_partial(A, B.bot, tp); else load_top(A, tp); }
+          B.d = dn; B.y = yn; oB = on;
+        }
+        if (k < n) stage2(A, tp);
+      }
+      mbar_arrive(s_bar + (s % 3) * 8);                 // full_a[stage]: block s is in the ring
+      j0 += nrows;
+      if (j0 >= NR) j0 -= NR;
+    }
+  } else if (t < FBW_A_WARPS * 32 + 128) {
+    // =========================== B warps: horizontal sums in place ===========================
+    const int bt = t - FBW_A_WARPS * 32, bw = bt >> 5, lane = bt & 31;
+    int plane, rr;
+    bool right, act;
+    if (bw < 3) { plane = bw; rr = lane & 15; right = (lane >> 4) != 0; act = true; }
+    else { plane = lane >> 3; rr = 16 + (lane & 3); right = ((lane >> 2) & 1) != 0; act = lane < 24; }
+    int j0 = 0;
+    for (int s = 0; s < nblk; ++s) {
+      const int nrows = s == 0 ? 2 * M + RB : RB;
+      mbar_wait(s_bar + (s % 3) * 8, (unsigned)((s / 3) & 1));           // full_a[stage]
+      for (int base = 0; base < nrows; base += RB) {
+        const int r = base + rr;
+        if (act && r < nrows) {
+          int pr = j0 + r;
+          if (pr >= NR) pr -= NR;
+          if (plane == 0) hpass_half_row<float2>(Pxy + pr * ES + 1, right);
+          else if (plane == 1) hpass_half_row<float2>(Pzw + pr * ES + 1, right);
+          else hpass_half_row<float>(Pe + pr * ES + 1, right);
+        }
+      }
+      mbar_arrive(s_bar + (3 + s % 3) * 8);             // full_b[stage]
+      j0 += nrows;
+      if (j0 >= NR) j0 -= NR;
+    }
+  } else {
+    // =========================== C warps: vertical running sums + solve ===========================
+    const int ct = t - FBW_A_WARPS * 32 - 128;
+    const bool act = ct < TW && x0 + ct < w;
+    const int col = 1 + (ct < HL ? ct : ct + 2 * M);    // where step B left this column's sums
+    float2* __restrict__ fo = a.flow_out + (size_t)pair * a.flow_out_pair_stride;
+    float2 vxy = make_float2(0.f, 0.f), vzw = vxy;
+    float ve = 0.f;
+    const float eps = 1e-3f / (a.inv_area * a.inv_area);
+    int po = 0;                                         // ring row of the oldest row of the window (row yb - M)
+    for (int s = 0; s < nblk; ++s) {
+      const int yb = ys + s * RB;
+      mbar_wait(s_bar + (3 + s % 3) * 8, (unsigned)((s / 3) & 1));       // full_b[stage]
+      if (act) {
+        int pn = po;
+        if (s == 0 || ((yb / RB) % FBS_REFRESH) == 0) {
+          // (re)start the running sums from the 14 rows above the window's newest row
+          vxy = make_float2(0.f, 0.f); vzw = vxy; ve = 0.f;
+#pragma unroll
+          for (int k = 0; k < 2 * M; ++k) {
+            const int e = pn * ES + col;
+            vxy = add2(vxy, Pxy[e]);
+            vzw = add2(vzw, Pzw[e]);
+            ve += Pe[e];
+            if (++pn == NR) pn = 0;
+          }
+        } else {
+          pn += 2 * M;
+          if (pn >= NR) pn -= NR;
+        }
+        int pold = po;
+        const int nr = min(RB, ye - yb);
+        float2* orow = fo + (size_t)yb * a.out_pitch + (x0 + ct);
+#pragma unroll 4
+        for (int r = 0; r < nr; ++r) {
+          const int en = pn * ES + col, eo = pold * ES + col;
+          vxy = add2(vxy, Pxy[en]);
+          vzw = add2(vzw, Pzw[en]);
+          ve += Pe[en];
+          const float g11 = vxy.x, g12 = vxy.y, g22 = vzw.x, h1 = vzw.y, h2 = ve;
+          const float idet = __frcp_rn(g11 * g22 - g12 * g12 + eps);
+          *orow = make_float2((g11 * h2 - g12 * h1) * idet, (g22 * h1 - g12 * h2) * idet);
+          orow += a.out_pitch;
+          vxy = sub2(vxy, Pxy[eo]);
+          vzw = sub2(vzw, Pzw[eo]);
+          ve -= Pe[eo];
+          if (++pn == NR) pn = 0;
+          if (++pold == NR) pold = 0;
+        }
+      }
+      mbar_arrive(s_bar + (6 + s % 3) * 8);             // empty_c[stage]: block s's oldest rows may be overwritten
+      po += RB;
+      if (po >= NR) po -= NR;
+    }
+  }
+}
