@@ -833,6 +833,9 @@ struct FbCorner { float4 a0, a1; float e0, e1; };   // two horizontally adjacent
 #ifndef FB_EXP
 #define FB_EXP 0
 #endif
+#ifndef FBW_EXP_NOFLOW
+#define FBW_EXP_NOFLOW 0
+#endif
 #ifndef FB_STRIP
 #define FB_STRIP 2
 #endif
@@ -842,6 +845,7 @@ struct FbCorner { float4 a0, a1; float e0, e1; };   // two horizontally adjacent
 
 __device__ __forceinline__ void pin(int& v) { asm volatile("" : "+r"(v)); }
 __device__ __forceinline__ void pin(float& v) { asm volatile("" : "+f"(v)); }
+__device__ __forceinline__ void pin(unsigned& v) { asm volatile("" : "+r"(v)); }
 template <typename T>
 __device__ __forceinline__ void pin(T*& v) { asm volatile("" : "+l"(v)); }
 
@@ -877,7 +881,7 @@ template <int MODE>
 __device__ __forceinline__ float2 fetch_flow_m(const IterArgs& a, const float2* fin, int o, int y, int xa, int xb,
                                                float ufx) {
   if (MODE == 0) return make_float2(0.f, 0.f);
-  if (MODE == 1) return FB_EXP == 1 ? make_float2(0.3f, 0.4f) : ldg_f2(fin + o);
+  if (MODE == 1) return (FB_EXP == 1 || FB_EXP == 7 || FBW_EXP_NOFLOW) ? make_float2(0.3f, 0.4f) : ldg_f2(fin + o);
   int ya = a.uy0[y], yb = a.uy1[y];
   float fy = a.ufy[y];
   float2 p00 = fin[ya * a.in_pitch + xa], p01 = fin[ya * a.in_pitch + xb];

@@ -12,15 +12,35 @@
 // 14 + 3 * FBW_RB rows as three planes (float2 ch0/1, float2 ch2/3, float ch4) with an odd row stride.
 // Arithmetic is the same as fb_iter_strip (fb_strip.cuh), which documents steps A, B and C.
 #pragma once
+#ifndef FBW_SLEEP_NS
+#define FBW_SLEEP_NS 200
+#endif
+#ifndef FBW_PF_AHEAD
+#define FBW_PF_AHEAD 4
+#endif
+#ifndef FBW_SETMAXNREG
+#define FBW_SETMAXNREG 0
+#endif
+#ifndef FBW_A_REGS
+#define FBW_A_REGS 80
+#endif
+#ifndef FBW_PIPE
+#define FBW_PIPE 0
+#endif
+#ifndef FBW_EXP
+#define FBW_EXP 0
+#endif
 
-constexpr int FBW_A_WARPS = 20;
+#ifndef FBW_A_WARPS_N
+#define FBW_A_WARPS_N 16
+#endif
+constexpr int FBW_A_WARPS = FBW_A_WARPS_N;           // 16 (80 registers / thread) or 20 (72)
 constexpr int FBW_NT = (FBW_A_WARPS + 8) * 32;          // 896 threads: 20 A warps, 4 B warps, 4 C warps
 constexpr int FBW_RUNS = FBW_A_WARPS / 4;               // row runs per block in step A (128 columns = 4 warps each)
-constexpr int FBW_RB = 20;                              // rows per block
+constexpr int FBW_RB = FBW_A_WARPS;                     // rows per block: 4 rows per A thread
 constexpr int FBW_NR = 2 * FBS_M + 3 * FBW_RB;          // ring rows (74)
 constexpr size_t FBW_PLANES = (size_t)FBW_NR * FBS_ES * 20;
 constexpr size_t FBW_SMEM = FBW_PLANES + 16 * 8;        // + mbarriers
-static_assert(FBW_A_WARPS == FBW_RB, "one A warp issues the L2 prefetch of one row of the next block");
 
 __device__ __forceinline__ void mbar_init(unsigned addr, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
@@ -29,10 +49,21 @@ __device__ __forceinline__ void mbar_arrive(unsigned addr) {
   asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
+  // poll with back-off: a spinning warp would take issue slots from the warps it is waiting for
   asm volatile(
       "{ .reg .pred p;\n"
-      "W_%=: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@!p bra W_%=;\n }" ::"r"(addr), "r"(parity) : "memory");
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra D_%=;\n"
+      "W_%=: nanosleep.u32 %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra W_%=;\n"
+      "D_%=: }" ::"r"(addr), "r"(parity), "n"(FBW_SLEEP_NS) : "memory");
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {     // 1 ulp; the determinant is >= 1e-3 / inv_area^2 > 0
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 
 // horizontal 15-sums of one ring row of one plane, in place (see fb_iter_strip step B)
@@ -45,30 +76,53 @@ __device__ __forceinline__ T hp_sub(T a, T b);
 template <> __device__ __forceinline__ float2 hp_sub<float2>(float2 a, float2 b) { return sub2(a, b); }
 template <> __device__ __forceinline__ float hp_sub<float>(float a, float b) { return a - b; }
 
+// The 15 most recent inputs stay in a register window (circular, statically indexed: the walk is unrolled by the
+// window length), so every element is read from shared memory once and written once: 2 accesses per element
+// instead of 3 on the unit that bounds the kernel.
 template <typename T>
 __device__ __forceinline__ void hpass_half_row(T* rowp, bool right) {
-  constexpr int M = FBS_M, TW = FBS_TW, HL = FBS_HL;
+  constexpr int M = FBS_M, TW = FBS_TW, HL = FBS_HL, WN = 2 * M + 1;
+  T win[WN];
   if (!right) {
+    // outputs xo = 0 .. HL-1: sum of positions [xo, xo + 14], stored at position xo
     T sm = rowp[0];
+    win[0] = sm;
 #pragma unroll
-    for (int k = 1; k < 2 * M; ++k) sm = hp_add(sm, rowp[k]);
-#pragma unroll 8
-    for (int xo = 0; xo < HL; ++xo) {
-      sm = hp_add(sm, rowp[xo + 2 * M]);
-      const T old = rowp[xo];
-      rowp[xo] = sm;
-      sm = hp_sub(sm, old);
+    for (int k = 1; k < 2 * M; ++k) { win[k] = rowp[k]; sm = hp_add(sm, win[k]); }
+    for (int xb = 0; xb < HL; xb += WN) {
+#pragma unroll
+      for (int j = 0; j < WN; ++j) {
+        const int xo = xb + j;
+        if (xo < HL) {
+          // slot (j + 14) % 15 receives position xo + 14; slot j holds position xo (the one leaving the window)
+          const T nw = rowp[xo + 2 * M];
+          sm = hp_add(sm, nw);
+          rowp[xo] = sm;
+          sm = hp_sub(sm, win[j]);
+          win[(j + 2 * M) % WN] = nw;
+        }
+      }
     }
   } else {
-    T sm = rowp[TW];
+    // outputs xo = TW-1 .. HL: sum of positions [xo, xo + 14], stored at position xo + 14; walk right to left:
+    // mirrored index u = TW - 1 - xo, position q(u, k) = TW - 1 + 14 - u - k
+    T* top = rowp + (TW - 1 + 2 * M);                   // position of the right-most input
+    T sm = top[0];
+    win[0] = sm;
 #pragma unroll
-    for (int k = 1; k < 2 * M; ++k) sm = hp_add(sm, rowp[TW + k]);
-#pragma unroll 8
-    for (int xo = TW - 1; xo >= HL; --xo) {
-      sm = hp_add(sm, rowp[xo]);
-      const T old = rowp[xo + 2 * M];
-      rowp[xo + 2 * M] = sm;
-      sm = hp_sub(sm, old);
+    for (int k = 1; k < 2 * M; ++k) { win[k] = top[-k]; sm = hp_add(sm, win[k]); }
+    for (int ub = 0; ub < TW - HL; ub += WN) {
+#pragma unroll
+      for (int j = 0; j < WN; ++j) {
+        const int u = ub + j;
+        if (u < TW - HL) {
+          const T nw = top[-(u + 2 * M)];
+          sm = hp_add(sm, nw);
+          top[-u] = sm;
+          sm = hp_sub(sm, win[j]);
+          win[(j + 2 * M) % WN] = nw;
+        }
+      }
     }
   }
 }
@@ -104,6 +158,9 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
 
   if (t < FBW_A_WARPS * 32) {
     // =========================== A warps: UpdateMatrices ===========================
+#if FBW_SETMAXNREG
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FBW_A_REGS));   // registers the B / C warps gave back
+#endif
     const float* base0 = a.R + (size_t)pair * a.pair_frame_step * a.r_frame_stride;
     const float4* __restrict__ R0a = (const float4*)base0;
     const float* __restrict__ R0b = base0 + 4 * a.plane_stride;
@@ -118,12 +175,17 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
     int uxa = 0, uxb = 0;
     float ufx = 0.f;
     if (MODE == 2) { uxa = a.ux0[x]; uxb = a.ux1[x]; ufx = a.ufx[x]; }
-    const float4* r0a = R0a; const float* r0b = R0b; const float4* r1a = R1a; const float* r1b = R1b;
+    // one 64-bit base (the pair's R0 record plane) and 32-bit byte offsets to the other three planes: four
+    // pinned pointers would not fit the register budget of the pipelined loop
+    const char* rb = (const char*)R0a;
+    unsigned c_r0b = (unsigned)(16 * a.plane_stride);                       // R0 ch4 plane
+    unsigned c_r1a = (unsigned)(4 * a.r_frame_stride);                      // R1 record plane
+    unsigned c_r1b = c_r1a + c_r0b;                                         // R1 ch4 plane
     const float2* fi = fin;
     int wm1 = w - 1, hm1 = h - 1, pit = pitch;
     int pitb = h > 1 ? pitch : 0;                       // keeps the unused bottom-corner loads in bounds
     int thr = xb_border ? 0 : h - 10;                   // (unsigned)(y - 5) >= thr  <=>  border pixel
-    pin(r0a); pin(r0b); pin(r1a); pin(r1b); pin(fi); pin(wm1); pin(hm1); pin(pit); pin(pitb); pin(thr);
+    pin(rb); pin(c_r0b); pin(c_r1a); pin(c_r1b); pin(fi); pin(wm1); pin(hm1); pin(pit); pin(pitb); pin(thr);
 
     int j0 = 0;                                         // ring row (mod NR) of the first new M row of the block
     for (int s = 0; s < nblk; ++s) {
@@ -131,20 +193,6 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
       const int nrows = s == 0 ? 2 * M + RB : RB;       // M rows [y_first, y_first + nrows), y_first below
       const int y_first = s == 0 ? yb - M : yb + M;     // image row of the first new M row
       if (s >= 3) mbar_wait(s_bar + (6 + s % 3) * 8, (unsigned)((s / 3 - 1) & 1));   // C is done with block s - 3
-
-      // L2 prefetch of the next block's new rows by the copy engine: one bulk prefetch per (row, stream)
-      if ((t & 31) == 0 && s + 1 < nblk) {
-        const int r = t >> 5;                            // warp = row of the next block (FBW_A_WARPS == FBW_RB)
-        const int yy = min(yb + RB + M + r, h - 1);
-        const int xs = max(x0 - FBS_PADL, 0);
-        const int cols = min(EW, pitch - xs);
-        const size_t o = (size_t)yy * pitch + xs;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(R0a + o), "r"(cols * 16) : "memory");
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(R1a + o), "r"(cols * 16) : "memory");
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(R0b + o), "r"(cols * 4) : "memory");
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(R1b + o), "r"(cols * 4) : "memory");
-        if (MODE == 1) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(fin + o), "r"(cols * 8) : "memory");
-      }
 
       const int RS = (nrows + FBW_RUNS - 1) / FBW_RUNS;
       const int l0 = run * RS;
@@ -157,16 +205,29 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
         int yu = y_first + l0;                          // unclamped image row of the row being set up
 
         auto stage1 = [&](FbRow& R, int o) {
-          R.q = ldg_f4<0>(r0a + o);
-          R.q4 = ldg_f1<0>(r0b + o);
+#if FBW_EXP == 3 || FBW_EXP == 5
+          R.q = make_float4(xf, 1.f, 2.f, 3.f); R.q4 = 0.5f;
+#else
+          R.q = ldg_f4<0>((const float4*)(rb + (unsigned)o * 16u));
+          R.q4 = ldg_f1<0>((const float*)(rb + ((unsigned)o * 4u + c_r0b)));
+#endif
           float fx = xf + R.d.x, fy = (float)R.y + R.d.y;
           const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
           R.fx = fx - (float)x1; R.fy = fy - (float)y1;
           R.inside = (unsigned)x1 < (unsigned)wm1 && (unsigned)y1 < (unsigned)hm1;
           R.ot = R.inside ? y1 * pit + x1 : 0;
+#if FBW_EXP == 2
+          R.ot = o;
+#endif
           const int ob = R.ot + pitb;
-          R.bot.a0 = ldg_f4<0>(r1a + ob); R.bot.a1 = ldg_f4<16>(r1a + ob);
-          R.bot.e0 = ldg_f1<0>(r1b + ob); R.bot.e1 = ldg_f1<4>(r1b + ob);
+#if FBW_EXP == 1 || FBW_EXP == 5
+          R.bot.a0 = R.q; R.bot.a1 = R.q; R.bot.e0 = R.q4; R.bot.e1 = R.q4;
+#else
+          const float4* pa = (const float4*)(rb + ((unsigned)ob * 16u + c_r1a));
+          const float* pe = (const float*)(rb + ((unsigned)ob * 4u + c_r1b));
+          R.bot.a0 = ldg_f4<0>(pa); R.bot.a1 = ldg_f4<16>(pa);
+          R.bot.e0 = ldg_f1<0>(pe); R.bot.e1 = ldg_f1<4>(pe);
+#endif
         };
         auto top_partial = [&](const FbRow& R, const FbCorner& c, float (&tp)[5]) {
           const float gy = 1.f - R.fy;
@@ -179,8 +240,13 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
         };
         auto load_top = [&](const FbRow& R, float (&tp)[5]) {
           FbCorner c;
-          c.a0 = ldg_f4<0>(r1a + R.ot); c.a1 = ldg_f4<16>(r1a + R.ot);
-          c.e0 = ldg_f1<0>(r1b + R.ot); c.e1 = ldg_f1<4>(r1b + R.ot);
+#if FBW_EXP == 5 || FBW_EXP == 1
+          c = R.bot; top_partial(R, c, tp); return;
+#endif
+          const float4* pa = (const float4*)(rb + ((unsigned)R.ot * 16u + c_r1a));
+          const float* pe = (const float*)(rb + ((unsigned)R.ot * 4u + c_r1b));
+          c.a0 = ldg_f4<0>(pa); c.a1 = ldg_f4<16>(pa);
+          c.e0 = ldg_f1<0>(pe); c.e1 = ldg_f1<4>(pe);
           top_partial(R, c, tp);
         };
         auto stage2 = [&](const FbRow& R, const float (&tp)[5]) {
@@ -220,6 +286,7 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
           ++yu;
         };
 
+#if FBW_PIPE
         FbRow A, B;
         float tp[5];
         int oA, oB = 0, yn = 0, on = 0;
@@ -244,6 +311,75 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
           B.d = dn; B.y = yn; oB = on;
         }
         if (k < n) stage2(A, tp);
+#else
+        // plain form (64 registers): a row's loads are issued and consumed in the same iteration; only the flow
+        // vector is fetched one row ahead; bottom corners carried as the next row's top corners
+        FbCorner cA, cB;
+        cA.a0 = cA.a1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        cA.e0 = cA.e1 = 0.f;
+        cB = cA;
+        int o_carry = -1 << 30;
+        int yA, oA, yB = 0, oB = 0;
+        next_row(yA, oA);
+        float2 dA = fetch_flow_m<MODE>(a, fi, oA, yA, uxa, uxb, ufx), dB = dA;
+        auto rowf = [&](const float2 d, float2& dn, const int y, int& yn, const int o, int& on, bool has_next,
+                        FbCorner& top, FbCorner& bot) {
+          const float4 q = ldg_f4<0>((const float4*)(rb + (unsigned)o * 16u));
+          const float q4 = ldg_f1<0>((const float*)(rb + ((unsigned)o * 4u + c_r0b)));
+          if (has_next) { next_row(yn, on); dn = fetch_flow_m<MODE>(a, fi, on, yn, uxa, uxb, ufx); }
+          float fx = xf + d.x, fy = (float)y + d.y;
+          const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
+          fx -= (float)x1; fy -= (float)y1;
+          const bool inside = (unsigned)x1 < (unsigned)wm1 && (unsigned)y1 < (unsigned)hm1;
+          const int ot = inside ? y1 * pit + x1 : 0;
+          if (ot != o_carry) {
+            const float4* pa = (const float4*)(rb + ((unsigned)ot * 16u + c_r1a));
+            const float* pe = (const float*)(rb + ((unsigned)ot * 4u + c_r1b));
+            top.a0 = ldg_f4<0>(pa); top.a1 = ldg_f4<16>(pa); top.e0 = ldg_f1<0>(pe); top.e1 = ldg_f1<4>(pe);
+          }
+          const int ob = ot + pitb;
+          {
+            const float4* pa = (const float4*)(rb + ((unsigned)ob * 16u + c_r1a));
+            const float* pe = (const float*)(rb + ((unsigned)ob * 4u + c_r1b));
+            bot.a0 = ldg_f4<0>(pa); bot.a1 = ldg_f4<16>(pa); bot.e0 = ldg_f1<0>(pe); bot.e1 = ldg_f1<4>(pe);
+          }
+          o_carry = ob;
+          const float gx = 1.f - fx, gy = 1.f - fy;
+          const float a00 = gx * gy, a01 = fx * gy, a10 = gx * fy, a11 = fx * fy;
+          float r2 = fmaf(a11, bot.a1.x, fmaf(a10, bot.a0.x, fmaf(a01, top.a1.x, a00 * top.a0.x)));
+          float r3 = fmaf(a11, bot.a1.y, fmaf(a10, bot.a0.y, fmaf(a01, top.a1.y, a00 * top.a0.y)));
+          float r4 = fmaf(a11, bot.a1.z, fmaf(a10, bot.a0.z, fmaf(a01, top.a1.z, a00 * top.a0.z)));
+          float r5 = fmaf(a11, bot.a1.w, fmaf(a10, bot.a0.w, fmaf(a01, top.a1.w, a00 * top.a0.w)));
+          float r6 = fmaf(a11, bot.e1, fmaf(a10, bot.e0, fmaf(a01, top.e1, a00 * top.e0)));
+          r2 = inside ? r2 : 0.f;
+          r3 = inside ? r3 : 0.f;
+          r4 = inside ? r4 : q.z;
+          r5 = inside ? r5 : q.w;
+          r6 = inside ? r6 : q4;
+          r4 = (q.z + r4) * 0.5f;
+          r5 = (q.w + r5) * 0.5f;
+          r6 = (q4 + r6) * 0.25f;
+          r2 = (q.x - r2) * 0.5f;
+          r3 = (q.y - r3) * 0.5f;
+          r2 += r4 * d.y + r6 * d.x;
+          r3 += r6 * d.y + r5 * d.x;
+          if ((unsigned)(y - 5) >= (unsigned)thr) {
+            const float sc = bwx * border_w(y, h);
+            r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
+          }
+          sts_f2(s_xy + sa * 8, r4 * r4 + r6 * r6, (r4 + r5) * r6);
+          sts_f2(s_zw + sa * 8, r5 * r5 + r6 * r6, r4 * r2 + r6 * r3);
+          sts_f1(s_e + sa * 4, r6 * r2 + r5 * r3);
+          sa += ES;
+          if (sa == sa_end) sa -= NR * ES;
+        };
+        int k = 0;
+        for (; k + 1 < n; k += 2) {
+          rowf(dA, dB, yA, yB, oA, oB, true, cA, cB);
+          rowf(dB, dA, yB, yA, oB, oA, k + 2 < n, cB, cA);
+        }
+        if (k < n) rowf(dA, dB, yA, yB, oA, oB, false, cA, cB);
+#endif
       }
       mbar_arrive(s_bar + (s % 3) * 8);                 // full_a[stage]: block s is in the ring
       j0 += nrows;
@@ -251,18 +387,22 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
     }
   } else if (t < FBW_A_WARPS * 32 + 128) {
     // =========================== B warps: horizontal sums in place ===========================
+#if FBW_SETMAXNREG
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+#endif
     const int bt = t - FBW_A_WARPS * 32, bw = bt >> 5, lane = bt & 31;
-    int plane, rr;
-    bool right, act;
-    if (bw < 3) { plane = bw; rr = lane & 15; right = (lane >> 4) != 0; act = true; }
-    else { plane = lane >> 3; rr = 16 + (lane & 3); right = ((lane >> 2) & 1) != 0; act = lane < 24; }
+    const int rr = lane & 15;
+    const bool right = (lane >> 4) != 0;
     int j0 = 0;
     for (int s = 0; s < nblk; ++s) {
       const int nrows = s == 0 ? 2 * M + RB : RB;
       mbar_wait(s_bar + (s % 3) * 8, (unsigned)((s / 3) & 1));           // full_a[stage]
-      for (int base = 0; base < nrows; base += RB) {
-        const int r = base + rr;
-        if (act && r < nrows) {
+      // work units = (group of 16 rows, plane), dealt round-robin to the four B warps; lane = row x half
+      const int units = ((nrows + 15) >> 4) * 3;
+      for (int u = bw; u < units; u += 4) {
+        const int grp = u / 3, plane = u - grp * 3;
+        const int r = grp * 16 + rr;
+        if (r < nrows) {
           int pr = j0 + r;
           if (pr >= NR) pr -= NR;
           if (plane == 0) hpass_half_row<float2>(Pxy + pr * ES + 1, right);
@@ -276,6 +416,9 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
     }
   } else {
     // =========================== C warps: vertical running sums + solve ===========================
+#if FBW_SETMAXNREG
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+#endif
     const int ct = t - FBW_A_WARPS * 32 - 128;
     const bool act = ct < TW && x0 + ct < w;
     const int col = 1 + (ct < HL ? ct : ct + 2 * M);    // where step B left this column's sums
@@ -283,6 +426,31 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
     float2 vxy = make_float2(0.f, 0.f), vzw = vxy;
     float ve = 0.f;
     const float eps = 1e-3f / (a.inv_area * a.inv_area);
+    // the C warps also feed the copy engine: L2 prefetch of the rows step A will need FBW_PF_AHEAD blocks from now,
+    // one bulk prefetch per (row, stream), issued by lanes 0..4 of each C warp for RB / 4 rows
+    const float* pbase0 = a.R + (size_t)pair * a.pair_frame_step * a.r_frame_stride;
+    const int pf_xs = max(x0 - FBS_PADL, 0);
+    const int pf_cols = min(EW, pitch - pf_xs);
+    auto prefetch_block = [&](int sb) {                 // rows of M that block sb adds: image rows [y0, y0 + nrows)
+      if (sb >= nblk) return;
+      const int lane = ct & 31, cw = ct >> 5;
+      if (lane >= 5 || (lane == 4 && MODE != 1)) return;
+      const int nrows = sb == 0 ? 2 * M + RB : RB;
+      const int y0 = sb == 0 ? ys - M : ys + sb * RB + M;
+      for (int r = cw; r < nrows; r += 4) {
+        const int yy = min(max(y0 + r, 0), h - 1);
+        const size_t o = (size_t)yy * pitch + pf_xs;
+        const void* p;
+        int bytes;
+        if (lane == 0) { p = (const float4*)pbase0 + o; bytes = pf_cols * 16; }
+        else if (lane == 1) { p = (const float4*)(pbase0 + a.r_frame_stride) + o; bytes = pf_cols * 16; }
+        else if (lane == 2) { p = pbase0 + 4 * a.plane_stride + o; bytes = pf_cols * 4; }
+        else if (lane == 3) { p = pbase0 + a.r_frame_stride + 4 * a.plane_stride + o; bytes = pf_cols * 4; }
+        else { p = a.flow_in + (size_t)pair * a.flow_in_pair_stride + o; bytes = pf_cols * 8; }
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+      }
+    };
+    for (int sb = 0; sb < FBW_PF_AHEAD; ++sb) prefetch_block(sb);
     int po = 0;                                         // ring row of the oldest row of the window (row yb - M)
     for (int s = 0; s < nblk; ++s) {
       const int yb = ys + s * RB;
@@ -307,24 +475,36 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
         int pold = po;
         const int nr = min(RB, ye - yb);
         float2* orow = fo + (size_t)yb * a.out_pitch + (x0 + ct);
-#pragma unroll 4
+        // software-pipelined one row deep: the six shared-memory reads of row r + 1 are in flight while row r is
+        // solved (this serial walk is the pipeline's critical stage: one warp per scheduler, in-order issue)
+        float2 nxy = Pxy[pn * ES + col], nzw = Pzw[pn * ES + col], oxy = Pxy[pold * ES + col], ozw = Pzw[pold * ES + col];
+        float ne = Pe[pn * ES + col], oe = Pe[pold * ES + col];
+#pragma unroll 2
         for (int r = 0; r < nr; ++r) {
-          const int en = pn * ES + col, eo = pold * ES + col;
-          vxy = add2(vxy, Pxy[en]);
-          vzw = add2(vzw, Pzw[en]);
-          ve += Pe[en];
-          const float g11 = vxy.x, g12 = vxy.y, g22 = vzw.x, h1 = vzw.y, h2 = ve;
-          const float idet = __frcp_rn(g11 * g22 - g12 * g12 + eps);
-          *orow = make_float2((g11 * h2 - g12 * h1) * idet, (g22 * h1 - g12 * h2) * idet);
-          orow += a.out_pitch;
-          vxy = sub2(vxy, Pxy[eo]);
-          vzw = sub2(vzw, Pzw[eo]);
-          ve -= Pe[eo];
           if (++pn == NR) pn = 0;
           if (++pold == NR) pold = 0;
+          float2 nxy2 = nxy, nzw2 = nzw, oxy2 = oxy, ozw2 = ozw;
+          float ne2 = ne, oe2 = oe;
+          if (r + 1 < nr) {
+            const int en = pn * ES + col, eo = pold * ES + col;
+            nxy2 = Pxy[en]; nzw2 = Pzw[en]; ne2 = Pe[en];
+            oxy2 = Pxy[eo]; ozw2 = Pzw[eo]; oe2 = Pe[eo];
+          }
+          vxy = add2(vxy, nxy);
+          vzw = add2(vzw, nzw);
+          ve += ne;
+          const float g11 = vxy.x, g12 = vxy.y, g22 = vzw.x, h1 = vzw.y, h2 = ve;
+          const float idet = rcp_approx(g11 * g22 - g12 * g12 + eps);
+          *orow = make_float2((g11 * h2 - g12 * h1) * idet, (g22 * h1 - g12 * h2) * idet);
+          orow += a.out_pitch;
+          vxy = sub2(vxy, oxy);
+          vzw = sub2(vzw, ozw);
+          ve -= oe;
+          nxy = nxy2; nzw = nzw2; ne = ne2; oxy = oxy2; ozw = ozw2; oe = oe2;
         }
       }
       mbar_arrive(s_bar + (6 + s % 3) * 8);             // empty_c[stage]: block s's oldest rows may be overwritten
+      prefetch_block(s + FBW_PF_AHEAD);
       po += RB;
       if (po >= NR) po -= NR;
     }
