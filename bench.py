@@ -272,7 +272,7 @@ def main():
                 "api": "cv2compat.calcOpticalFlowFarnebackSequence -> b2of_farneback_sequence_host (pinned host buffers; "
                        "H2D of the frames and D2H of every flow field inside the timed region)"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "fb_iter<false> @ finest level (fused UpdateMatrices+box+solve)",
+        "roofline": {"bound": "hbm", "kernel": "fb_iter_ws @ finest level (warp-specialised fused UpdateMatrices + 15x15 box + 2x2 solve)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                      "traffic": traffic, "peak_source": peak_src, "launches": dom["launches"],
                      "avg_launch_ms": dom["ms"] / dom["launches"] if dom["launches"] else None,

@@ -753,13 +753,11 @@ __global__ void __launch_bounds__(320) fb_polyexp_n(const float* __restrict__ I,
 //        vertical pass straight into the solve
 //   -> per-pixel 2x2 solve -> flow_out
 // Packed f32x2 adds (FADD2) carry 4 of the 5 channels two at a time.
-// Specialised for the reference's window (T=56, m=7: 99.4 KB smem, 2 CTAs/SM); generic <0,0> takes any m.
+// This is the GENERAL form (any window radius at run time, box or Gaussian window: template <NT, 0, 0, GAUSS, MODE>;
+// the compile-time tile / radius parameters CT / CM are kept for experiments).  The reference's own window
+// (winsize 15, box) runs on the warp-specialised strip kernel fb_iter_ws (fb_ws.cuh).
 // ----------------------------------------------------------------------------------------------
 constexpr int IT_THREADS = 512;
-constexpr int IT_T_FAST = 56;
-#ifndef IT_NT_FAST
-#define IT_NT_FAST 512
-#endif
 
 struct IterArgs {
   const float* R;          // level base, [frame]{float4 plane ch0..3, float plane ch4}
@@ -818,30 +816,8 @@ __device__ __forceinline__ float2 solve2x2(float g11, float g12, float g22, floa
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-__device__ __forceinline__ void touch_l2(const void* p) {
-  unsigned v;
-  asm volatile("ld.global.cg.b32 %0, [%1];" : "=r"(v) : "l"(p));
-}
 struct FbCorner { float4 a0, a1; float e0, e1; };   // two horizontally adjacent R1 records (ch0..3, ch4)
 
-#ifndef FB_L2_PREFETCH
-#define FB_L2_PREFETCH 1
-#endif
-#ifndef FB_PAIR_FASTEST
-#define FB_PAIR_FASTEST 1
-#endif
-#ifndef FB_EXP
-#define FB_EXP 0
-#endif
-#ifndef FBW_EXP_NOFLOW
-#define FBW_EXP_NOFLOW 0
-#endif
-#ifndef FB_STRIP
-#define FB_STRIP 2
-#endif
-#ifndef FB_PF_DIST
-#define FB_PF_DIST 4
-#endif
 
 __device__ __forceinline__ void pin(int& v) { asm volatile("" : "+r"(v)); }
 __device__ __forceinline__ void pin(float& v) { asm volatile("" : "+f"(v)); }
@@ -881,7 +857,7 @@ template <int MODE>
 __device__ __forceinline__ float2 fetch_flow_m(const IterArgs& a, const float2* fin, int o, int y, int xa, int xb,
                                                float ufx) {
   if (MODE == 0) return make_float2(0.f, 0.f);
-  if (MODE == 1) return (FB_EXP == 1 || FB_EXP == 7 || FBW_EXP_NOFLOW) ? make_float2(0.3f, 0.4f) : ldg_f2(fin + o);
+  if (MODE == 1) return ldg_f2(fin + o);
   int ya = a.uy0[y], yb = a.uy1[y];
   float fy = a.ufy[y];
   float2 p00 = fin[ya * a.in_pitch + xa], p01 = fin[ya * a.in_pitch + xb];
@@ -903,8 +879,8 @@ __global__ void __launch_bounds__(NT, CT ? 2 : 1) fb_iter(IterArgs a) {
   float* sM1 = smem + 4 * E * ES;   // [E][ES]  (M4)
   // launch order: pair index fastest, so the CTAs of pairs p and p + 1 on the same tile run together and the
   // expansion of frame p + 1 (R1 of pair p, R0 of pair p + 1) comes from HBM once and from L2 the second time
-  const int pair = FB_PAIR_FASTEST ? blockIdx.x : blockIdx.z;
-  const int bx = FB_PAIR_FASTEST ? blockIdx.y : blockIdx.x, by = FB_PAIR_FASTEST ? blockIdx.z : blockIdx.y;
+  const int pair = blockIdx.x;
+  const int bx = blockIdx.y, by = blockIdx.z;
   const int x0 = bx * T;
   const int w = a.w, h = a.h, pitch = a.pitch;
   const float* base0 = a.R + (size_t)pair * a.pair_frame_step * a.r_frame_stride;
@@ -950,33 +926,20 @@ __global__ void __launch_bounds__(NT, CT ? 2 : 1) fb_iter(IterArgs a) {
     // advanced by exactly one row (almost always: the flow is smooth), so they are carried in registers and only
     // the two new corners are loaded.  The loop is unrolled by two with the carried / new corner sets swapping
     // roles (no register moves); the flow vector of the next row is fetched one row ahead.
-    if (FB_EXP != 4 && ty < RP) {
+    if (ty < RP) {
       const int RS = (nrows + RP - 1) / RP;
       int l = lstart + ty * RS;
       const int l_end = min(l + RS, E);
-      // first touches come from HBM (flow, R0, most of the R1 neighbourhood).  The rows of a tile are pulled into
-      // L2 one tile ahead: the first tile of a CTA prefetches its own rows up front, every tile prefetches the new
-      // rows of the next one (FB_L2_PREFETCH 2: after its own gathers are issued, 3: before them; 1: own rows only)
-      auto prefetch_rows = [&](int ytop, int r0, int r1) {
-        for (int r = r0; r < r1; ++r) {
-          const int yy = clampi(ytop - m + r, 0, h - 1);
-          const int o = yy * pitch + x;
-          if (MODE == 1) prefetch_l2(fin + o);
-          prefetch_l2(R0a + o);
-          prefetch_l2(R0b + o);
-          prefetch_l2(R1a + o);
-          prefetch_l2(R1b + o);
-        }
-      };
-      const bool pf_next = FB_L2_PREFETCH >= 2 && c + 1 < a.nb && y0 + T < h;
-      const int rs_next = (T + RP - 1) / RP;
-      if (FB_L2_PREFETCH == 1 || ((FB_L2_PREFETCH == 2 || FB_L2_PREFETCH == 3) && c == 0)) prefetch_rows(y0, l, l_end);
-      // FB_L2_PREFETCH 4: rolling prefetch FB_PF_DIST rows ahead in this thread's own row sequence (its run in this
-      // tile, then its run in the next tile): a small L2 footprint per CTA instead of a whole tile at once
-      if ((FB_L2_PREFETCH == 4 || FB_L2_PREFETCH == 5) && c == 0) prefetch_rows(y0, l, min(l + FB_PF_DIST, l_end));
-      const int nl0 = 2 * m + ty * rs_next, nl1 = min(nl0 + rs_next, E);   // this thread's run in the next tile
-      if (FB_L2_PREFETCH == 3 && pf_next)
-        prefetch_rows(y0 + T, 2 * m + ty * rs_next, min(2 * m + (ty + 1) * rs_next, E));
+      // first touches come from HBM (flow, R0, most of the R1 neighbourhood): pull the run into L2 now
+      for (int r = l; r < l_end; ++r) {
+        const int yy = clampi(y0 - m + r, 0, h - 1);
+        const int o = yy * pitch + x;
+        if (MODE == 1) prefetch_l2(fin + o);
+        prefetch_l2(R0a + o);
+        prefetch_l2(R0b + o);
+        prefetch_l2(R1a + o);
+        prefetch_l2(R1b + o);
+      }
       if (l < l_end) {
         int pr = l + off;
         if (pr >= E) pr -= E;
@@ -1000,32 +963,9 @@ __global__ void __launch_bounds__(NT, CT ? 2 : 1) fb_iter(IterArgs a) {
         int oA = yA * pit + x, oB = oA;
         float2 dA = fetch_flow_m<MODE>(a, fi, oA, yA, uxa, uxb, ufx), dB = dA;
         auto row = [&](const float2 d, float2& dn, const int y, int& yn, const int o, int& on, bool has_next,
-                       FbCorner& top, FbCorner& bot, int lcur) {
-#if FB_EXP == 1   // timing experiment: no streamed loads (R0, flow)
-          const float4 q = make_float4(xf, (float)y, 1.f, 2.f);
-          const float q4 = xf * 0.001f;
-#else
+                       FbCorner& top, FbCorner& bot) {
           const float4 q = ldg_f4<0>(r0a + o);
           const float q4 = ldg_f1<0>(r0b + o);
-#endif
-          if (FB_L2_PREFETCH == 4 || FB_L2_PREFETCH == 5) {
-            int lt = lcur + FB_PF_DIST, yt = -1;
-            if (lt < l_end) yt = y0 - m + lt;
-            else if (pf_next && nl0 + (lt - l_end) < nl1) yt = y0 + T - m + nl0 + (lt - l_end);
-            if (yt >= 0) {
-              const int op = min(yt, hm1) * pit + x;
-              if (FB_L2_PREFETCH == 5) {          // experiment: real (discarded) L2-only loads instead of prefetch hints
-                if (MODE == 1) touch_l2(fi + op);
-                touch_l2(r0a + op); touch_l2(r0b + op); touch_l2(r1a + op); touch_l2(r1b + op);
-              } else {
-                if (MODE == 1) prefetch_l2(fi + op);
-                prefetch_l2(r0a + op);
-                prefetch_l2(r0b + op);
-                prefetch_l2(r1a + op);
-                prefetch_l2(r1b + op);
-              }
-            }
-          }
           ++yu;
           if (has_next) {
             yn = min(max(yu, 0), hm1);
@@ -1037,17 +977,13 @@ __global__ void __launch_bounds__(NT, CT ? 2 : 1) fb_iter(IterArgs a) {
           fx -= (float)x1; fy -= (float)y1;
           const bool inside = (unsigned)x1 < (unsigned)wm1 && (unsigned)y1 < (unsigned)hm1;
           const int ot = inside ? y1 * pit + x1 : 0;
-          if (FB_EXP != 2 && ot != o_carry) {   // top corners are not the carried bottom corners: load them
+          if (ot != o_carry) {                  // top corners are not the carried bottom corners: load them
             top.a0 = ldg_f4<0>(r1a + ot); top.a1 = ldg_f4<16>(r1a + ot);
             top.e0 = ldg_f1<0>(r1b + ot); top.e1 = ldg_f1<4>(r1b + ot);
           }
           const int ob = ot + pitb;
-#if FB_EXP == 2   // timing experiment: no gathers
-          bot.a0 = q; bot.a1 = q; bot.e0 = q4; bot.e1 = q4;
-#else
           bot.a0 = ldg_f4<0>(r1a + ob); bot.a1 = ldg_f4<16>(r1a + ob);
           bot.e0 = ldg_f1<0>(r1b + ob); bot.e1 = ldg_f1<4>(r1b + ob);
-#endif
           o_carry = ob;
           const float gx = 1.f - fx, gy = 1.f - fy;
           const float a00 = gx * gy, a01 = fx * gy, a10 = gx * fy, a11 = fx * fy;
@@ -1078,13 +1014,11 @@ __global__ void __launch_bounds__(NT, CT ? 2 : 1) fb_iter(IterArgs a) {
           if (sa4 == sa4_end) { sa4 -= E * ES * 16; sa1 -= E * ES * 4; }   // ring wrap
         };
         for (; l + 1 < l_end; l += 2) {
-          row(dA, dB, yA, yB, oA, oB, true, cA, cB, l);
-          row(dB, dA, yB, yA, oB, oA, l + 2 < l_end, cB, cA, l + 1);
+          row(dA, dB, yA, yB, oA, oB, true, cA, cB);
+          row(dB, dA, yB, yA, oB, oA, l + 2 < l_end, cB, cA);
         }
-        if (l < l_end) row(dA, dB, yA, yB, oA, oB, false, cA, cB, l);
+        if (l < l_end) row(dA, dB, yA, yB, oA, oB, false, cA, cB);
       }
-      if (FB_L2_PREFETCH == 2 && pf_next)
-        prefetch_rows(y0 + T, 2 * m + ty * rs_next, min(2 * m + (ty + 1) * rs_next, E));
     }
     __syncthreads();
 
@@ -1095,7 +1029,7 @@ __global__ void __launch_bounds__(NT, CT ? 2 : 1) fb_iter(IterArgs a) {
     {
       const int gs = (E + 31) & ~31;            // group stride: each group starts on a warp boundary
       const int g = t / gs, r = t - g * gs;
-      if (FB_EXP != 3 && g < 4 && r < nrows) {
+      if (g < 4 && r < nrows) {
         int pr = lstart + r + off;
         if (pr >= E) pr -= E;
         const bool right = g & 1;
@@ -1181,7 +1115,7 @@ __global__ void __launch_bounds__(NT, CT ? 2 : 1) fb_iter(IterArgs a) {
       const int seg = t / T, xo = t - seg * T;
       const int gx = x0 + xo;
       const int xs = xo < HL ? xo : xo + 2 * m;   // where step B left this column's sums
-      if (FB_EXP != 3 && seg < nseg && gx < w) {
+      if (seg < nseg && gx < w) {
         const int r0 = seg * segr;
         const int r1 = min(r0 + segr, T);
         if (GAUSS) {
@@ -1231,7 +1165,6 @@ __global__ void __launch_bounds__(NT, CT ? 2 : 1) fb_iter(IterArgs a) {
   }
 }
 
-#include "fb_strip.cuh"
 #include "fb_ws.cuh"
 
 // ----------------------------------------------------------------------------------------------
@@ -1397,16 +1330,12 @@ static void set_func_attrs() {
   cudaFuncSetAttribute(fb_iter<NT_, CT_, CM_, G_, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);    \
   cudaFuncSetAttribute(fb_iter<NT_, CT_, CM_, G_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);    \
   cudaFuncSetAttribute(fb_iter<NT_, CT_, CM_, G_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  B2OF_ATTR(IT_NT_FAST, IT_T_FAST, 7, false)
   B2OF_ATTR(512, 0, 0, false)
   B2OF_ATTR(512, 0, 0, true)
 #undef B2OF_ATTR
   cudaFuncSetAttribute(fb_iter_ws<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
   cudaFuncSetAttribute(fb_iter_ws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
   cudaFuncSetAttribute(fb_iter_ws<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
-  cudaFuncSetAttribute(fb_iter_strip<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBS_SMEM);
-  cudaFuncSetAttribute(fb_iter_strip<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBS_SMEM);
-  cudaFuncSetAttribute(fb_iter_strip<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBS_SMEM);
   cudaFuncSetAttribute(fb_polyexp, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   cudaFuncSetAttribute(fb_level_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 }
@@ -1418,17 +1347,21 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
   const int call_flags = p.flags;
   const int m = p.winsize / 2;
   const bool gauss = (p.flags & B2OF_OPTFLOW_FARNEBACK_GAUSSIAN) != 0;
-  // tile: the specialised kernel for the reference's window, else the largest tile whose halo fits one SM
-  const bool fast = !gauss && m == 7;
-  int tile = IT_T_FAST;
-  if (!fast) {
-    tile = 64;
-    while (tile > 16 && (size_t)5 * (tile + 2 * m) * ((tile + 2 * m) | 1) * sizeof(float) > 200 * 1024) tile -= 8;
-  }
+  // the reference's window runs on the strip kernel; anything else on the general kernel with the largest tile whose
+  // halo fits one SM
+  const bool fast = !gauss && m == FBS_M;
+  int tile = 64;
+  while (tile > 16 && (size_t)5 * (tile + 2 * m) * ((tile + 2 * m) | 1) * sizeof(float) > 200 * 1024) tile -= 8;
   const int E = tile + 2 * m;
   size_t smem = (size_t)5 * E * (E | 1) * sizeof(float);
-  if (smem > 227 * 1024 || (!fast && E > IT_THREADS / 4))
+  if (!fast && (smem > 227 * 1024 || E > IT_THREADS / 4))
     return fail(B2OF_E_UNSUPPORTED, "winsize %d needs %zu B of shared memory", p.winsize, smem);
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+  }
   size_t lvl_off = 0;
   const float2* coarse = nullptr;
   int cpitch = 0, cw = 0, ch = 0;
@@ -1457,14 +1390,11 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
     // vertical streaming: as many tiles per CTA as still leaves >= ~4 waves of CTAs
     const int cx = cdiv(L.w, tile), cy = cdiv(L.h, tile);
     int nb = (int)(((long long)cx * cy * pairs) / (4 * 296));
-#ifndef FB_NB_CAP
-#define FB_NB_CAP 8
-#endif
-    const int nb_cap = FB_NB_CAP;
+    const int nb_cap = 8;
     nb = nb < 1 ? 1 : (nb > nb_cap ? nb_cap : nb);
     nb = cdiv(cy, cdiv(cy, nb));                 // balance the row groups
     a.nb = nb;
-    dim3 grid = FB_PAIR_FASTEST ? dim3(pairs, cx, cdiv(cy, nb)) : dim3(cx, cdiv(cy, nb), pairs);
+    dim3 grid(pairs, cx, cdiv(cy, nb));
     int iters = p.iterations;
     if (iters == 0) {
       // cv2 with iterations == 0 returns the (upsampled) initial flow of the finest level untouched;
@@ -1514,32 +1444,20 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
     else if (a.mode == 1) fb_iter<NT_, CT_, CM_, G_, 1><<<grid, NT_, smem, st>>>(a);        \
     else fb_iter<NT_, CT_, CM_, G_, 2><<<grid, NT_, smem, st>>>(a);                         \
   } while (0)
-        if (fast && FB_STRIP == 2) {
-          // warp-specialised strip kernel: one CTA per SM, 112-column strips, nseg row segments of nb 20-row blocks
+        if (fast) {
+          // warp-specialised strip kernel: one CTA per SM, 112-column strips, nseg row segments of nb 16-row blocks
+          // (at least two waves of CTAs when the batch is small)
           IterArgs b = a;
           const int nstrips = cdiv(L.w, FBS_TW), blocks = cdiv(L.h, FBW_RB);
-          int nseg = cdiv(2 * 148, pairs * nstrips);
+          int nseg = cdiv(2 * n_sm, pairs * nstrips);
           nseg = nseg < 1 ? 1 : (nseg > blocks ? blocks : nseg);
-          b.nb = cdiv(cdiv(blocks, nseg), FBS_REFRESH) * FBS_REFRESH;   // segments start on refresh blocks: results
+          b.nb = cdiv(cdiv(blocks, nseg), FBW_REFRESH) * FBW_REFRESH;   // segments start on refresh blocks: results
                                                                         // are independent of the batch size
           dim3 gs(pairs, nstrips, cdiv(blocks, b.nb));
           if (b.mode == 0) fb_iter_ws<0><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
           else if (b.mode == 1) fb_iter_ws<1><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
           else fb_iter_ws<2><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
-        } else if (fast && FB_STRIP) {
-          // strip kernel: 112-column strips, nseg row segments of nblk 15-row blocks each (>= ~4 waves of CTAs)
-          IterArgs b = a;
-          const int nstrips = cdiv(L.w, FBS_TW), blocks = cdiv(L.h, FBS_RB);
-          int nseg = cdiv(4 * 296, pairs * nstrips);
-          nseg = nseg < 1 ? 1 : (nseg > blocks ? blocks : nseg);
-          b.nb = cdiv(cdiv(blocks, nseg), FBS_REFRESH) * FBS_REFRESH;   // segments start on refresh blocks: results
-                                                                        // are independent of the batch size
-          dim3 gs(pairs, nstrips, cdiv(blocks, b.nb));
-          if (b.mode == 0) fb_iter_strip<0><<<gs, FBS_NT, FBS_SMEM, st>>>(b);
-          else if (b.mode == 1) fb_iter_strip<1><<<gs, FBS_NT, FBS_SMEM, st>>>(b);
-          else fb_iter_strip<2><<<gs, FBS_NT, FBS_SMEM, st>>>(b);
-        } else if (fast) B2OF_ITER_LAUNCH(IT_NT_FAST, IT_T_FAST, 7, false);
-        else if (gauss) B2OF_ITER_LAUNCH(512, 0, 0, true);
+        } else if (gauss) B2OF_ITER_LAUNCH(512, 0, 0, true);
         else B2OF_ITER_LAUNCH(512, 0, 0, false);
 #undef B2OF_ITER_LAUNCH
       }

@@ -1,46 +1,57 @@
-// K5/K6, warp-specialised strip form (the reference's window: winsize 15, box): one fused kernel per
-// (level, iteration), one persistent-style CTA per SM walking down a strip of 112 output columns in blocks of
-// FBW_RB rows.  The three steps of a block run on DIFFERENT warps and on different blocks at the same time:
+// K5/K6 for the reference's window (winsize 15, box): ONE fused kernel per (level, iteration) --
+//   flow_in (zero | previous iteration | bilinear x(1/pyr_scale) upsample of the coarser level)
+//   -> UpdateMatrices (bilinear warp of R1, border attenuation) -> 15x15 box sum -> 2x2 solve -> flow_out
+// M (the 5-channel matrix field) never leaves the SM.
 //
-//   A warps (20): UpdateMatrices for block s + 2 -> ring rows          (memory-latency bound: gathers)
-//   B warps  (4): horizontal 15-sums in place on block s + 1           (shared-memory latency bound, serial in x)
-//   C warps  (4): vertical running 15-sums + 2x2 solve for block s     (shared-memory latency bound, serial in y)
+// Shape: one CTA per SM walks down a strip of 112 output columns (128 halo columns = 4 whole warps per row, so
+// every row load falls on whole 128-byte lines) in blocks of FBW_RB rows.  The three steps of a block run on
+// DIFFERENT warps, on different blocks, at the same time:
+//
+//   A warps (16): UpdateMatrices for block s + 2 -> ring rows.  thread = (halo column, run of 4 rows); walking
+//                 down a column the bottom corners of one pixel's bilinear gather are the top corners of the next
+//                 one whenever the integer part of the warp advanced by exactly one row (almost always), so they
+//                 are carried in registers and only two new corners are loaded; the flow vector is fetched one
+//                 row ahead.  Memory-latency bound.
+//   B warps  (4): horizontal 15-sums in place on block s + 1.  lane = (row, half-row); each half-row is walked
+//                 once with the 15 most recent inputs in a register window (one read and one write per element).
+//   C warps  (4): vertical 15-sums for block s as running sums carried in registers down the whole strip (one
+//                 add and one subtract per row), restarted from the ring every FBW_REFRESH blocks so rounding does
+//                 not accumulate; 2x2 solve; coalesced 8-byte stores.  The C warps also feed the copy engine: bulk
+//                 L2 prefetches (cp.async.bulk.prefetch.L2) of the rows step A needs FBW_PF_BLOCKS blocks later.
 //
 // so the serial row / column walks of B and C hide behind the gathers of A instead of stalling the whole CTA at a
-// barrier (in the phase-structured kernels 44 % of all warp time was barrier wait).  Blocks are handed from
-// stage to stage through mbarriers (full_a[3], full_b[3], empty_c[3]; stage = block mod 3); the M ring holds
-// 14 + 3 * FBW_RB rows as three planes (float2 ch0/1, float2 ch2/3, float ch4) with an odd row stride.
-// Arithmetic is the same as fb_iter_strip (fb_strip.cuh), which documents steps A, B and C.
+// barrier (with barrier-separated phases 44 % of all warp time was barrier wait).  Blocks are handed from stage to
+// stage through mbarriers (full_a[3], full_b[3], empty_c[3]; stage = block mod 3).  The M ring holds
+// 14 + 3 * FBW_RB rows as three planes (float2 ch0/1, float2 ch2/3, float ch4) whose odd row stride makes the
+// row-parallel accesses of B and the column-parallel accesses of A and C conflict-free.
+//
+// What bounds it (ncu, profiles/README.md): the L1 / shared-memory data pipe.  Every global or shared access costs
+// one wavefront per 128 bytes it touches and the pipe sustains about 0.6 wavefronts per cycle per SM; this kernel
+// needs 2.9 wavefronts per output pixel (1.4 global: the unaligned 16-byte corner gathers; 1.5 shared), its
+// predecessor with 56x56 tiles and barrier-separated phases needed 3.6.
 #pragma once
-#ifndef FBW_SLEEP_NS
-#define FBW_SLEEP_NS 200
-#endif
-#ifndef FBW_PF_AHEAD
-#define FBW_PF_AHEAD 4
-#endif
-#ifndef FBW_SETMAXNREG
-#define FBW_SETMAXNREG 0
-#endif
-#ifndef FBW_A_REGS
-#define FBW_A_REGS 80
-#endif
-#ifndef FBW_PIPE
-#define FBW_PIPE 0
-#endif
-#ifndef FBW_EXP
-#define FBW_EXP 0
-#endif
 
-#ifndef FBW_A_WARPS_N
-#define FBW_A_WARPS_N 16
-#endif
-constexpr int FBW_A_WARPS = FBW_A_WARPS_N;           // 16 (80 registers / thread) or 20 (72)
-constexpr int FBW_NT = (FBW_A_WARPS + 8) * 32;          // 896 threads: 20 A warps, 4 B warps, 4 C warps
+constexpr int FBS_EW = 128;               // halo columns per strip
+constexpr int FBS_TW = 112;               // output columns per strip
+constexpr int FBS_M = 7;                  // window radius
+constexpr int FBS_PADL = 8;               // halo column 0 sits at image column x0 - 8 (8-pixel aligned)
+constexpr int FBS_ES = 129;               // plane row stride in elements (odd)
+constexpr int FBS_HL = FBS_TW / 2;        // outputs [0,HL) are summed left->right, [HL,TW) right->left
+constexpr int FBW_REFRESH = 4;            // blocks between restarts of the vertical running sums
+constexpr int FBW_A_WARPS = 16;
+constexpr int FBW_NT = (FBW_A_WARPS + 8) * 32;          // 768 threads: 16 A warps, 4 B warps, 4 C warps
 constexpr int FBW_RUNS = FBW_A_WARPS / 4;               // row runs per block in step A (128 columns = 4 warps each)
 constexpr int FBW_RB = FBW_A_WARPS;                     // rows per block: 4 rows per A thread
-constexpr int FBW_NR = 2 * FBS_M + 3 * FBW_RB;          // ring rows (74)
+constexpr int FBW_PF_BLOCKS = 4;                        // L2 prefetch distance in blocks
+constexpr int FBW_NR = 2 * FBS_M + 3 * FBW_RB;          // ring rows (62)
 constexpr size_t FBW_PLANES = (size_t)FBW_NR * FBS_ES * 20;
 constexpr size_t FBW_SMEM = FBW_PLANES + 16 * 8;        // + mbarriers
+
+__device__ __forceinline__ void sts_f2(unsigned addr, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
 
 __device__ __forceinline__ void mbar_init(unsigned addr, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
@@ -57,7 +68,7 @@ __device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
       "W_%=: nanosleep.u32 %2;\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@!p bra W_%=;\n"
-      "D_%=: }" ::"r"(addr), "r"(parity), "n"(FBW_SLEEP_NS) : "memory");
+      "D_%=: }" ::"r"(addr), "r"(parity), "n"(200) : "memory");
 }
 
 __device__ __forceinline__ float rcp_approx(float x) {     // 1 ulp; the determinant is >= 1e-3 / inv_area^2 > 0
@@ -66,7 +77,10 @@ __device__ __forceinline__ float rcp_approx(float x) {     // 1 ulp; the determi
   return r;
 }
 
-// horizontal 15-sums of one ring row of one plane, in place (see fb_iter_strip step B)
+// ---- step B: horizontal 15-sums of one half ring row of one plane, in place.  Window positions p = cx - 1:
+// output xo sums p in [xo, xo + 14].  The left half (outputs [0,HL)) is walked left->right and stored at p = xo
+// (reads p >= xo); the right half (outputs [HL,TW)) right->left, stored at p = xo + 14 (reads p <= xo + 14);
+// positions [HL, HL + 14) are written by neither, so the two halves never race.
 template <typename T>
 __device__ __forceinline__ T hp_add(T a, T b);
 template <> __device__ __forceinline__ float2 hp_add<float2>(float2 a, float2 b) { return add2(a, b); }
@@ -158,14 +172,8 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
 
   if (t < FBW_A_WARPS * 32) {
     // =========================== A warps: UpdateMatrices ===========================
-#if FBW_SETMAXNREG
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FBW_A_REGS));   // registers the B / C warps gave back
-#endif
+    // R of the pair's first frame: {float4 plane ch0..3, float plane ch4}; the second frame follows at r_frame_stride
     const float* base0 = a.R + (size_t)pair * a.pair_frame_step * a.r_frame_stride;
-    const float4* __restrict__ R0a = (const float4*)base0;
-    const float* __restrict__ R0b = base0 + 4 * a.plane_stride;
-    const float4* __restrict__ R1a = (const float4*)(base0 + a.r_frame_stride);
-    const float* __restrict__ R1b = base0 + a.r_frame_stride + 4 * a.plane_stride;
     const float2* __restrict__ fin = MODE ? a.flow_in + (size_t)pair * a.flow_in_pair_stride : nullptr;
     const int cx = t & (EW - 1), run = t >> 7;
     const int x = clampi(x0 - FBS_PADL + cx, 0, w - 1);
@@ -175,9 +183,9 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
     int uxa = 0, uxb = 0;
     float ufx = 0.f;
     if (MODE == 2) { uxa = a.ux0[x]; uxb = a.ux1[x]; ufx = a.ufx[x]; }
-    // one 64-bit base (the pair's R0 record plane) and 32-bit byte offsets to the other three planes: four
-    // pinned pointers would not fit the register budget of the pipelined loop
-    const char* rb = (const char*)R0a;
+    // one 64-bit base (the pair's R0 record plane) and 32-bit byte offsets to the other three planes; loop
+    // invariants are pinned in registers (ptxas otherwise re-derives them from the constant bank every row)
+    const char* rb = (const char*)base0;
     unsigned c_r0b = (unsigned)(16 * a.plane_stride);                       // R0 ch4 plane
     unsigned c_r1a = (unsigned)(4 * a.r_frame_stride);                      // R1 record plane
     unsigned c_r1b = c_r1a + c_r0b;                                         // R1 ch4 plane
@@ -204,114 +212,12 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
         const unsigned sa_end = (unsigned)(NR * ES + cx);
         int yu = y_first + l0;                          // unclamped image row of the row being set up
 
-        auto stage1 = [&](FbRow& R, int o) {
-#if FBW_EXP == 3 || FBW_EXP == 5
-          R.q = make_float4(xf, 1.f, 2.f, 3.f); R.q4 = 0.5f;
-#else
-          R.q = ldg_f4<0>((const float4*)(rb + (unsigned)o * 16u));
-          R.q4 = ldg_f1<0>((const float*)(rb + ((unsigned)o * 4u + c_r0b)));
-#endif
-          float fx = xf + R.d.x, fy = (float)R.y + R.d.y;
-          const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
-          R.fx = fx - (float)x1; R.fy = fy - (float)y1;
-          R.inside = (unsigned)x1 < (unsigned)wm1 && (unsigned)y1 < (unsigned)hm1;
-          R.ot = R.inside ? y1 * pit + x1 : 0;
-#if FBW_EXP == 2
-          R.ot = o;
-#endif
-          const int ob = R.ot + pitb;
-#if FBW_EXP == 1 || FBW_EXP == 5
-          R.bot.a0 = R.q; R.bot.a1 = R.q; R.bot.e0 = R.q4; R.bot.e1 = R.q4;
-#else
-          const float4* pa = (const float4*)(rb + ((unsigned)ob * 16u + c_r1a));
-          const float* pe = (const float*)(rb + ((unsigned)ob * 4u + c_r1b));
-          R.bot.a0 = ldg_f4<0>(pa); R.bot.a1 = ldg_f4<16>(pa);
-          R.bot.e0 = ldg_f1<0>(pe); R.bot.e1 = ldg_f1<4>(pe);
-#endif
-        };
-        auto top_partial = [&](const FbRow& R, const FbCorner& c, float (&tp)[5]) {
-          const float gy = 1.f - R.fy;
-          const float a00 = (1.f - R.fx) * gy, a01 = R.fx * gy;
-          tp[0] = fmaf(a01, c.a1.x, a00 * c.a0.x);
-          tp[1] = fmaf(a01, c.a1.y, a00 * c.a0.y);
-          tp[2] = fmaf(a01, c.a1.z, a00 * c.a0.z);
-          tp[3] = fmaf(a01, c.a1.w, a00 * c.a0.w);
-          tp[4] = fmaf(a01, c.e1, a00 * c.e0);
-        };
-        auto load_top = [&](const FbRow& R, float (&tp)[5]) {
-          FbCorner c;
-#if FBW_EXP == 5 || FBW_EXP == 1
-          c = R.bot; top_partial(R, c, tp); return;
-#endif
-          const float4* pa = (const float4*)(rb + ((unsigned)R.ot * 16u + c_r1a));
-          const float* pe = (const float*)(rb + ((unsigned)R.ot * 4u + c_r1b));
-          c.a0 = ldg_f4<0>(pa); c.a1 = ldg_f4<16>(pa);
-          c.e0 = ldg_f1<0>(pe); c.e1 = ldg_f1<4>(pe);
-          top_partial(R, c, tp);
-        };
-        auto stage2 = [&](const FbRow& R, const float (&tp)[5]) {
-          const float a10 = (1.f - R.fx) * R.fy, a11 = R.fx * R.fy;
-          float r2 = fmaf(a11, R.bot.a1.x, fmaf(a10, R.bot.a0.x, tp[0]));
-          float r3 = fmaf(a11, R.bot.a1.y, fmaf(a10, R.bot.a0.y, tp[1]));
-          float r4 = fmaf(a11, R.bot.a1.z, fmaf(a10, R.bot.a0.z, tp[2]));
-          float r5 = fmaf(a11, R.bot.a1.w, fmaf(a10, R.bot.a0.w, tp[3]));
-          float r6 = fmaf(a11, R.bot.e1, fmaf(a10, R.bot.e0, tp[4]));
-          const float4 q = R.q;
-          const float q4 = R.q4;
-          r2 = R.inside ? r2 : 0.f;
-          r3 = R.inside ? r3 : 0.f;
-          r4 = R.inside ? r4 : q.z;               // (q + q) * 0.5 = q, (q4 + q4) * 0.25 = q4 * 0.5: exact
-          r5 = R.inside ? r5 : q.w;
-          r6 = R.inside ? r6 : q4;
-          r4 = (q.z + r4) * 0.5f;
-          r5 = (q.w + r5) * 0.5f;
-          r6 = (q4 + r6) * 0.25f;
-          r2 = (q.x - r2) * 0.5f;
-          r3 = (q.y - r3) * 0.5f;
-          r2 += r4 * R.d.y + r6 * R.d.x;
-          r3 += r6 * R.d.y + r5 * R.d.x;
-          if ((unsigned)(R.y - 5) >= (unsigned)thr) {
-            const float sc = bwx * border_w(R.y, h);
-            r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
-          }
-          sts_f2(s_xy + sa * 8, r4 * r4 + r6 * r6, (r4 + r5) * r6);
-          sts_f2(s_zw + sa * 8, r5 * r5 + r6 * r6, r4 * r2 + r6 * r3);
-          sts_f1(s_e + sa * 4, r6 * r2 + r5 * r3);
-          sa += ES;
-          if (sa == sa_end) sa -= NR * ES;
-        };
         auto next_row = [&](int& y, int& o) {
           y = min(max(yu, 0), hm1);
           o = y * pit + x;
           ++yu;
         };
 
-#if FBW_PIPE
-        FbRow A, B;
-        float tp[5];
-        int oA, oB = 0, yn = 0, on = 0;
-        float2 dn = make_float2(0.f, 0.f);
-        next_row(A.y, oA);
-        A.d = fetch_flow_m<MODE>(a, fi, oA, A.y, uxa, uxb, ufx);
-        B.y = A.y; B.d = A.d;
-        if (n > 1) { next_row(B.y, oB); B.d = fetch_flow_m<MODE>(a, fi, oB, B.y, uxa, uxb, ufx); }
-        stage1(A, oA);
-        load_top(A, tp);
-        int k = 0;
-        for (; k + 1 < n; k += 2) {
-          stage1(B, oB);
-          if (k + 2 < n) { next_row(yn, on); dn = fetch_flow_m<MODE>(a, fi, on, yn, uxa, uxb, ufx); }
-          stage2(A, tp);
-          if (B.ot == A.ot + pitb) top_partial(B, A.bot, tp); else load_top(B, tp);
-          A.d = dn; A.y = yn; oA = on;
-          if (k + 2 < n) stage1(A, oA);
-          if (k + 3 < n) { next_row(yn, on); dn = fetch_flow_m<MODE>(a, fi, on, yn, uxa, uxb, ufx); }
-          stage2(B, tp);
-          if (k + 2 < n) { if (A.ot == B.ot + pitb) top_partial(A, B.bot, tp); else load_top(A, tp); }
-          B.d = dn; B.y = yn; oB = on;
-        }
-        if (k < n) stage2(A, tp);
-#else
         // plain form (64 registers): a row's loads are issued and consumed in the same iteration; only the flow
         // vector is fetched one row ahead; bottom corners carried as the next row's top corners
         FbCorner cA, cB;
@@ -379,7 +285,6 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
           rowf(dB, dA, yB, yA, oB, oA, k + 2 < n, cB, cA);
         }
         if (k < n) rowf(dA, dB, yA, yB, oA, oB, false, cA, cB);
-#endif
       }
       mbar_arrive(s_bar + (s % 3) * 8);                 // full_a[stage]: block s is in the ring
       j0 += nrows;
@@ -387,9 +292,6 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
     }
   } else if (t < FBW_A_WARPS * 32 + 128) {
     // =========================== B warps: horizontal sums in place ===========================
-#if FBW_SETMAXNREG
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-#endif
     const int bt = t - FBW_A_WARPS * 32, bw = bt >> 5, lane = bt & 31;
     const int rr = lane & 15;
     const bool right = (lane >> 4) != 0;
@@ -416,9 +318,6 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
     }
   } else {
     // =========================== C warps: vertical running sums + solve ===========================
-#if FBW_SETMAXNREG
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-#endif
     const int ct = t - FBW_A_WARPS * 32 - 128;
     const bool act = ct < TW && x0 + ct < w;
     const int col = 1 + (ct < HL ? ct : ct + 2 * M);    // where step B left this column's sums
@@ -426,7 +325,7 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
     float2 vxy = make_float2(0.f, 0.f), vzw = vxy;
     float ve = 0.f;
     const float eps = 1e-3f / (a.inv_area * a.inv_area);
-    // the C warps also feed the copy engine: L2 prefetch of the rows step A will need FBW_PF_AHEAD blocks from now,
+    // the C warps also feed the copy engine: L2 prefetch of the rows step A will need FBW_PF_BLOCKS blocks from now,
     // one bulk prefetch per (row, stream), issued by lanes 0..4 of each C warp for RB / 4 rows
     const float* pbase0 = a.R + (size_t)pair * a.pair_frame_step * a.r_frame_stride;
     const int pf_xs = max(x0 - FBS_PADL, 0);
@@ -450,14 +349,14 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
       }
     };
-    for (int sb = 0; sb < FBW_PF_AHEAD; ++sb) prefetch_block(sb);
+    for (int sb = 0; sb < FBW_PF_BLOCKS; ++sb) prefetch_block(sb);
     int po = 0;                                         // ring row of the oldest row of the window (row yb - M)
     for (int s = 0; s < nblk; ++s) {
       const int yb = ys + s * RB;
       mbar_wait(s_bar + (3 + s % 3) * 8, (unsigned)((s / 3) & 1));       // full_b[stage]
       if (act) {
         int pn = po;
-        if (s == 0 || ((yb / RB) % FBS_REFRESH) == 0) {
+        if (s == 0 || ((yb / RB) % FBW_REFRESH) == 0) {
           // (re)start the running sums from the 14 rows above the window's newest row
           vxy = make_float2(0.f, 0.f); vzw = vxy; ve = 0.f;
 #pragma unroll
@@ -504,7 +403,7 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
         }
       }
       mbar_arrive(s_bar + (6 + s % 3) * 8);             // empty_c[stage]: block s's oldest rows may be overwritten
-      prefetch_block(s + FBW_PF_AHEAD);
+      prefetch_block(s + FBW_PF_BLOCKS);
       po += RB;
       if (po >= NR) po -= NR;
     }
