@@ -1449,10 +1449,16 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
           // (at least two waves of CTAs when the batch is small)
           IterArgs b = a;
           const int nstrips = cdiv(L.w, FBS_TW), blocks = cdiv(L.h, FBW_RB);
-          int nseg = cdiv(2 * n_sm, pairs * nstrips);
-          nseg = nseg < 1 ? 1 : (nseg > blocks ? blocks : nseg);
-          b.nb = cdiv(cdiv(blocks, nseg), FBW_REFRESH) * FBW_REFRESH;   // segments start on refresh blocks: results
-                                                                        // are independent of the batch size
+          // row segments: the split that minimises (waves of CTAs) x (rows per CTA + the 30 rows of pipeline fill
+          // and halo); nb is a multiple of the refresh period, so results do not depend on the split or the batch
+          int best_nb = cdiv(blocks, FBW_REFRESH) * FBW_REFRESH;
+          long long best_cost = -1;
+          for (int nbc = FBW_REFRESH; nbc <= cdiv(blocks, FBW_REFRESH) * FBW_REFRESH; nbc += FBW_REFRESH) {
+            const long long ctas = (long long)pairs * nstrips * cdiv(blocks, nbc);
+            const long long cost = ((ctas + n_sm - 1) / n_sm) * (nbc * FBW_RB + 30);
+            if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best_nb = nbc; }
+          }
+          b.nb = best_nb;
           dim3 gs(pairs, nstrips, cdiv(blocks, b.nb));
           if (b.mode == 0) fb_iter_ws<0><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
           else if (b.mode == 1) fb_iter_ws<1><<<gs, FBW_NT, FBW_SMEM, st>>>(b);

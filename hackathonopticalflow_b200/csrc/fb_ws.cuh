@@ -21,8 +21,8 @@
 //
 // so the serial row / column walks of B and C hide behind the gathers of A instead of stalling the whole CTA at a
 // barrier (with barrier-separated phases 44 % of all warp time was barrier wait).  Blocks are handed from stage to
-// stage through mbarriers (full_a[3], full_b[3], empty_c[3]; stage = block mod 3).  The M ring holds
-// 14 + 3 * FBW_RB rows as three planes (float2 ch0/1, float2 ch2/3, float ch4) whose odd row stride makes the
+// stage through mbarriers (full_a[], full_b[], empty_c[]; stage = block mod FBW_STAGES).  The M ring holds
+// 14 + FBW_STAGES * FBW_RB rows as three planes (float2 ch0/1, float2 ch2/3, float ch4) whose odd row stride makes the
 // row-parallel accesses of B and the column-parallel accesses of A and C conflict-free.
 //
 // What bounds it (ncu, profiles/README.md): the L1 / shared-memory data pipe.  Every global or shared access costs
@@ -43,9 +43,13 @@ constexpr int FBW_NT = (FBW_A_WARPS + 8) * 32;          // 768 threads: 16 A war
 constexpr int FBW_RUNS = FBW_A_WARPS / 4;               // row runs per block in step A (128 columns = 4 warps each)
 constexpr int FBW_RB = FBW_A_WARPS;                     // rows per block: 4 rows per A thread
 constexpr int FBW_PF_BLOCKS = 4;                        // L2 prefetch distance in blocks
-constexpr int FBW_NR = 2 * FBS_M + 3 * FBW_RB;          // ring rows (62)
+#ifndef FBW_STAGES_N
+#define FBW_STAGES_N 3
+#endif
+constexpr int FBW_STAGES = FBW_STAGES_N;                // blocks in flight between step A and step C
+constexpr int FBW_NR = 2 * FBS_M + FBW_STAGES * FBW_RB; // ring rows
 constexpr size_t FBW_PLANES = (size_t)FBW_NR * FBS_ES * 20;
-constexpr size_t FBW_SMEM = FBW_PLANES + 16 * 8;        // + mbarriers
+constexpr size_t FBW_SMEM = FBW_PLANES + 3 * FBW_STAGES * 8;   // + mbarriers
 
 __device__ __forceinline__ void sts_f2(unsigned addr, float x, float y) {
   asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
@@ -161,10 +165,10 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
   const int t = threadIdx.x;
 
   if (t == 0) {
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < FBW_STAGES; ++i) {
       mbar_init(s_bar + i * 8, FBW_A_WARPS * 32);       // full_a: every A thread arrives
-      mbar_init(s_bar + (3 + i) * 8, 128);              // full_b
-      mbar_init(s_bar + (6 + i) * 8, 128);              // empty_c
+      mbar_init(s_bar + (FBW_STAGES + i) * 8, 128);     // full_b
+      mbar_init(s_bar + (2 * FBW_STAGES + i) * 8, 128); // empty_c
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -200,7 +204,8 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
       const int yb = ys + s * RB;
       const int nrows = s == 0 ? 2 * M + RB : RB;       // M rows [y_first, y_first + nrows), y_first below
       const int y_first = s == 0 ? yb - M : yb + M;     // image row of the first new M row
-      if (s >= 3) mbar_wait(s_bar + (6 + s % 3) * 8, (unsigned)((s / 3 - 1) & 1));   // C is done with block s - 3
+      if (s >= FBW_STAGES)                              // C must be done with block s - FBW_STAGES
+        mbar_wait(s_bar + (2 * FBW_STAGES + s % FBW_STAGES) * 8, (unsigned)((s / FBW_STAGES - 1) & 1));
 
       const int RS = (nrows + FBW_RUNS - 1) / FBW_RUNS;
       const int l0 = run * RS;
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
         }
         if (k < n) rowf(dA, dB, yA, yB, oA, oB, false, cA, cB);
       }
-      mbar_arrive(s_bar + (s % 3) * 8);                 // full_a[stage]: block s is in the ring
+      mbar_arrive(s_bar + (s % FBW_STAGES) * 8);        // full_a[stage]: block s is in the ring
       j0 += nrows;
       if (j0 >= NR) j0 -= NR;
     }
@@ -298,7 +303,7 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
     int j0 = 0;
     for (int s = 0; s < nblk; ++s) {
       const int nrows = s == 0 ? 2 * M + RB : RB;
-      mbar_wait(s_bar + (s % 3) * 8, (unsigned)((s / 3) & 1));           // full_a[stage]
+      mbar_wait(s_bar + (s % FBW_STAGES) * 8, (unsigned)((s / FBW_STAGES) & 1));   // full_a[stage]
       // work units = (group of 16 rows, plane), dealt round-robin to the four B warps; lane = row x half
       const int units = ((nrows + 15) >> 4) * 3;
       for (int u = bw; u < units; u += 4) {
@@ -312,7 +317,7 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
           else hpass_half_row<float>(Pe + pr * ES + 1, right);
         }
       }
-      mbar_arrive(s_bar + (3 + s % 3) * 8);             // full_b[stage]
+      mbar_arrive(s_bar + (FBW_STAGES + s % FBW_STAGES) * 8);   // full_b[stage]
       j0 += nrows;
       if (j0 >= NR) j0 -= NR;
     }
@@ -353,7 +358,7 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
     int po = 0;                                         // ring row of the oldest row of the window (row yb - M)
     for (int s = 0; s < nblk; ++s) {
       const int yb = ys + s * RB;
-      mbar_wait(s_bar + (3 + s % 3) * 8, (unsigned)((s / 3) & 1));       // full_b[stage]
+      mbar_wait(s_bar + (FBW_STAGES + s % FBW_STAGES) * 8, (unsigned)((s / FBW_STAGES) & 1));   // full_b[stage]
       if (act) {
         int pn = po;
         if (s == 0 || ((yb / RB) % FBW_REFRESH) == 0) {
@@ -402,7 +407,7 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
           nxy = nxy2; nzw = nzw2; ne = ne2; oxy = oxy2; ozw = ozw2; oe = oe2;
         }
       }
-      mbar_arrive(s_bar + (6 + s % 3) * 8);             // empty_c[stage]: block s's oldest rows may be overwritten
+      mbar_arrive(s_bar + (2 * FBW_STAGES + s % FBW_STAGES) * 8);   // empty_c[stage]: its oldest rows may be reused
       prefetch_block(s + FBW_PF_BLOCKS);
       po += RB;
       if (po >= NR) po -= NR;
