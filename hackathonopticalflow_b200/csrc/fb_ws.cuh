@@ -43,6 +43,9 @@ constexpr int FBW_NT = (FBW_A_WARPS + 8) * 32;          // 768 threads: 16 A war
 constexpr int FBW_RUNS = FBW_A_WARPS / 4;               // row runs per block in step A (128 columns = 4 warps each)
 constexpr int FBW_RB = FBW_A_WARPS;                     // rows per block: 4 rows per A thread
 constexpr int FBW_PF_BLOCKS = 4;                        // L2 prefetch distance in blocks
+#ifndef FBW_SKIP
+#define FBW_SKIP 0   // timing experiments only: bit 0 / 1 / 2 switches step A / B / C off
+#endif
 #ifndef FBW_STAGES_N
 #define FBW_STAGES_N 3
 #endif
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
       const int RS = (nrows + FBW_RUNS - 1) / FBW_RUNS;
       const int l0 = run * RS;
       const int n = min(l0 + RS, nrows) - l0;           // rows of this thread's run
-      if (n > 0) {
+      if (!(FBW_SKIP & 1) && n > 0) {
         int pr = j0 + l0;
         if (pr >= NR) pr -= NR;
         unsigned sa = (unsigned)(pr * ES + cx);         // element index into the planes
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
       for (int u = bw; u < units; u += 4) {
         const int grp = u / 3, plane = u - grp * 3;
         const int r = grp * 16 + rr;
-        if (r < nrows) {
+        if (!(FBW_SKIP & 2) && r < nrows) {
           int pr = j0 + r;
           if (pr >= NR) pr -= NR;
           if (plane == 0) hpass_half_row<float2>(Pxy + pr * ES + 1, right);
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
     for (int s = 0; s < nblk; ++s) {
       const int yb = ys + s * RB;
       mbar_wait(s_bar + (FBW_STAGES + s % FBW_STAGES) * 8, (unsigned)((s / FBW_STAGES) & 1));   // full_b[stage]
-      if (act) {
+      if (!(FBW_SKIP & 4) && act) {
         int pn = po;
         if (s == 0 || ((yb / RB) % FBW_REFRESH) == 0) {
           // (re)start the running sums from the 14 rows above the window's newest row
@@ -379,32 +382,49 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
         int pold = po;
         const int nr = min(RB, ye - yb);
         float2* orow = fo + (size_t)yb * a.out_pitch + (x0 + ct);
-        // software-pipelined one row deep: the six shared-memory reads of row r + 1 are in flight while row r is
-        // solved (this serial walk is the pipeline's critical stage: one warp per scheduler, in-order issue)
-        float2 nxy = Pxy[pn * ES + col], nzw = Pzw[pn * ES + col], oxy = Pxy[pold * ES + col], ozw = Pzw[pold * ES + col];
-        float ne = Pe[pn * ES + col], oe = Pe[pold * ES + col];
-#pragma unroll 2
-        for (int r = 0; r < nr; ++r) {
-          if (++pn == NR) pn = 0;
-          if (++pold == NR) pold = 0;
-          float2 nxy2 = nxy, nzw2 = nzw, oxy2 = oxy, ozw2 = ozw;
-          float ne2 = ne, oe2 = oe;
-          if (r + 1 < nr) {
-            const int en = pn * ES + col, eo = pold * ES + col;
-            nxy2 = Pxy[en]; nzw2 = Pzw[en]; ne2 = Pe[en];
-            oxy2 = Pxy[eo]; ozw2 = Pzw[eo]; oe2 = Pe[eo];
-          }
-          vxy = add2(vxy, nxy);
-          vzw = add2(vzw, nzw);
-          ve += ne;
-          const float g11 = vxy.x, g12 = vxy.y, g22 = vzw.x, h1 = vzw.y, h2 = ve;
+        // This serial walk is the pipeline's critical stage (one warp per scheduler, in-order issue), so it is
+        // written for instruction-level parallelism: four rows per step, all 24 shared-memory reads first, then
+        //   W0 = V + n0,  W1 = W0 + (n1 - o0),  W2 = W1 + (n2 - o1),  W3 = W2 + (n3 - o2),  V = W3 - o3
+        // (n = row entering the window, o = row leaving it): the only serial chain is four adds, the differences
+        // and the four 2x2 solves are independent of it.
+        auto solve_store = [&](float2 wxy, float2 wzw, float we) {
+          const float g11 = wxy.x, g12 = wxy.y, g22 = wzw.x, h1 = wzw.y, h2 = we;
           const float idet = rcp_approx(g11 * g22 - g12 * g12 + eps);
           *orow = make_float2((g11 * h2 - g12 * h1) * idet, (g22 * h1 - g12 * h2) * idet);
           orow += a.out_pitch;
-          vxy = sub2(vxy, oxy);
-          vzw = sub2(vzw, ozw);
-          ve -= oe;
-          nxy = nxy2; nzw = nzw2; ne = ne2; oxy = oxy2; ozw = ozw2; oe = oe2;
+        };
+        int r = 0;
+        for (; r + 4 <= nr; r += 4) {
+          float2 nxy[4], nzw[4], oxy[4], ozw[4];
+          float ne[4], oe[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int en = pn * ES + col, eo = pold * ES + col;
+            nxy[k] = Pxy[en]; nzw[k] = Pzw[en]; ne[k] = Pe[en];
+            oxy[k] = Pxy[eo]; ozw[k] = Pzw[eo]; oe[k] = Pe[eo];
+            if (++pn == NR) pn = 0;
+            if (++pold == NR) pold = 0;
+          }
+          float2 wxy[4], wzw[4];
+          float we[4];
+          wxy[0] = add2(vxy, nxy[0]); wzw[0] = add2(vzw, nzw[0]); we[0] = ve + ne[0];
+#pragma unroll
+          for (int k = 1; k < 4; ++k) {
+            wxy[k] = add2(wxy[k - 1], sub2(nxy[k], oxy[k - 1]));
+            wzw[k] = add2(wzw[k - 1], sub2(nzw[k], ozw[k - 1]));
+            we[k] = we[k - 1] + (ne[k] - oe[k - 1]);
+          }
+          vxy = sub2(wxy[3], oxy[3]); vzw = sub2(wzw[3], ozw[3]); ve = we[3] - oe[3];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) solve_store(wxy[k], wzw[k], we[k]);
+        }
+        for (; r < nr; ++r) {                           // last rows of the image
+          const int en = pn * ES + col, eo = pold * ES + col;
+          vxy = add2(vxy, Pxy[en]); vzw = add2(vzw, Pzw[en]); ve += Pe[en];
+          solve_store(vxy, vzw, ve);
+          vxy = sub2(vxy, Pxy[eo]); vzw = sub2(vzw, Pzw[eo]); ve -= Pe[eo];
+          if (++pn == NR) pn = 0;
+          if (++pold == NR) pold = 0;
         }
       }
       mbar_arrive(s_bar + (2 * FBW_STAGES + s % FBW_STAGES) * 8);   // empty_c[stage]: its oldest rows may be reused

@@ -222,6 +222,30 @@ def test_farneback_full_size_properties(batch, seq1080):
 
 
 @pytest.mark.skipif(not have_cv2(), reason="cv2 wheel not importable on this box")
+@pytest.mark.parametrize("h,w", [(17, 113), (31, 225), (48, 112), (65, 337), (96, 111)])
+def test_farneback_strip_and_block_edges_vs_oracle(b2, h, w):
+    """The reference window runs on 112-column strips walked in 16-row blocks: widths and heights one off the strip
+    and block sizes, on every pyramid level."""
+    from oracle import farneback as ofb
+    rng = np.random.default_rng(h * 977 + w)
+    a = (np.kron(rng.random((h // 4 + 1, w // 4 + 1)), np.ones((4, 4)))[:h, :w] * 200 + 20).astype(np.uint8)
+    b = np.roll(np.roll(a, 1, axis=1), -1, axis=0)
+    got = b2.calcOpticalFlowFarneback(a, b, None, *REF_FB)
+    mean, mx = epe(got, ofb.farneback(a, b, None, *REF_FB))
+    assert mean <= 1e-4 and mx <= 1e-2, (h, w, mean, mx)
+
+
+def test_farneback_result_independent_of_batch_split(batch):
+    """Row segments and pairs per launch change with the batch size; the flow field must not (bit for bit)."""
+    import torch
+    from hackathonopticalflow_b200 import synth
+    frames = torch.from_numpy(synth.sequence(270, 480, 9, seed=1003)).cuda()
+    ref = batch.FarnebackEngine(270, 480, chunk_pairs=8).flow_sequence(frames)
+    for chunk in (1, 3):
+        got = batch.FarnebackEngine(270, 480, chunk_pairs=chunk).flow_sequence(frames)
+        assert torch.equal(ref, got), chunk
+
+
 def test_farneback_live_cv2_1080p_and_720p(b2, seq1080):
     import cv2
     from hackathonopticalflow_b200 import synth
