@@ -90,7 +90,7 @@ def build(force=False, verbose=False, defines=(), out=None):
             raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
         return out
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(_HERE, "..", "include", "b2of.h")]
+    deps = srcs + [os.path.join(CSRC, h) for h in ("common.cuh", "fb_ws.cuh")] + [os.path.join(_HERE, "..", "include", "b2of.h")]
     if not force and os.path.exists(LIB_PATH):
         mt = os.path.getmtime(LIB_PATH)
         if all(os.path.getmtime(d) <= mt for d in deps):
