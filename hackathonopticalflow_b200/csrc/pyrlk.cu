@@ -112,69 +112,167 @@ struct LkWalk {
   }
 };
 
+// Patch layout in shared memory: rows of wwp = ww rounded up to even elements, so that two horizontally adjacent
+// elements are one aligned 4-byte (Iw pair) / 8-byte (derivative pair) access.
+__host__ __device__ inline int lk_wwp(int ww) { return (ww + 1) & ~1; }
+__host__ __device__ inline size_t lk_patch_bytes(int ww, int wh) {
+  size_t n = (size_t)lk_wwp(ww) * wh;
+  return ((((n + 3) & ~(size_t)3) * 2 + n * 4) + 15) & ~(size_t)15;
+}
+
+// Work split of a window inside the image: the warp's lanes own strips two columns wide (S = wwp / 2 strips) and,
+// when the window is narrow, G = 32 / S groups of rows.  A lane walks down its strip: the three bytes of the next
+// image row are loaded once and serve as bottom neighbours of this row and top neighbours of the next one
+// (1.5 loads per element instead of 4), addresses advance by one row step, and the template patch comes in as
+// aligned pairs.  Window sums are exact 64-bit integers, so the result does not depend on the split.
+struct LkStrips {
+  int S, G, RG;
+  __device__ __forceinline__ LkStrips(int ww, int wh) {
+    S = lk_wwp(ww) >> 1;
+    G = S <= 16 ? 32 / S : 1;
+    RG = (wh + G - 1) / G;
+  }
+};
+
 // sum over the window of (bilinear(J) >> 9 - Iw) * {Ixw, Iyw}  (or |diff| when ABS).
-// Four window elements per lane are in flight at a time (16 independent byte loads), so the L1 latency of the
-// gathers overlaps instead of serialising one pixel after the other.
+// Windows that stick out of the image read BORDER_REFLECT_101 pixels: the three reflected column indices of a
+// strip are computed once, the reflected row index once per row.
+template <bool ABS, bool INSIDE>
+__device__ __forceinline__ void lk_window_strips(const uint8_t* __restrict__ J, size_t step, int w, int h, int ix,
+                                                 int iy, int w00, int w01, int w10, int w11, const short* sI,
+                                                 const short2* sD, int ww, int wh, int lane, long long& s1,
+                                                 long long& s2) {
+  const int wwp = lk_wwp(ww);
+  const LkStrips st(ww, wh);
+  for (int u = lane; u < st.S * st.G; u += 32) {
+    const int g = u / st.S, sx = u - g * st.S;
+    const int x0 = 2 * sx;
+    const bool two = x0 + 1 < ww;
+    const int y0 = g * st.RG, y1 = min(wh, y0 + st.RG);
+    int c0 = ix + x0, c1 = c0 + 1, c2 = c0 + 2;
+    if (!INSIDE) { c0 = reflect101(c0, w); c1 = reflect101(c1, w); c2 = reflect101(c2, w); }
+    auto rowp = [&](int y) { return J + (size_t)(INSIDE ? iy + y : reflect101(iy + y, h)) * step; };
+    const uint8_t* r = rowp(y0);
+    int t0 = r[c0], t1 = r[c1], t2 = two ? r[c2] : 0;
+    const short* pI = sI + y0 * wwp + x0;
+    const short2* pD = sD + y0 * wwp + x0;
+    auto one_row = [&](int b0, int b1, int b2, int ipair, int2 dp) {
+      const int v0 = t0 * w00 + t1 * w01 + b0 * w10 + b1 * w11;
+      const int v1 = t1 * w00 + t2 * w01 + b1 * w10 + b2 * w11;
+      const int diff0 = ((v0 + 256) >> 9) - (int)(short)(ipair & 0xffff);
+      const int diff1 = ((v1 + 256) >> 9) - (ipair >> 16);
+      if (ABS) {
+        s1 += abs(diff0);
+        if (two) s1 += abs(diff1);
+      } else {
+        s1 += (long long)diff0 * (int)(short)(dp.x & 0xffff);
+        s2 += (long long)diff0 * (dp.x >> 16);
+        if (two) {
+          s1 += (long long)diff1 * (int)(short)(dp.y & 0xffff);
+          s2 += (long long)diff1 * (dp.y >> 16);
+        }
+      }
+      t0 = b0; t1 = b1; t2 = b2;
+    };
+    int y = y0;
+    // four rows per step, every load of the step issued before the first use
+    for (; y + 4 <= y1; y += 4) {
+      int b[4][3], ip[4];
+      int2 dp[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint8_t* rk = INSIDE ? r + (size_t)(k + 1) * step : rowp(y + k + 1);
+        b[k][0] = rk[c0]; b[k][1] = rk[c1]; b[k][2] = two ? rk[c2] : 0;
+        ip[k] = *(const int*)(pI + k * wwp);
+        dp[k] = ABS ? make_int2(0, 0) : *(const int2*)(pD + k * wwp);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) one_row(b[k][0], b[k][1], b[k][2], ip[k], dp[k]);
+      if (INSIDE) r += 4 * step;
+      pI += 4 * wwp; pD += 4 * wwp;
+    }
+    for (; y < y1; ++y) {
+      const uint8_t* rk = INSIDE ? r + step : rowp(y + 1);
+      if (INSIDE) r = rk;
+      one_row(rk[c0], rk[c1], two ? rk[c2] : 0, *(const int*)pI, ABS ? make_int2(0, 0) : *(const int2*)pD);
+      pI += wwp; pD += wwp;
+    }
+  }
+}
+
 template <bool ABS>
 __device__ __forceinline__ void lk_window_pass(const uint8_t* __restrict__ J, size_t step, int w, int h, int ix,
                                                int iy, int w00, int w01, int w10, int w11, const short* sI,
                                                const short2* sD, int ww, int wh, int lane, long long& o1,
                                                long long& o2) {
   const bool inside = ix >= 0 && iy >= 0 && ix + ww < w && iy + wh < h;
-  const int n = ww * wh;
   long long s1 = 0, s2 = 0;
-  int a1 = 0, a2 = 0, cnt = 0;
-  LkWalk wk(lane, ww);
-  if (inside) {
-    const uint8_t* base = J + (size_t)iy * step + ix;
-    for (int p = lane; p < n; p += 128) {
-      int v[4];
-      int pp[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        pp[k] = p + 32 * k;
-        v[k] = 0;
-        if (pp[k] < n) {
-          const uint8_t* q = base + (size_t)wk.y * step + wk.x;
-          v[k] = q[0] * w00 + q[1] * w01 + q[step] * w10 + q[step + 1] * w11;
-        }
-        wk.next();
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (pp[k] < n) {
-          int diff = ((v[k] + 256) >> 9) - (int)sI[pp[k]];
-          if (ABS) {
-            a1 += diff < 0 ? -diff : diff;
-          } else {
-            short2 d = sD[pp[k]];
-            a1 += diff * (int)d.x;
-            a2 += diff * (int)d.y;
-          }
-        }
-      }
-      if (++cnt == 8) { s1 += a1; s2 += a2; a1 = a2 = 0; cnt = 0; }   // 32 products per lane fit an int32
-    }
-  } else {
-    for (int p = lane; p < n; p += 32) {
-      int gx = ix + wk.x, gy = iy + wk.y;
-      int v = img_px(J, step, w, h, gx, gy, false) * w00 + img_px(J, step, w, h, gx + 1, gy, false) * w01 +
-              img_px(J, step, w, h, gx, gy + 1, false) * w10 + img_px(J, step, w, h, gx + 1, gy + 1, false) * w11;
-      int diff = ((v + 256) >> 9) - (int)sI[p];
-      if (ABS) {
-        a1 += diff < 0 ? -diff : diff;
-      } else {
-        short2 d = sD[p];
-        a1 += diff * (int)d.x;
-        a2 += diff * (int)d.y;
-      }
-      if (++cnt == 32) { s1 += a1; s2 += a2; a1 = a2 = 0; cnt = 0; }
-      wk.next();
-    }
-  }
-  s1 += a1; s2 += a2;
+  if (inside) lk_window_strips<ABS, true>(J, step, w, h, ix, iy, w00, w01, w10, w11, sI, sD, ww, wh, lane, s1, s2);
+  else lk_window_strips<ABS, false>(J, step, w, h, ix, iy, w00, w01, w10, w11, sI, sD, ww, wh, lane, s1, s2);
   o1 = warp_sum_ll(s1);
   o2 = ABS ? 0 : warp_sum_ll(s2);
+}
+
+// template patch (Iw, Ixw, Iyw) of the window at (ipx, ipy) + the three sums of the normal matrix.  Image pixels
+// outside the frame are BORDER_REFLECT_101, derivatives outside the frame are zero.
+template <bool INSIDE>
+__device__ __forceinline__ void lk_patch_strips(const uint8_t* __restrict__ I, const short2* __restrict__ D, size_t step,
+                                                int W, int H, int ipx, int ipy, int w00, int w01, int w10, int w11,
+                                                short* sI, short2* sD, int ww, int wh, int lane, long long& sA11,
+                                                long long& sA12, long long& sA22) {
+  const int wwp = lk_wwp(ww);
+  const LkStrips st(ww, wh);
+  for (int u = lane; u < st.S * st.G; u += 32) {
+    const int g = u / st.S, sx = u - g * st.S;
+    const int x0 = 2 * sx;
+    const bool two = x0 + 1 < ww;
+    const int y0 = g * st.RG, y1 = min(wh, y0 + st.RG);
+    const int a0 = ipx + x0;                     // unreflected columns a0, a0 + 1, a0 + 2
+    int c0 = a0, c1 = a0 + 1, c2 = a0 + 2;
+    bool v0 = true, v1 = true, v2 = two;         // derivative columns inside the frame
+    if (!INSIDE) {
+      v0 = (unsigned)c0 < (unsigned)W; v1 = (unsigned)c1 < (unsigned)W; v2 = two && (unsigned)c2 < (unsigned)W;
+      c0 = reflect101(c0, W); c1 = reflect101(c1, W); c2 = reflect101(c2, W);
+    }
+    const short2 z = make_short2(0, 0);
+    auto load_row = [&](int y, int& i0, int& i1, int& i2, short2& d0, short2& d1, short2& d2) {
+      const int ya = ipy + y;
+      const uint8_t* r = I + (size_t)(INSIDE ? ya : reflect101(ya, H)) * step;
+      i0 = r[c0]; i1 = r[c1]; i2 = two ? r[c2] : 0;
+      const bool vy = INSIDE || (unsigned)ya < (unsigned)H;
+      const short2* dr = D + (size_t)(vy ? ya : 0) * W;
+      d0 = (vy && v0) ? dr[a0] : z;
+      d1 = (vy && v1) ? dr[a0 + 1] : z;
+      d2 = (vy && v2) ? dr[a0 + 2] : z;
+    };
+    int t0, t1, t2;
+    short2 e0, e1, e2;
+    load_row(y0, t0, t1, t2, e0, e1, e2);
+    short* pI = sI + y0 * wwp + x0;
+    short2* pD = sD + y0 * wwp + x0;
+#pragma unroll 2
+    for (int y = y0; y < y1; ++y) {
+      int b0, b1, b2;
+      short2 f0, f1, f2;
+      load_row(y + 1, b0, b1, b2, f0, f1, f2);
+      const int iv0 = t0 * w00 + t1 * w01 + b0 * w10 + b1 * w11;
+      const int iv1 = t1 * w00 + t2 * w01 + b1 * w10 + b2 * w11;
+      const int dx0 = e0.x * w00 + e1.x * w01 + f0.x * w10 + f1.x * w11;
+      const int dy0 = e0.y * w00 + e1.y * w01 + f0.y * w10 + f1.y * w11;
+      const int dx1 = e1.x * w00 + e2.x * w01 + f1.x * w10 + f2.x * w11;
+      const int dy1 = e1.y * w00 + e2.y * w01 + f1.y * w10 + f2.y * w11;
+      const int ival0 = (iv0 + 256) >> 9, ixv0 = (dx0 + 8192) >> 14, iyv0 = (dy0 + 8192) >> 14;
+      int ival1 = (iv1 + 256) >> 9, ixv1 = (dx1 + 8192) >> 14, iyv1 = (dy1 + 8192) >> 14;
+      if (!two) ival1 = ixv1 = iyv1 = 0;             // padding column of an odd-width window
+      *(int*)pI = (ival0 & 0xffff) | (ival1 << 16);
+      *(int2*)pD = make_int2((ixv0 & 0xffff) | (iyv0 << 16), (ixv1 & 0xffff) | (iyv1 << 16));
+      sA11 += (long long)ixv0 * ixv0 + (long long)ixv1 * ixv1;
+      sA12 += (long long)ixv0 * iyv0 + (long long)ixv1 * iyv1;
+      sA22 += (long long)iyv0 * iyv0 + (long long)iyv1 * iyv1;
+      t0 = b0; t1 = b1; t2 = b2; e0 = f0; e1 = f1; e2 = f2;
+      pI += wwp; pD += wwp;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(LK_WARPS * 32) lk_track(LkArgs a) {
@@ -184,9 +282,10 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_track(LkArgs a) {
   const int b = blockIdx.y;
   if (pt >= a.n_pts) return;
   const int ww = a.ww, wh = a.wh, n = ww * wh;
-  const size_t per_warp = (((size_t)n * 6) + 15) & ~(size_t)15;
-  short* sI = (short*)(lk_smem + warp * per_warp);
-  short2* sD = (short2*)(sI + ((n + 1) & ~1));
+  const int wwp = lk_wwp(ww);
+  const size_t per_warp = lk_patch_bytes(ww, wh);
+  short* sI = (short*)(lk_smem + warp * per_warp);                 // [wh][wwp] int16
+  short2* sD = (short2*)(sI + (((size_t)wwp * wh + 3) & ~(size_t)3));   // [wh][wwp] (Ixw, Iyw), 8-byte aligned
   const uint8_t* PI = a.pyr_i + (size_t)b * a.L.pyr_bytes;
   const uint8_t* PJ = a.pyr_j + (size_t)b * a.L.pyr_bytes;
   const short2* DV = a.deriv + (size_t)b * a.L.deriv_elems;
@@ -229,65 +328,9 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_track(LkArgs a) {
     long long sA11 = 0, sA12 = 0, sA22 = 0;
     {
       const bool inside = ipx >= 0 && ipy >= 0 && ipx + ww < W && ipy + wh < H;
-      int c11 = 0, c12 = 0, c22 = 0, cnt = 0;
-      LkWalk wk(lane, ww);
       __syncwarp();
-      if (inside) {
-        const uint8_t* ibase = I + (size_t)ipy * step + ipx;
-        const short2* dbase = D + (size_t)ipy * W + ipx;
-        for (int p = lane; p < n; p += 128) {
-          int iv[4], dxv[4], dyv[4], pp[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            pp[k] = p + 32 * k;
-            iv[k] = dxv[k] = dyv[k] = 0;
-            if (pp[k] < n) {
-              const uint8_t* q = ibase + (size_t)wk.y * step + wk.x;
-              iv[k] = q[0] * w00 + q[1] * w01 + q[step] * w10 + q[step + 1] * w11;
-              const short2* dq = dbase + (size_t)wk.y * W + wk.x;
-              short2 d00 = dq[0], d01 = dq[1], d10 = dq[W], d11 = dq[W + 1];
-              dxv[k] = d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11;
-              dyv[k] = d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11;
-            }
-            wk.next();
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (pp[k] < n) {
-              int ival = (iv[k] + 256) >> 9;
-              int ixv = (dxv[k] + 8192) >> 14, iyv = (dyv[k] + 8192) >> 14;
-              sI[pp[k]] = (short)ival;
-              sD[pp[k]] = make_short2((short)ixv, (short)iyv);
-              c11 += ixv * ixv; c12 += ixv * iyv; c22 += iyv * iyv;
-            }
-          }
-          if (++cnt == 8) { sA11 += c11; sA12 += c12; sA22 += c22; c11 = c12 = c22 = 0; cnt = 0; }
-        }
-      } else {
-        for (int p = lane; p < n; p += 32) {
-          int gx = ipx + wk.x, gy = ipy + wk.y;
-          int iv = img_px(I, step, W, H, gx, gy, false) * w00 + img_px(I, step, W, H, gx + 1, gy, false) * w01 +
-                   img_px(I, step, W, H, gx, gy + 1, false) * w10 + img_px(I, step, W, H, gx + 1, gy + 1, false) * w11;
-          int dxv = 0, dyv = 0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            int xx = gx + (k & 1), yy = gy + (k >> 1);
-            int wgt = k == 0 ? w00 : k == 1 ? w01 : k == 2 ? w10 : w11;
-            if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
-              short2 d = D[(size_t)yy * W + xx];
-              dxv += d.x * wgt; dyv += d.y * wgt;
-            }
-          }
-          int ival = (iv + 256) >> 9;
-          int ixv = (dxv + 8192) >> 14, iyv = (dyv + 8192) >> 14;
-          sI[p] = (short)ival;
-          sD[p] = make_short2((short)ixv, (short)iyv);
-          c11 += ixv * ixv; c12 += ixv * iyv; c22 += iyv * iyv;
-          if (++cnt == 32) { sA11 += c11; sA12 += c12; sA22 += c22; c11 = c12 = c22 = 0; cnt = 0; }
-          wk.next();
-        }
-      }
-      sA11 += c11; sA12 += c12; sA22 += c22;
+      if (inside) lk_patch_strips<true>(I, D, step, W, H, ipx, ipy, w00, w01, w10, w11, sI, sD, ww, wh, lane, sA11, sA12, sA22);
+      else lk_patch_strips<false>(I, D, step, W, H, ipx, ipy, w00, w01, w10, w11, sI, sD, ww, wh, lane, sA11, sA12, sA22);
       sA11 = warp_sum_ll(sA11); sA12 = warp_sum_ll(sA12); sA22 = warp_sum_ll(sA22);
       __syncwarp();
     }
@@ -353,7 +396,7 @@ static int lk_check(int rows, int cols, const b2of_lk_params* p) {
   B2OF_ASSERT(p != nullptr, fn);
   B2OF_ASSERT(rows > 0 && cols > 0, fn);
   B2OF_ASSERT(p->max_level >= 0 && p->win_w > 2 && p->win_h > 2, fn);
-  size_t per_warp = align_up((size_t)p->win_w * p->win_h * 6, 16) + 16;
+  size_t per_warp = lk_patch_bytes(p->win_w, p->win_h);
   if (per_warp * LK_WARPS > 200 * 1024)
     return fail(B2OF_E_UNSUPPORTED, "winSize %dx%d needs more shared memory than one SM has", p->win_w, p->win_h);
   return B2OF_OK;
@@ -429,7 +472,7 @@ int pyrlk_dev(const uint8_t* prev, const uint8_t* next, size_t step, size_t fram
   a.eps2d_lo = (float)(eps2 - (double)a.eps2d_hi);
   a.flags = p->flags;
   a.min_eig_thr = (float)p->min_eig_threshold;
-  size_t per_warp = align_up((size_t)p->win_w * p->win_h * 6, 16);
+  size_t per_warp = lk_patch_bytes(p->win_w, p->win_h);
   size_t smem = per_warp * LK_WARPS;
   static std::atomic<size_t> max_set{0};
   if (smem > 48 * 1024 && smem > max_set.load()) {
