@@ -501,7 +501,9 @@ struct LevelRegArgs {
 };
 
 constexpr int LR_TW = 64;
-__host__ __device__ constexpr int lr_th(int S) { return S >= 8 ? 8 : 16; }
+// output rows per CTA: taller tiles for the fine levels (the 64 x 16 tiles were CTA-launch bound: 132,600 CTAs for
+// 65 frames at 1080p)
+__host__ __device__ constexpr int lr_th(int S) { return S == 1 ? 64 : S == 2 ? 32 : S == 4 ? 16 : 8; }
 __host__ __device__ constexpr int lr_rwp(int K, int S) { return ((S * (LR_TW - 1) + K + 3 + 3) / 4 + 1) * 4; }
 __host__ __device__ constexpr int lr_rh(int K, int S) { return S * (lr_th(S) - 1) + K; }
 __host__ __device__ constexpr size_t lr_smem(int K, int S) {

@@ -48,18 +48,41 @@ static int lk_plan(int rows, int cols, const b2of_lk_params* p, LkLevels* L) {
 }
 
 // ---- K10: Scharr 3x3 -> (Ix, Iy) int16, REFLECT_101 (calcScharrDeriv) ----
+__device__ __forceinline__ int reflect101_pm1(int i, int n) {   // BORDER_REFLECT_101 for i in [-1, n]
+  if (n == 1) return 0;
+  return i < 0 ? 1 : (i >= n ? n - 2 : i);
+}
+
+// four pixels per thread: the 3 x 6 neighbourhood comes in as bytes from L1, the four (Ix, Iy) pairs go out as one
+// 16-byte store when the row start is aligned
 __global__ void __launch_bounds__(256) lk_scharr(const uint8_t* __restrict__ img, size_t step, size_t img_bstride,
                                                   int w, int h, short2* __restrict__ d, size_t d_bstride) {
-  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= w) return;
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+  if (x0 >= w) return;
   const uint8_t* b = img + blockIdx.z * img_bstride;
-  int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
-  const uint8_t* r0 = b + (size_t)reflect101(y - 1, h) * step;
+  const uint8_t* r0 = b + (size_t)reflect101_pm1(y - 1, h) * step;
   const uint8_t* r1 = b + (size_t)y * step;
-  const uint8_t* r2 = b + (size_t)reflect101(y + 1, h) * step;
-  int t0m = (r0[xm] + r2[xm]) * 3 + r1[xm] * 10, t0p = (r0[xp] + r2[xp]) * 3 + r1[xp] * 10;
-  int t1m = r2[xm] - r0[xm], t1c = r2[x] - r0[x], t1p = r2[xp] - r0[xp];
-  d[blockIdx.z * d_bstride + (size_t)y * w + x] = make_short2((short)(t0p - t0m), (short)((t1m + t1p) * 3 + t1c * 10));
+  const uint8_t* r2 = b + (size_t)reflect101_pm1(y + 1, h) * step;
+  int t0[6], t1[6];                      // vertical smooth (3, 10, 3) and difference at columns x0 - 1 .. x0 + 4
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int xx = reflect101_pm1(min(x0 - 1 + k, w), w);
+    const int a = r0[xx], c = r1[xx], e = r2[xx];
+    t0[k] = (a + e) * 3 + c * 10;
+    t1[k] = e - a;
+  }
+  short2 o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    o[k] = make_short2((short)(t0[k + 2] - t0[k]), (short)((t1[k] + t1[k + 2]) * 3 + t1[k + 1] * 10));
+  short2* out = d + blockIdx.z * d_bstride + (size_t)y * w + x0;
+  if (x0 + 3 < w && (((size_t)out) & 15) == 0) {
+    *(int4*)out = make_int4(*(int*)&o[0], *(int*)&o[1], *(int*)&o[2], *(int*)&o[3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (x0 + k < w) out[k] = o[k];
+  }
 }
 
 struct LkArgs {
@@ -449,7 +472,7 @@ int pyrlk_dev(const uint8_t* prev, const uint8_t* next, size_t step, size_t fram
     }
   }
   for (int l = 0; l < a.L.n; ++l) {
-    dim3 grid(cdiv(a.L.w[l], 256), a.L.h[l], batch);
+    dim3 grid(cdiv(cdiv(a.L.w[l], 4), 256), a.L.h[l], batch);
     {
       ProfScope ps(PT_LK_SCHARR, st, batch * 5.0 * a.L.w[l] * a.L.h[l]);
       lk_scharr<<<grid, 256, 0, st>>>(pi + a.L.off[l], a.L.step[l], a.L.pyr_bytes, a.L.w[l], a.L.h[l], dv + a.L.doff[l],
