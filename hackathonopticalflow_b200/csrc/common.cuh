@@ -49,8 +49,12 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 __host__ __device__ inline int reflect101(int i, int n) {
-  // BORDER_REFLECT_101, valid for any offset
+  // BORDER_REFLECT_101, valid for any offset.  In range and single reflections (every access of the kernels except
+  // on images smaller than a filter) take no division.
+  if ((unsigned)i < (unsigned)n) return i;
   if (n == 1) return 0;
+  if (i < 0 && -i < n) return -i;
+  if (i >= n && i < 2 * n - 1) return 2 * n - 2 - i;
   int period = 2 * (n - 1);
   i %= period;
   if (i < 0) i += period;
