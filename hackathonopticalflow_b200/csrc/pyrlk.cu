@@ -116,25 +116,6 @@ __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01,
   w11 = 16384 - w00 - w01 - w10;
 }
 
-__device__ __forceinline__ int img_px(const uint8_t* img, size_t step, int w, int h, int x, int y, bool inside) {
-  if (!inside) { x = reflect101(x, w); y = reflect101(y, h); }
-  return img[(size_t)y * step + x];
-}
-
-// Window walk shared by the passes below: element p = lane + 32*i of the ww x wh window sits at (x, y);
-// advancing by 32 elements is (dq rows, dr columns) with one carry.
-struct LkWalk {
-  int x, y, dq, dr, ww;
-  __device__ __forceinline__ LkWalk(int lane, int ww_) : ww(ww_) {
-    dq = 32 / ww_; dr = 32 - dq * ww_;
-    y = lane / ww_; x = lane - y * ww_;
-  }
-  __device__ __forceinline__ void next() {
-    x += dr; y += dq;
-    if (x >= ww) { x -= ww; ++y; }
-  }
-};
-
 // Patch layout in shared memory: rows of wwp = ww rounded up to even elements, so that two horizontally adjacent
 // elements are one aligned 4-byte (Iw pair) / 8-byte (derivative pair) access.
 __host__ __device__ inline int lk_wwp(int ww) { return (ww + 1) & ~1; }
@@ -304,7 +285,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_track(LkArgs a) {
   const int pt = blockIdx.x * LK_WARPS + warp;
   const int b = blockIdx.y;
   if (pt >= a.n_pts) return;
-  const int ww = a.ww, wh = a.wh, n = ww * wh;
+  const int ww = a.ww, wh = a.wh;
   const int wwp = lk_wwp(ww);
   const size_t per_warp = lk_patch_bytes(ww, wh);
   short* sI = (short*)(lk_smem + warp * per_warp);                 // [wh][wwp] int16
