@@ -73,6 +73,7 @@ SIGNATURES = {
     "b2of_gftt_host": (_i, [_vp, _vp, _sz, _sz, _i, _i, _PG, _vp, _i, _vp]),
     "b2of_pathfinder_filter_dev": (_i, [_vp, _sz, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b2of_flow_sample_dev": (_i, [_vp, _i, _i, _i, _vp, _sz, _i, _vp, _vp]),
+    "b2of_flow_hsv_dev": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "b2of_flow_stats_dev": (_i, [_vp, _i, _i, _i, _vp, _vp]),
 }
 

@@ -212,6 +212,15 @@ def flow_sample(flow, pts):
     return nxt
 
 
+def flow_hsv(flow):
+    """float32 (B,H,W,2) dense flow -> uint8 (B,H,W,3) BGR picture, the reference's draw_hsv (pathfinder_viewer.py:124-141)."""
+    b, h, w, _ = flow.shape
+    bgr = torch.empty((b, h, w, 3), dtype=torch.uint8, device=flow.device)
+    with torch.cuda.device(flow.device):
+        _lib.check(_lib.lib().b2of_flow_hsv_dev(_p(flow), b, h, w, _p(bgr), _stream()))
+    return bgr
+
+
 def flow_stats(flow):
     """float32 (B,H,W,2) -> float32 (B,8): mean|flow|, max|flow|, mean dx, mean dy, 0, 0, 0, 0 (deterministic)."""
     b, h, w, _ = flow.shape

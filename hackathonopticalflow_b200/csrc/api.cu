@@ -64,6 +64,7 @@ int pathfinder_filter_dev(const float*, size_t, const float*, int, int, int, int
                           uint8_t*, int32_t*, float*, cudaStream_t);
 int flow_stats_dev(const float*, int, int, int, float*, cudaStream_t);
 int flow_sample_dev(const float*, int, int, int, const float*, size_t, int, float*, cudaStream_t);
+int flow_hsv_dev(const float*, int, int, int, uint8_t*, cudaStream_t);
 
 // ----------------------------------------------------------------------------------------------
 // host-call context: one per device, grow-only device buffers + non-blocking streams.
@@ -454,6 +455,10 @@ int b2of_pathfinder_filter_dev(const float* pts, size_t pts_batch_stride, const 
 int b2of_flow_sample_dev(const float* flow, int n_pairs, int rows, int cols, const float* pts, size_t pts_batch_stride,
                          int n_pts, float* next_pts, void* stream) {
   return flow_sample_dev(flow, n_pairs, rows, cols, pts, pts_batch_stride, n_pts, next_pts, (cudaStream_t)stream);
+}
+
+int b2of_flow_hsv_dev(const float* flow, int n_pairs, int rows, int cols, uint8_t* bgr, void* stream) {
+  return flow_hsv_dev(flow, n_pairs, rows, cols, bgr, (cudaStream_t)stream);
 }
 
 int b2of_flow_stats_dev(const float* flow, int n_pairs, int rows, int cols, float* stats, void* stream) {

@@ -252,6 +252,59 @@ __global__ void flow_stats_final(float* __restrict__ stats, size_t n_px, int n_p
   s[4] = s[5] = s[6] = s[7] = 0.f;
 }
 
+// ---- dense flow as a picture: draw_hsv, pathfinder_viewer.py:124-141 ----
+//   ang = arctan2(fy, fx) + pi;  v = sqrt(fx^2 + fy^2)                          (float32, as numpy computes them)
+//   hsv = uint8(ang * (180/pi/2)), 255, uint8(min(4 v, 255));  bgr = cv2.cvtColor(hsv, COLOR_HSV2BGR)
+// The cvtColor call is third-party (opencv color_hsv.simd.hpp): float32 h * (6/180), v * (1/255), the table
+// {v, v(1-s), v(1-s f), v(1-s(1-f))} with s = 1, times 255, truncated (oracle/pathfinder.py::hsv2bgr_u8, pinned
+// against cv2 for every (h, v) at the saturation the reference writes).  arctan2 is evaluated in double and rounded
+// once, which reproduces numpy's correctly rounded float32 result.
+__global__ void __launch_bounds__(256) flow_hsv_bgr(const float2* __restrict__ flow, size_t n_px,
+                                                     uint8_t* __restrict__ bgr) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n_px) return;
+  const float2 f = flow[i];
+  const float ang = __fadd_rn((float)atan2((double)f.y, (double)f.x), 3.14159274101257324f);   // + float32(pi)
+  const float v = __fsqrt_rn(__fadd_rn(__fmul_rn(f.x, f.x), __fmul_rn(f.y, f.y)));
+  const int hq = (int)__fmul_rn(ang, 28.6478897565411604f);                // uint8(ang * (180/pi/2)): truncation
+  const int vq = (int)fminf(__fmul_rn(v, 4.f), 255.f);
+  // HSV -> BGR, s = 255
+  float h = __fmul_rn((float)(hq & 255), (float)(6.0 / 180.0));
+  const float s = __fmul_rn(255.f, (float)(1.0 / 255.0));
+  const float vf = __fmul_rn((float)vq, (float)(1.0 / 255.0));
+  if (h >= 6.f) h = __fsub_rn(h, 6.f);
+  const float sec = floorf(h);
+  const float fr = __fsub_rn(h, sec);
+  int sector = (int)sec;
+  if (sector >= 6) sector -= 6;
+  float tab[4];
+  tab[0] = vf;
+  tab[1] = __fmul_rn(vf, __fsub_rn(1.f, s));
+  tab[2] = __fmul_rn(vf, __fsub_rn(1.f, __fmul_rn(s, fr)));
+  tab[3] = __fmul_rn(vf, __fsub_rn(1.f, __fmul_rn(s, __fsub_rn(1.f, fr))));
+  // sector -> (b, g, r) table indices, 2 bits each: {1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0}
+  const unsigned code[6] = {1u | 3u << 2 | 0u << 4, 1u | 0u << 2 | 2u << 4, 3u | 0u << 2 | 1u << 4,
+                            0u | 2u << 2 | 1u << 4, 0u | 1u << 2 | 3u << 4, 2u | 1u << 2 | 0u << 4};
+  const unsigned c = code[sector];
+  auto q = [&](unsigned k) {
+    const float x = __fmul_rn(tab[k], 255.f);
+    return (uint8_t)min(max((int)x, 0), 255);
+  };
+  uint8_t* o = bgr + 3 * i;
+  o[0] = q(c & 3u); o[1] = q((c >> 2) & 3u); o[2] = q((c >> 4) & 3u);
+}
+
+int flow_hsv_dev(const float* flow, int n_pairs, int rows, int cols, uint8_t* bgr, cudaStream_t st) {
+  const char* fn = "draw_hsv";
+  B2OF_ASSERT(n_pairs >= 0 && rows > 0 && cols > 0, fn);
+  if (n_pairs == 0) return B2OF_OK;
+  B2OF_ASSERT(flow != nullptr && bgr != nullptr, fn);
+  const size_t n_px = (size_t)n_pairs * rows * cols;
+  flow_hsv_bgr<<<(unsigned)((n_px + 255) / 256), 256, 0, st>>>((const float2*)flow, n_px, bgr);
+  B2OF_LAUNCH_CHECK();
+  return B2OF_OK;
+}
+
 int flow_stats_dev(const float* flow, int n_pairs, int rows, int cols, float* stats, cudaStream_t st) {
   const char* fn = "flow_stats";
   B2OF_ASSERT(n_pairs >= 0 && rows > 0 && cols > 0, fn);

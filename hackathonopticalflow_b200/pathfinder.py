@@ -7,6 +7,7 @@ Same names and argument meaning as the reference's functions, minus the drawing 
                           (note the argument order at :156), modulus normalisation, median/p99 filter, int rounding
 * ``draw_sparse_lamps``-- pathfinder_viewer.py:196-223: returns the danger intensity V per kept point
                           (what :210-217 writes) instead of a drawn image
+* ``draw_hsv``         -- pathfinder_viewer.py:124-141: dense flow -> BGR picture (hue = direction, value = length)
 """
 import numpy as np
 import torch
@@ -46,6 +47,12 @@ def draw_sparse_lamps(flow_, points_):
     f = torch.from_numpy(np.ascontiguousarray(flow_)).to(torch.float64)
     m = torch.sqrt(f[:, 0] * f[:, 0] + f[:, 1] * f[:, 1])
     return torch.clamp(50 + m * 2, max=255).to(torch.uint8).numpy()
+
+
+def draw_hsv(flow_, device="cuda"):
+    """flow_: float32 (H,W,2) numpy, as the reference passes it -> uint8 (H,W,3) BGR (pathfinder_viewer.py:124-141)."""
+    f = torch.from_numpy(np.ascontiguousarray(flow_, dtype=np.float32)).to(device)[None]
+    return batch.flow_hsv(f)[0].cpu().numpy()
 
 
 class PathfinderPipeline:

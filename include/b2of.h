@@ -184,6 +184,10 @@ int b2of_pathfinder_filter_dev(const float* pts_dev, size_t pts_batch_stride, co
 int b2of_flow_sample_dev(const float* flow_dev, int n_pairs, int rows, int cols, const float* pts_dev,
                          size_t pts_batch_stride, int n_pts, float* next_pts_dev, void* stream);
 
+/* dense flow as a picture -- draw_hsv, pathfinder_viewer.py:124-141 (DenseOF.py:113-121): hue = direction,
+ * value = 4 x length, converted as cv2.cvtColor(hsv, COLOR_HSV2BGR) does; uint8 (n_pairs, rows, cols, 3) BGR */
+int b2of_flow_hsv_dev(const float* flow_dev, int n_pairs, int rows, int cols, uint8_t* bgr_dev, void* stream);
+
 /* dense-flow statistics (what draw_flow / draw_hsv consume, DenseOF.py:44-50, :113-121):
  * per pair float32[8]: mean|flow|, max|flow|, mean dx, mean dy, 0, 0, 0, 0 */
 int b2of_flow_stats_dev(const float* flow_dev, int n_pairs, int rows, int cols, float* stats_dev, void* stream);

@@ -6,6 +6,8 @@ reference code (not cv2), restated without the drawing calls:
 * grid generator          pathfinder_viewer.py:255-267 (DenseOF.py:166-180)
 * vector filter           pathfinder_viewer.py:159-178 (get_flow_lk, after the LK call)
 * danger-point intensity  pathfinder_viewer.py:210-217 (draw_sparse_lamps, before drawing)
+* dense-flow HSV picture   pathfinder_viewer.py:124-141 (draw_hsv; its cv2.cvtColor(HSV2BGR) call is third-party:
+                          opencv color_hsv.simd.hpp, restated in hsv2bgr_u8 and pinned exhaustively against cv2)
 """
 import numpy as np
 
@@ -54,3 +56,39 @@ def danger_intensity(flow_, points_):
     for i, m in enumerate(modulus):
         v[i] = np.minimum(50 + m * 2, 255)
     return v
+
+
+def hsv2bgr_u8(hsv):
+    """cv2.cvtColor(hsv, COLOR_HSV2BGR) for uint8 input with H in [0, 180] (third-party: opencv-python, imgproc
+    color_hsv.simd.hpp HSV2RGB_b / HSV2RGB_f).  float32 throughout: h * (6/180), s and v * (1/255), the four-entry
+    table {v, v(1-s), v(1-s f), v(1-s(1-f))}, times 255 and TRUNCATED.  Pinned bit for bit against cv2 for all
+    181 x 256 (h, v) at s = 255 (the only saturation draw_hsv writes) and s = 0 in tests/test_oracle_golden.py;
+    other saturations differ from cv2's SIMD rounding by one level in places and are not used."""
+    f32 = np.float32
+    h = hsv[..., 0].astype(f32) * f32(6.0 / 180.0)
+    s = hsv[..., 1].astype(f32) * f32(1.0 / 255.0)
+    v = hsv[..., 2].astype(f32) * f32(1.0 / 255.0)
+    h = np.where(h >= 6, h - f32(6), h)
+    sector = np.floor(h)
+    f = h - sector
+    sector = sector.astype(np.int64) % 6
+    one = f32(1)
+    tab = np.stack([v, v * (one - s), v * (one - s * f), v * (one - s * (one - f))], -1)
+    sd = np.array([[1, 3, 0], [1, 0, 2], [3, 0, 1], [0, 2, 1], [0, 1, 3], [2, 1, 0]])
+    idx = sd[sector]
+    out = np.stack([np.take_along_axis(tab, idx[..., k:k + 1], -1)[..., 0] for k in range(3)], -1) * f32(255.0)
+    return np.clip(np.trunc(out), 0, 255).astype(np.uint8)
+
+
+def draw_hsv(flow_):
+    """pathfinder_viewer.py:124-141: hue = direction, value = 4 x length, BGR uint8 (H,W,3).
+    Returns (bgr, hsv) -- the reference returns bgr; hsv is kept for the tests."""
+    h, w = flow_.shape[:2]
+    fx, fy = flow_[:, :, 0], flow_[:, :, 1]
+    ang = np.arctan2(fy, fx) + np.pi
+    v = np.sqrt(fx * fx + fy * fy)
+    hsv = np.zeros((h, w, 3), np.uint8)
+    hsv[..., 0] = ang * (180 / np.pi / 2)
+    hsv[..., 1] = 255
+    hsv[..., 2] = np.minimum(v * 4, 255)
+    return hsv2bgr_u8(hsv), hsv

@@ -551,3 +551,35 @@ def test_flow_stats_deterministic_and_correct(batch):
     assert torch.allclose(s1[:, 0].double(), mag.mean(dim=(1, 2)), rtol=1e-5)
     assert torch.allclose(s1[:, 1].double(), mag.amax(dim=(1, 2)), rtol=1e-6)
     assert torch.allclose(s1[:, 2].double(), flow[..., 0].double().mean(dim=(1, 2)), atol=1e-5)
+
+
+def test_draw_hsv_vs_oracle_and_live_cv2(b2, batch, seq1080):
+    """draw_hsv (pathfinder_viewer.py:124-141) on a real dense flow field: identical to the numpy oracle; against the
+    reference formula with live cv2 identical in every column cv2 converts with its vector body (its scalar tail
+    columns round differently by one level, see tests/test_oracle_golden.py)."""
+    import torch
+    from hackathonopticalflow_b200 import pathfinder
+    from oracle import pathfinder as opf
+    flow = b2.calcOpticalFlowFarneback(seq1080[0], seq1080[1], None, *REF_FB)
+    flow[0, :4] = [(0, 0), (-1, -0.0), (-1, 0.0), (100, 100)]
+    got = pathfinder.draw_hsv(flow)
+    want, _ = opf.draw_hsv(flow)
+    assert got.shape == want.shape and got.dtype == np.uint8
+    bad = (got != want).any(-1)
+    assert bad.mean() <= 1e-5, bad.mean()                      # float32 arctan2 ties at a hue boundary, if any
+    if have_cv2():
+        import cv2
+        fx, fy = flow[:, :, 0], flow[:, :, 1]
+        hsv = np.zeros(flow.shape[:2] + (3,), np.uint8)
+        hsv[..., 0] = (np.arctan2(fy, fx) + np.pi) * (180 / np.pi / 2)
+        hsv[..., 1] = 255
+        hsv[..., 2] = np.minimum(np.sqrt(fx * fx + fy * fy) * 4, 255)
+        ref = cv2.cvtColor(hsv, cv2.COLOR_HSV2BGR)
+        diff = np.abs(got.astype(int) - ref.astype(int)).max(-1)
+        assert (diff[:, :1920 - 1920 % 32] > 0).mean() <= 1e-5 and diff.max() <= 9
+    # batch form, odd size
+    f2 = torch.randn(3, 37, 53, 2, device="cuda") * 7
+    out = batch.flow_hsv(f2).cpu().numpy()
+    for k in range(3):
+        w2, _ = opf.draw_hsv(f2[k].cpu().numpy())
+        assert ((out[k] != w2).any(-1)).mean() <= 2e-3

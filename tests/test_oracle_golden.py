@@ -127,3 +127,36 @@ def test_oracle_matches_live_cv2_small():
     s = ogp.scharr_s16(g)
     assert np.array_equal(s[..., 0], cv2.Scharr(g, cv2.CV_16S, 1, 0))
     assert np.array_equal(s[..., 1], cv2.Scharr(g, cv2.CV_16S, 0, 1))
+
+
+def test_hsv2bgr_restatement_exhaustive_and_draw_hsv_vs_reference_formula():
+    """oracle.hsv2bgr_u8 == cv2.cvtColor(HSV2BGR) for every uint8 (h <= 180, v) at s = 255 -- the only saturation the
+    reference writes (pathfinder_viewer.py:137) -- and s = 0; oracle.draw_hsv == the reference's draw_hsv
+    (pathfinder_viewer.py:124-141) evaluated with live cv2."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import pathfinder as opf
+    hh, vv = np.meshgrid(np.arange(181), np.arange(256), indexing="ij")
+    for s in (255, 0):
+        hsv = np.stack([hh, np.full_like(hh, s), vv], -1).astype(np.uint8)
+        assert np.array_equal(opf.hsv2bgr_u8(hsv), cv2.cvtColor(hsv, cv2.COLOR_HSV2BGR)), s
+    # cv2 converts the last (width mod SIMD-width) columns of a row with scalar code that rounds where the vector body
+    # truncates, so its own output depends on the image width and the host's SIMD width: the restatement follows the
+    # vector body (every column of a width that is a multiple of 32); in the tail columns the two differ by one level
+    for (hgt, wid) in ((96, 128), (97, 131)):
+        rng = np.random.default_rng(5)
+        flow = (rng.standard_normal((hgt, wid, 2)) * 9).astype(np.float32)
+        flow[0, :4] = [(0, 0), (-1, -0.0), (-1, 0.0), (100, 100)]
+        fx, fy = flow[:, :, 0], flow[:, :, 1]
+        ang = np.arctan2(fy, fx) + np.pi
+        v = np.sqrt(fx * fx + fy * fy)
+        hsv = np.zeros(flow.shape[:2] + (3,), np.uint8)
+        hsv[..., 0] = ang * (180 / np.pi / 2)
+        hsv[..., 1] = 255
+        hsv[..., 2] = np.minimum(v * 4, 255)
+        want = cv2.cvtColor(hsv, cv2.COLOR_HSV2BGR)
+        got, got_hsv = opf.draw_hsv(flow)
+        assert np.array_equal(got_hsv, hsv)
+        diff = np.abs(got.astype(int) - want.astype(int)).max(-1)
+        body = wid - wid % 32
+        assert not diff[:, :body].any(), (hgt, wid)
+        assert diff.max() <= 1
