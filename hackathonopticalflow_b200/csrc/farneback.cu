@@ -515,8 +515,13 @@ __device__ __forceinline__ int reflect_once(int i, int n) {  // REFLECT_101 for 
   return i >= n ? 2 * n - 2 - i : i;
 }
 
+// threads per CTA: 512 for the coarsest level (its 59 KB source region allows three CTAs per SM: more warps per CTA
+// instead), 256 otherwise
+__host__ __device__ constexpr int lr_nt(int S) { return S >= 8 ? 512 : 256; }
+
 template <int K, int S>
-__global__ void __launch_bounds__(256) fb_level_regular(LevelRegArgs a) {
+__global__ void __launch_bounds__(lr_nt(S)) fb_level_regular(LevelRegArgs a) {
+  constexpr int NT = lr_nt(S), NQ = NT / LR_TW;
   constexpr int TH = lr_th(S), RWP = lr_rwp(K, S), RH = lr_rh(K, S), RW = S * (LR_TW - 1) + K;
   extern __shared__ __align__(16) unsigned char lsm[];
   uint8_t* s_src = lsm;                               // [RH][RWP] u8
@@ -532,7 +537,7 @@ __global__ void __launch_bounds__(256) fb_level_regular(LevelRegArgs a) {
   // only what valid outputs consume is loaded (keeps the border overshoot below one reflection)
   const int rows_needed = S * (min(TH, a.hk - y0) - 1) + K;
   const int cols_needed = lpad + S * (min(LR_TW, a.wk - x0) - 1) + K;
-  for (int rr = warp; rr < rows_needed; rr += 8) {
+  for (int rr = warp; rr < rows_needed; rr += NT / 32) {
     const uint8_t* row = fb + (size_t)reflect_once(gy0 + rr, a.H) * a.step;
     if (cols_in) {
       for (int wc = lane; wc < NW; wc += 32)
@@ -542,10 +547,10 @@ __global__ void __launch_bounds__(256) fb_level_regular(LevelRegArgs a) {
     }
   }
   __syncthreads();
-  const int x = t & (LR_TW - 1), q = t >> 6;          // 64 columns x 4 row phases
+  const int x = t & (LR_TW - 1), q = t >> 6;          // 64 columns x NQ row phases
   {
     const uint8_t* p = s_src + lpad + S * x;
-    for (int rr = q; rr < rows_needed; rr += 4) {
+    for (int rr = q; rr < rows_needed; rr += NQ) {
       const uint8_t* pr = p + rr * RWP;
       float v = 0.f;
 #pragma unroll
@@ -557,7 +562,7 @@ __global__ void __launch_bounds__(256) fb_level_regular(LevelRegArgs a) {
   if (x0 + x < a.wk) {
     float* ob = a.I + blockIdx.z * a.i_frame_stride + x0 + x;
 #pragma unroll
-    for (int y = q; y < TH; y += 4) {
+    for (int y = q; y < TH; y += NQ) {
       if (y0 + y >= a.hk) break;
       const float* p = s_h + (S * y) * LR_TW + x;
       float v = 0.f;
@@ -576,7 +581,7 @@ static void launch_level_regular(const LevelRegArgs& ra, int frames, cudaStream_
     attr_done = true;
   }
   dim3 g(cdiv(ra.wk, LR_TW), cdiv(ra.hk, lr_th(S)), frames);
-  fb_level_regular<K, S><<<g, 256, lr_smem(K, S), st>>>(ra);
+  fb_level_regular<K, S><<<g, lr_nt(S), lr_smem(K, S), st>>>(ra);
 }
 
 
