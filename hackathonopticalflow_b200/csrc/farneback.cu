@@ -1466,6 +1466,8 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
             if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best_nb = nbc; }
           }
           b.nb = best_nb;
+          if (b.mode == 1 && b.in_pitch != L.pitch)     // the kernel indexes flow_in with the level's own pitch
+            return fail(B2OF_E_BADARG, "internal: flow_in pitch %d != level pitch %d", b.in_pitch, L.pitch);
           dim3 gs(pairs, nstrips, cdiv(blocks, b.nb));
           if (b.mode == 0) fb_iter_ws<0><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
           else if (b.mode == 1) fb_iter_ws<1><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
