@@ -256,6 +256,18 @@ def test_farneback_live_cv2_1080p_and_720p(b2, seq1080):
         assert mean <= 1e-4 and mx <= 1e-2, ("regression guard", mean, mx)
 
 
+@pytest.mark.skipif(not have_cv2(), reason="cv2 wheel not importable on this box")
+def test_farneback_live_cv2_4k(b2):
+    """BASELINE configs[4] frame size (3840x2160: 35 strips, 135 row blocks per strip), one pair against live cv2."""
+    import cv2
+    from hackathonopticalflow_b200 import synth
+    fr = synth.sequence(2160, 3840, 2, seed=1004)
+    ref = cv2.calcOpticalFlowFarneback(fr[0], fr[1], None, *REF_FB)
+    mean, mx = epe(b2.calcOpticalFlowFarneback(fr[0], fr[1], None, *REF_FB), ref)
+    assert mean <= FB_MEAN_TOL and mx <= FB_MAX_TOL, (mean, mx)
+    assert mean <= 1e-4 and mx <= 1e-2, ("regression guard", mean, mx)
+
+
 def test_farneback_host_batch_matches_single_calls(b2, synth_small):
     f0, f1 = synth_small["f0"], synth_small["f1"]
     prev = np.stack([f0, f1, f0, f1, f0, f1, f0])
