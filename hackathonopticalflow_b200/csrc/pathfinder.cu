@@ -24,6 +24,49 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return s;
 }
 
+// exact k-th smallest (k = 0 .. n-1) of n non-negative floats in shared memory: most-significant-digit radix
+// selection, 8 bits per pass; lanes with the same digit are counted with one shared-memory atomic per warp.
+// Called by all threads of the block; returns the same value in every thread.
+__device__ float select_kth(const float* s_key, int n, int k, unsigned int* s_hist, unsigned int* s_sel) {
+  const int t = threadIdx.x;
+  unsigned int prefix = 0, mask = 0;
+  int kk = k;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    if (t < 256) s_hist[t] = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += PF_THREADS) {
+      const int i = i0 + t;
+      const bool in = i < n;
+      const unsigned int u = in ? __float_as_uint(s_key[i]) : 0u;
+      const bool take = in && (u & mask) == prefix;
+      const unsigned int d = (u >> shift) & 255u;
+      const unsigned int active = __ballot_sync(0xffffffffu, take);
+      if (take) {
+        const unsigned int peers = __match_any_sync(active, d);
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[d], (unsigned int)__popc(peers));
+      }
+    }
+    __syncthreads();
+    if (t == 0) {
+      unsigned int cum = 0, d = 0;
+      for (; d < 255; ++d) {
+        const unsigned int c = s_hist[d];
+        if (cum + c > (unsigned int)kk) break;
+        cum += c;
+      }
+      *s_sel = (d << 16) | 0;               // digit
+      s_hist[0] = cum;                        // elements below the chosen digit
+    }
+    __syncthreads();
+    const unsigned int d = *s_sel >> 16;
+    kk -= (int)s_hist[0];
+    prefix |= d << shift;
+    mask |= 255u << shift;
+    __syncthreads();
+  }
+  return __uint_as_float(prefix);
+}
+
 __global__ void __launch_bounds__(PF_THREADS) pathfinder_filter(const float* __restrict__ pts, size_t pts_bstride,
                                                                  const float* __restrict__ next_pts, int n,
                                                                  int width, int height, int32_t* __restrict__ kept_pts,
@@ -32,7 +75,9 @@ __global__ void __launch_bounds__(PF_THREADS) pathfinder_filter(const float* __r
                                                                  uint8_t* __restrict__ mask_out,
                                                                  int32_t* __restrict__ n_kept,
                                                                  float* __restrict__ stats, int np2) {
-  extern __shared__ float s_key[];  // np2 sorted moduli
+  extern __shared__ float s_key[];  // the n moduli
+  __shared__ unsigned int s_hist[256];
+  __shared__ unsigned int s_sel;
   __shared__ float red[PF_THREADS / 32];
   __shared__ int warp_off[PF_THREADS / 32 + 1];
   __shared__ int s_base;
@@ -41,9 +86,9 @@ __global__ void __launch_bounds__(PF_THREADS) pathfinder_filter(const float* __r
   const float* Q = next_pts + (size_t)b * n * 2;
   const float hw = (float)(width / 2), hh = (float)(height / 2);
   float sum_mag = 0.f, max_mag = 0.f, sum_dx = 0.f, sum_dy = 0.f;
-  for (int i = t; i < np2; i += PF_THREADS) {
-    float key = INFINITY;
-    if (i < n) {
+  for (int i = t; i < n; i += PF_THREADS) {
+    float key = 0.f;
+    {
       float x = P[2 * i], y = P[2 * i + 1];
       float fx = Q[2 * i] - x, fy = Q[2 * i + 1] - y;
       float mod = sqrtf(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)));
@@ -55,30 +100,19 @@ __global__ void __launch_bounds__(PF_THREADS) pathfinder_filter(const float* __r
     s_key[i] = key;
   }
   __syncthreads();
-  // bitonic sort ascending (NaN-free input assumed; +inf padding sorts last)
-  for (int k = 2; k <= np2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = t; i < np2; i += PF_THREADS) {
-        int l = i ^ j;
-        if (l > i) {
-          float a = s_key[i], c = s_key[l];
-          bool asc = (i & k) == 0;
-          if (asc ? a > c : a < c) { s_key[i] = c; s_key[l] = a; }
-        }
-      }
-      __syncthreads();
-    }
-  }
-  // np.median / np.percentile(., 99) in float32
+  // np.median / np.percentile(., 99) in float32 need four order statistics, not the sorted array: exact radix
+  // selection on the bit patterns (the moduli are non-negative, so bit order is value order; NaN-free input assumed)
   float med, p99;
   {
-    if (n & 1) med = s_key[n / 2];
-    else med = __fdiv_rn(__fadd_rn(s_key[n / 2 - 1], s_key[n / 2]), 2.f);
+    const float k_mid = select_kth(s_key, n, n / 2, s_hist, &s_sel);
+    if (n & 1) med = k_mid;
+    else med = __fdiv_rn(__fadd_rn(select_kth(s_key, n, n / 2 - 1, s_hist, &s_sel), k_mid), 2.f);
     double vi = 0.99 * (double)(n - 1);
     int lo = (int)floor(vi);
     int hi = lo + 1 < n ? lo + 1 : n - 1;
     float tt = (float)(vi - (double)lo);
-    float a = s_key[lo], c = s_key[hi];
+    float a = select_kth(s_key, n, lo, s_hist, &s_sel);
+    float c = hi == lo ? a : select_kth(s_key, n, hi, s_hist, &s_sel);
     float diff = c - a;
     p99 = tt >= 0.5f ? c - diff * (1.f - tt) : a + diff * tt;
   }
