@@ -264,13 +264,32 @@ __global__ void __launch_bounds__(256) flow_stats_accum(const float2* __restrict
     sy += __shfl_xor_sync(0xffffffffu, sy, o);
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   }
+  // fixed-point (Q20) per-warp partials are integers: summing the block's eight warps in shared memory first and
+  // issuing one set of atomics per block gives the same bits as eight sets, with an eighth of the contention
+  __shared__ unsigned long long s_acc[3][8];
+  __shared__ unsigned int s_mx[8];
+  const double Q = 1048576.0;
   if ((threadIdx.x & 31) == 0) {
+    const int wdx = threadIdx.x >> 5;
+    s_acc[0][wdx] = (unsigned long long)llrint((double)sm * Q);
+    s_acc[1][wdx] = (unsigned long long)llrint((double)sx * Q);   // two's complement wrap = signed add
+    s_acc[2][wdx] = (unsigned long long)llrint((double)sy * Q);
+    s_mx[wdx] = __float_as_uint(mx);                              // mx >= 0: bit order == value order
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
     unsigned long long* acc = (unsigned long long*)(stats + (size_t)b * B2OF_STATS_WIDTH);
-    const double Q = 1048576.0;
-    atomicAdd(acc + 0, (unsigned long long)llrint((double)sm * Q));
-    atomicAdd(acc + 1, (unsigned long long)llrint((double)sx * Q));  // two's complement wrap = signed add
-    atomicAdd(acc + 2, (unsigned long long)llrint((double)sy * Q));
-    atomicMax((unsigned int*)(acc + 3), __float_as_uint(mx));        // mx >= 0: bit order == value order
+    if (threadIdx.x < 3) {
+      unsigned long long v = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v += s_acc[threadIdx.x][k];
+      atomicAdd(acc + threadIdx.x, v);
+    } else {
+      unsigned int v = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v = max(v, s_mx[k]);
+      atomicMax((unsigned int*)(acc + 3), v);
+    }
   }
 }
 
