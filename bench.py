@@ -164,6 +164,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=CHUNK_PAIRS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--separate-stats", action="store_true",
+                    help="A/B only: per-pair statistics by a second pass over the flow fields (b2of_flow_stats_dev)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -185,12 +187,16 @@ def main():
     frames = torch.from_numpy(frames_host).to(dev)
     eng = batch.FarnebackEngine(H, W, chunk_pairs=args.chunk, device=dev, **PARAMS)
     flow = torch.empty((P, H, W, 2), dtype=torch.float32, device=dev)
+    pair_stats = torch.empty((P, 8), dtype=torch.float32, device=dev)
     lib = _lib.lib()
 
     def step():
-        eng.flow_sequence(frames, flow)
-        st = batch.flow_stats(flow)
-        return b2dist.gather_stats(st, n_frames_global, rank, world)
+        # flow fields + per-pair statistics (reduced inside the last iteration kernel), then the gather to rank 0
+        if args.separate_stats:
+            eng.flow_sequence(frames, flow)
+            return b2dist.gather_stats(batch.flow_stats(flow), n_frames_global, rank, world)
+        eng.flow_sequence(frames, flow, stats=pair_stats)
+        return b2dist.gather_stats(pair_stats, n_frames_global, rank, world)
 
     def barrier():
         if world > 1:

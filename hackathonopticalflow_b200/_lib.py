@@ -49,6 +49,7 @@ _PF, _PL, _PG = C.POINTER(FarnebackParams), C.POINTER(LKParams), C.POINTER(GFTTP
 SIGNATURES = {
     "b2of_version": (_i, []),
     "b2of_last_error": (C.c_char_p, []),
+    "b2of_release": (_i, []),
     "b2of_launch_count": (C.c_ulonglong, []),
     "b2of_profile_enable": (None, [_i]),
     "b2of_profile_reset": (None, []),
@@ -62,6 +63,7 @@ SIGNATURES = {
     "b2of_farneback_workspace_bytes": (_sz, [_i, _i, _PF, _i, _i]),
     "b2of_farneback_pairs_dev": (_i, [_vp, _vp, _sz, _sz, _i, _i, _i, _PF, _vp, _vp, _sz, _vp]),
     "b2of_farneback_sequence_dev": (_i, [_vp, _sz, _sz, _i, _i, _i, _PF, _vp, _vp, _sz, _vp]),
+    "b2of_farneback_sequence_stats_dev": (_i, [_vp, _sz, _sz, _i, _i, _i, _PF, _vp, _vp, _vp, _sz, _vp]),
     "b2of_farneback_host": (_i, [_vp, _vp, _sz, _i, _i, _PF, _vp]),
     "b2of_farneback_pairs_host": (_i, [_vp, _vp, _sz, _sz, _i, _i, _i, _PF, _vp]),
     "b2of_farneback_sequence_host": (_i, [_vp, _sz, _sz, _i, _i, _i, _PF, _vp]),
@@ -71,7 +73,7 @@ SIGNATURES = {
     "b2of_gftt_workspace_bytes": (_sz, [_i, _i, _PG, _i]),
     "b2of_gftt_dev": (_i, [_vp, _vp, _sz, _sz, _i, _i, _i, _PG, _vp, _i, _vp, _vp, _sz, _vp]),
     "b2of_gftt_host": (_i, [_vp, _vp, _sz, _sz, _i, _i, _PG, _vp, _i, _vp]),
-    "b2of_pathfinder_filter_dev": (_i, [_vp, _sz, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b2of_pathfinder_filter_dev": (_i, [_vp, _sz, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b2of_flow_sample_dev": (_i, [_vp, _i, _i, _i, _vp, _sz, _i, _vp, _vp]),
     "b2of_flow_hsv_dev": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "b2of_flow_stats_dev": (_i, [_vp, _i, _i, _i, _vp, _vp]),

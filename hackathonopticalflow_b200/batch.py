@@ -31,6 +31,13 @@ def _check_u8_frames(t, name):
         raise _lib.error(-215, f"{name} must be a contiguous CUDA uint8 tensor (N,H,W)")
 
 
+def _check_out(t, shape, dtype, device, name):
+    """A caller-supplied output tensor must be exactly what the kernel will write (the C-ABI takes bare pointers)."""
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.device == device and t.dtype == dtype
+            and tuple(t.shape) == tuple(shape) and t.is_contiguous()):
+        raise _lib.error(-215, f"{name} must be a contiguous {dtype} CUDA tensor of shape {tuple(shape)} on {device}")
+
+
 def bgr2gray(bgr, out=None):
     """uint8 (N,H,W,3) or (H,W,3) CUDA tensor -> uint8 (N,H,W) / (H,W).  Bit-exact with cv2.cvtColor(BGR2GRAY)."""
     squeeze = bgr.dim() == 3
@@ -40,6 +47,7 @@ def bgr2gray(bgr, out=None):
     n, h, w, _ = b.shape
     if out is None:
         out = torch.empty((n, h, w), dtype=torch.uint8, device=b.device)
+    _check_out(out, (n, h, w), torch.uint8, b.device, "out")
     with torch.cuda.device(b.device):
         _lib.check(_lib.lib().b2of_bgr2gray_u8_dev(_p(b), h, w, w * 3, h * w * 3, _p(out), w, h * w, n, _stream()))
     return out[0] if squeeze else out
@@ -52,6 +60,7 @@ def pyrdown(img, out=None):
     dh, dw = (h + 1) // 2, (w + 1) // 2
     if out is None:
         out = torch.empty((n, dh, dw), dtype=torch.uint8, device=img.device)
+    _check_out(out, (n, dh, dw), torch.uint8, img.device, "out")
     with torch.cuda.device(img.device):
         _lib.check(_lib.lib().b2of_pyrdown_u8_dev(_p(img), h, w, w, h * w, _p(out), dw, dh * dw, n, _stream()))
     return out
@@ -80,17 +89,26 @@ class FarnebackEngine:
             _lib.check(-215)
         self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
 
-    def flow_sequence(self, frames, out=None):
-        """uint8 (F,H,W) consecutive frames -> float32 (F-1,H,W,2); per-frame work is done once per frame."""
+    def flow_sequence(self, frames, out=None, stats=None):
+        """uint8 (F,H,W) consecutive frames -> float32 (F-1,H,W,2); per-frame work is done once per frame.
+
+        ``stats``: optional float32 (F-1,8) CUDA tensor that receives the per-pair flow statistics of
+        :func:`flow_stats`, reduced inside the last iteration kernel (no second pass over the flow fields)."""
         _check_u8_frames(frames, "frames")
         f, h, w = frames.shape
-        assert (h, w) == (self.rows, self.cols)
+        if (h, w) != (self.rows, self.cols):
+            raise _lib.error(-215, f"frames are {h}x{w}, the engine was built for {self.rows}x{self.cols}")
+        shape = (max(f - 1, 0), h, w, 2)
         if out is None:
-            out = torch.empty((max(f - 1, 0), h, w, 2), dtype=torch.float32, device=frames.device)
+            out = torch.empty(shape, dtype=torch.float32, device=frames.device)
+        _check_out(out, shape, torch.float32, frames.device, "out")
+        if stats is not None:
+            _check_out(stats, (shape[0], 8), torch.float32, frames.device, "stats")
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().b2of_farneback_sequence_dev(_p(frames), w, h * w, f, h, w, C.byref(self.params),
-                                                              _p(out), _p(self.workspace), self.workspace.numel(),
-                                                              _stream()))
+            _lib.check(_lib.lib().b2of_farneback_sequence_stats_dev(_p(frames), w, h * w, f, h, w,
+                                                                    C.byref(self.params), _p(out), _p(stats),
+                                                                    _p(self.workspace), self.workspace.numel(),
+                                                                    _stream()))
         return out
 
     def flow_pairs(self, prev, next, out=None):
@@ -99,9 +117,11 @@ class FarnebackEngine:
         _check_u8_frames(next, "next")
         assert prev.shape == next.shape
         b, h, w = prev.shape
-        assert (h, w) == (self.rows, self.cols)
+        if (h, w) != (self.rows, self.cols):
+            raise _lib.error(-215, f"frames are {h}x{w}, the engine was built for {self.rows}x{self.cols}")
         if out is None:
             out = torch.empty((b, h, w, 2), dtype=torch.float32, device=prev.device)
+        _check_out(out, (b, h, w, 2), torch.float32, prev.device, "out")
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().b2of_farneback_pairs_dev(_p(prev), _p(next), w, h * w, b, h, w,
                                                            C.byref(self.params), _p(out), _p(self.workspace),
@@ -136,6 +156,7 @@ def pyrlk(prev, next, prev_pts, next_pts=None, winSize=(21, 21), maxLevel=3, cri
         if flags & 4:
             raise _lib.error(-215, "nextPtsMat.checkVector(2, CV_32F, true) == npoints")
         next_pts = torch.empty((b, n, 2), dtype=torch.float32, device=prev.device)
+    _check_out(next_pts, (b, n, 2), torch.float32, prev.device, "next_pts")
     status = torch.empty((b, n), dtype=torch.uint8, device=prev.device)
     err = torch.empty((b, n), dtype=torch.float32, device=prev.device)
     with torch.cuda.device(prev.device):
@@ -176,16 +197,25 @@ def gftt(img, mask=None, maxCorners=20, qualityLevel=0.3, minDistance=10, blockS
     return corners, count
 
 
-def pathfinder_filter(pts, next_pts, width, height):
+FILTER_VIEWER, FILTER_DENSEOF = 0, 1
+
+
+def pathfinder_filter(pts, next_pts, width, height, mode=FILTER_VIEWER):
     """The viewer's vector filter + danger intensity (pathfinder_viewer.py:159-178, :210-217) per frame.
 
     pts float32 (N,2) shared grid or (B,N,2); next_pts float32 (B,N,2).
+    mode: FILTER_VIEWER keeps median < m < p99 (pathfinder_viewer.py:171); FILTER_DENSEOF keeps m > 1.2 * median
+    (the development script's rule, DenseOF.py:228).
     Returns dict(kept_pts int32 (B,N,2), kept_flow int32 (B,N,2), danger_v uint8 (B,N), mask uint8 (B,N),
                  n_kept int32 (B), stats float32 (B,8)); rows [0, n_kept[b]) of the kept_* arrays are valid.
     """
+    if not (isinstance(next_pts, torch.Tensor) and next_pts.is_cuda and next_pts.dtype == torch.float32
+            and next_pts.dim() == 3 and next_pts.shape[-1] == 2 and next_pts.is_contiguous()):
+        raise _lib.error(-215, "next_pts must be a contiguous float32 CUDA tensor (B,N,2)")
     b, n, _ = next_pts.shape
     shared = pts.dim() == 2
     dev = next_pts.device
+    _check_out(pts, (n, 2) if shared else (b, n, 2), torch.float32, dev, "pts")
     out = dict(kept_pts=torch.zeros((b, n, 2), dtype=torch.int32, device=dev),
                kept_flow=torch.zeros((b, n, 2), dtype=torch.int32, device=dev),
                danger_v=torch.zeros((b, n), dtype=torch.uint8, device=dev),
@@ -194,7 +224,7 @@ def pathfinder_filter(pts, next_pts, width, height):
                stats=torch.zeros((b, 8), dtype=torch.float32, device=dev))
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().b2of_pathfinder_filter_dev(_p(pts), 0 if shared else n, _p(next_pts), n, b, int(width),
-                                                         int(height), _p(out["kept_pts"]), _p(out["kept_flow"]),
+                                                         int(height), int(mode), _p(out["kept_pts"]), _p(out["kept_flow"]),
                                                          _p(out["danger_v"]), _p(out["mask"]), _p(out["n_kept"]),
                                                          _p(out["stats"]), _stream()))
     return out

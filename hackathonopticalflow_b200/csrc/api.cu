@@ -53,14 +53,15 @@ int bgr2gray_dev(const uint8_t*, int, int, size_t, size_t, uint8_t*, size_t, siz
 int pyrdown_dev(const uint8_t*, int, int, size_t, size_t, uint8_t*, size_t, size_t, int, cudaStream_t);
 size_t farneback_workspace_bytes(int, int, const b2of_farneback_params*, int, int);
 int farneback_dev(const uint8_t*, const uint8_t*, size_t, size_t, int, int, int, int, const b2of_farneback_params*,
-                  float*, void*, size_t, cudaStream_t);
+                  float*, float*, void*, size_t, cudaStream_t);
+void farneback_release();
 size_t pyrlk_workspace_bytes(int, int, const b2of_lk_params*, int);
 int pyrlk_dev(const uint8_t*, const uint8_t*, size_t, size_t, int, int, int, const float*, size_t, int, float*,
               uint8_t*, float*, const b2of_lk_params*, void*, size_t, cudaStream_t);
 size_t gftt_workspace_bytes(int, int, const b2of_gftt_params*, int);
 int gftt_dev(const uint8_t*, const uint8_t*, size_t, size_t, int, int, int, const b2of_gftt_params*, float*, int, int*,
              void*, size_t, cudaStream_t);
-int pathfinder_filter_dev(const float*, size_t, const float*, int, int, int, int, int32_t*, int32_t*, uint8_t*,
+int pathfinder_filter_dev(const float*, size_t, const float*, int, int, int, int, int, int32_t*, int32_t*, uint8_t*,
                           uint8_t*, int32_t*, float*, cudaStream_t);
 int flow_stats_dev(const float*, int, int, int, float*, cudaStream_t);
 int flow_sample_dev(const float*, int, int, int, const float*, size_t, int, float*, cudaStream_t);
@@ -132,6 +133,38 @@ using namespace b2of;
 extern "C" {
 
 int b2of_version(void) { return B2OF_VERSION; }
+
+// Frees what the library caches between calls: the host-call contexts (streams, events, grow-only device buffers)
+// of every device and the Farneback plans (device tables).  The caller guarantees that no call is in flight; the
+// next call rebuilds what it needs.
+int b2of_release(void) {
+  int cur = 0;
+  cudaGetDevice(&cur);
+  {
+    std::lock_guard<std::mutex> lock(g_ctx_mu);
+    for (int d = 0; d < 64; ++d) {
+      HostCtx* c = g_ctx[d];
+      if (!c) continue;
+      cudaSetDevice(d);
+      {
+        std::lock_guard<std::mutex> l2(c->mu);
+        if (c->ready) {
+          for (auto& s : c->st) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+          for (auto& e : c->ev) cudaEventDestroy(e);
+        }
+        for (DevBuf* b : {&c->in[0], &c->in[1], &c->out[0], &c->out[1], &c->ws, &c->aux[0], &c->aux[1], &c->aux[2],
+                          &c->aux[3]})
+          if (b->p) cudaFree(b->p);
+      }
+      delete c;
+      g_ctx[d] = nullptr;
+    }
+  }
+  cudaSetDevice(cur);
+  farneback_release();
+  b2of_profile_reset();
+  return B2OF_OK;
+}
 const char* b2of_last_error(void) { return t_err; }
 unsigned long long b2of_launch_count(void) { return g_launches.load(); }
 
@@ -238,7 +271,7 @@ size_t b2of_farneback_workspace_bytes(int rows, int cols, const b2of_farneback_p
 int b2of_farneback_pairs_dev(const uint8_t* prev, const uint8_t* next, size_t step, size_t frame_stride, int n_pairs,
                              int rows, int cols, const b2of_farneback_params* p, float* flow, void* ws, size_t ws_bytes,
                              void* stream) {
-  return farneback_dev(prev, next, step, frame_stride, n_pairs, 0, rows, cols, p, flow, ws, ws_bytes,
+  return farneback_dev(prev, next, step, frame_stride, n_pairs, 0, rows, cols, p, flow, nullptr, ws, ws_bytes,
                        (cudaStream_t)stream);
 }
 
@@ -246,8 +279,16 @@ int b2of_farneback_sequence_dev(const uint8_t* frames, size_t step, size_t frame
                                 int cols, const b2of_farneback_params* p, float* flow, void* ws, size_t ws_bytes,
                                 void* stream) {
   if (n_frames < 2) return B2OF_OK;
-  return farneback_dev(frames, frames + frame_stride, step, frame_stride, n_frames - 1, 1, rows, cols, p, flow, ws,
-                       ws_bytes, (cudaStream_t)stream);
+  return farneback_dev(frames, frames + frame_stride, step, frame_stride, n_frames - 1, 1, rows, cols, p, flow, nullptr,
+                       ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int b2of_farneback_sequence_stats_dev(const uint8_t* frames, size_t step, size_t frame_stride, int n_frames, int rows,
+                                      int cols, const b2of_farneback_params* p, float* flow, float* stats, void* ws,
+                                      size_t ws_bytes, void* stream) {
+  if (n_frames < 2) return B2OF_OK;
+  return farneback_dev(frames, frames + frame_stride, step, frame_stride, n_frames - 1, 1, rows, cols, p, flow, stats,
+                       ws, ws_bytes, (cudaStream_t)stream);
 }
 
 // Pipelined host form shared by the pairs and the sequence entry points: H2D (st[1]) -> compute (st[0]) -> D2H
@@ -317,9 +358,10 @@ static int farneback_host_pipeline(const uint8_t* prev, const uint8_t* next, siz
     B2OF_CUDA(cudaStreamWaitEvent(s_c, c->ev[b], 0));
     if (ci >= 2) B2OF_CUDA(cudaStreamWaitEvent(s_c, c->ev[4 + b], 0));  // previous output in this slot drained
     if (shared)
-      rc = farneback_dev(din, din + frame, cols, frame, np, 1, rows, cols, p, dout, c->ws.p, c->ws.cap, s_c);
+      rc = farneback_dev(din, din + frame, cols, frame, np, 1, rows, cols, p, dout, nullptr, c->ws.p, c->ws.cap, s_c);
     else
-      rc = farneback_dev(din, din + frame, cols, 2 * frame, np, 0, rows, cols, p, dout, c->ws.p, c->ws.cap, s_c);
+      rc = farneback_dev(din, din + frame, cols, 2 * frame, np, 0, rows, cols, p, dout, nullptr, c->ws.p, c->ws.cap,
+                         s_c);
     if (rc) return rc;
     B2OF_CUDA(cudaEventRecord(c->ev[2 + b], s_c));
     B2OF_CUDA(cudaStreamWaitEvent(s_out, c->ev[2 + b], 0));
@@ -446,9 +488,9 @@ int b2of_gftt_host(const uint8_t* img, const uint8_t* mask, size_t step, size_t 
 
 // ---- K12 ----
 int b2of_pathfinder_filter_dev(const float* pts, size_t pts_batch_stride, const float* next_pts, int n_pts, int batch,
-                               int width, int height, int32_t* kept_pts, int32_t* kept_flow, uint8_t* danger_v,
-                               uint8_t* mask, int32_t* n_kept, float* stats, void* stream) {
-  return pathfinder_filter_dev(pts, pts_batch_stride, next_pts, n_pts, batch, width, height, kept_pts, kept_flow,
+                               int width, int height, int mode, int32_t* kept_pts, int32_t* kept_flow,
+                               uint8_t* danger_v, uint8_t* mask, int32_t* n_kept, float* stats, void* stream) {
+  return pathfinder_filter_dev(pts, pts_batch_stride, next_pts, n_pts, batch, width, height, mode, kept_pts, kept_flow,
                                danger_v, mask, n_kept, stats, (cudaStream_t)stream);
 }
 

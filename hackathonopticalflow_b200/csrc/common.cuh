@@ -81,6 +81,32 @@ struct ProfScope {
   ~ProfScope() { if (on) prof_mark(tag, st, true, 0); }
 };
 
+// Function attributes (the dynamic shared-memory opt-in) apply to the device that is current when they are set, so
+// every "set it once" site keeps one record per device ordinal.
+constexpr int B2OF_MAX_DEVICES = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev < 0 || dev >= B2OF_MAX_DEVICES ? 0 : dev;
+}
+struct PerDeviceOnce {            // first(): true exactly once per device (benign race: the guarded calls are idempotent)
+  std::atomic<unsigned long long> mask{0};
+  bool first() {
+    const unsigned long long bit = 1ull << current_device();
+    return (mask.fetch_or(bit) & bit) == 0;
+  }
+};
+struct PerDeviceMax {             // raise(n): true when n exceeds what was recorded for the current device
+  std::atomic<size_t> v[B2OF_MAX_DEVICES];
+  PerDeviceMax() { for (auto& x : v) x.store(0); }
+  bool raise(size_t n) {
+    auto& x = v[current_device()];
+    if (n <= x.load()) return false;
+    x.store(n);
+    return true;
+  }
+};
+
 // linear bump allocator over a caller-provided workspace
 struct Arena {
   char* base;

@@ -346,6 +346,20 @@ static int build_plan(int rows, int cols, const b2of_farneback_params& p, FbPlan
   return B2OF_OK;
 }
 
+// b2of_release(): drop every cached plan (their device tables) -- the caller guarantees no call is in flight
+void farneback_release() {
+  std::lock_guard<std::mutex> lock(g_plan_mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (auto& kv : g_plans) {
+    cudaSetDevice(kv.first.dev);
+    cudaFree(kv.second->table_block);
+    delete kv.second;
+  }
+  g_plans.clear();
+  cudaSetDevice(cur);
+}
+
 static int get_plan(int rows, int cols, const b2of_farneback_params& p, FbPlan** out) {
   PlanKey key;
   memset(&key, 0, sizeof key);
@@ -575,11 +589,9 @@ __global__ void __launch_bounds__(lr_nt(S)) fb_level_regular(LevelRegArgs a) {
 
 template <int K, int S>
 static void launch_level_regular(const LevelRegArgs& ra, int frames, cudaStream_t st) {
-  static bool attr_done = false;  // benign race: idempotent
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first())
     cudaFuncSetAttribute(fb_level_regular<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lr_smem(K, S));
-    attr_done = true;
-  }
   dim3 g(cdiv(ra.wk, LR_TW), cdiv(ra.hk, lr_th(S)), frames);
   fb_level_regular<K, S><<<g, lr_nt(S), lr_smem(K, S), st>>>(ra);
 }
@@ -787,6 +799,7 @@ struct IterArgs {
   int nb;                  // vertically adjacent tiles walked by one CTA
   float inv_area;          // 1 / winsize^2 (box)
   const float* gtaps;      // Gaussian window taps or nullptr
+  unsigned long long* stats_acc;  // fb_iter_ws, last iteration only: per-pair fixed-point flow statistics, or nullptr
 };
 
 __device__ __forceinline__ float4 add4(float4 a, float4 b) {
@@ -1211,6 +1224,22 @@ __global__ void __launch_bounds__(256) fb_initflow_area(const float2* __restrict
 }
 
 // ----------------------------------------------------------------------------------------------
+// iterations == 0: cv2 still walks the pyramid, so the result is the initial flow (zero, or the caller's field
+// area-resized to the coarsest level) carried up by the x(1/pyr_scale) bilinear resize of every level.
+// ----------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) fb_flow_only(IterArgs a) {
+  const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y, pair = blockIdx.z;
+  if (x >= a.w) return;
+  const float2* fin = MODE ? a.flow_in + (size_t)pair * a.flow_in_pair_stride : nullptr;
+  int xa = 0, xb = 0;
+  float fx = 0.f;
+  if (MODE == 2) { xa = a.ux0[x]; xb = a.ux1[x]; fx = a.ufx[x]; }
+  a.flow_out[(size_t)pair * a.flow_out_pair_stride + (size_t)y * a.out_pitch + x] =
+      fetch_flow_m<MODE>(a, fin, y * a.pitch + x, y, xa, xb, fx);
+}
+
+// ----------------------------------------------------------------------------------------------
 // host driver
 // ----------------------------------------------------------------------------------------------
 struct FbWorkspace {
@@ -1330,7 +1359,7 @@ static int fb_frames(const FbPlan* pl, const FbWorkspace& ws, const uint8_t* fra
   return B2OF_OK;
 }
 
-static std::once_flag g_attr_once;
+static PerDeviceOnce g_attr_once;
 static void set_func_attrs() {
   const int big = 227 * 1024;
 #define B2OF_ATTR(NT_, CT_, CM_, G_)                                                                        \
@@ -1340,16 +1369,22 @@ static void set_func_attrs() {
   B2OF_ATTR(512, 0, 0, false)
   B2OF_ATTR(512, 0, 0, true)
 #undef B2OF_ATTR
-  cudaFuncSetAttribute(fb_iter_ws<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
-  cudaFuncSetAttribute(fb_iter_ws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
-  cudaFuncSetAttribute(fb_iter_ws<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
+  cudaFuncSetAttribute(fb_iter_ws<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
+  cudaFuncSetAttribute(fb_iter_ws<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
+  cudaFuncSetAttribute(fb_iter_ws<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
+  cudaFuncSetAttribute(fb_iter_ws<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
+  cudaFuncSetAttribute(fb_iter_ws<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
+  cudaFuncSetAttribute(fb_iter_ws<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
   cudaFuncSetAttribute(fb_polyexp, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   cudaFuncSetAttribute(fb_level_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 }
 
 // iterations for `pairs` pairs whose frames sit in workspace slots (pair p -> slots p*fstep, p*fstep+1)
+int flow_stats_dev(const float*, int, int, int, float*, cudaStream_t);          // pathfinder.cu
+int flow_stats_finalize_dev(float*, size_t, int, cudaStream_t);
+
 static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fstep, int total_slots, float* flow_out,
-                    const b2of_farneback_params& p, cudaStream_t st) {
+                    float* stats, const b2of_farneback_params& p, cudaStream_t st) {
   // `p` is THIS call's parameter block: the cached plan only fixes what its key holds (sizes, windows, taps)
   const int call_flags = p.flags;
   const int m = p.winsize / 2;
@@ -1363,11 +1398,12 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
   size_t smem = (size_t)5 * E * (E | 1) * sizeof(float);
   if (!fast && (smem > 227 * 1024 || E > IT_THREADS / 4))
     return fail(B2OF_E_UNSUPPORTED, "winsize %d needs %zu B of shared memory", p.winsize, smem);
-  static int n_sm = 0;
+  static std::atomic<int> n_sm_dev[B2OF_MAX_DEVICES];
+  int n_sm = n_sm_dev[current_device()].load();
   if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, current_device()) != cudaSuccess || n_sm <= 0)
+      n_sm = 148;
+    n_sm_dev[current_device()].store(n_sm);
   }
   size_t lvl_off = 0;
   const float2* coarse = nullptr;
@@ -1403,11 +1439,8 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
     a.nb = nb;
     dim3 grid(pairs, cx, cdiv(cy, nb));
     int iters = p.iterations;
-    if (iters == 0) {
-      // cv2 with iterations == 0 returns the (upsampled) initial flow of the finest level untouched;
-      // run one pass of the upsample through a degenerate path is not worth a kernel: treat as unsupported
-      return fail(B2OF_E_UNSUPPORTED, "iterations == 0 is not supported");
-    }
+    const bool flow_only = iters == 0;              // cv2: the level's initial flow is its result
+    if (flow_only) iters = 1;
     for (int it = 0; it < iters; ++it) {
       if (it == 0) {
         if (!coarse && (call_flags & B2OF_OPTFLOW_USE_INITIAL_FLOW)) {   // per call: the plan is shared
@@ -1439,6 +1472,21 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
         dst = (it & 1) ? B : A; dpitch = L.pitch; dstride = plane;
       }
       a.flow_out = dst; a.out_pitch = dpitch; a.flow_out_pair_stride = dstride;
+      a.stats_acc = nullptr;
+      if (flow_only) {
+        dim3 gf(cdiv(L.w, 256), L.h, pairs);
+        if (a.mode == 0) fb_flow_only<0><<<gf, 256, 0, st>>>(a);
+        else if (a.mode == 1) fb_flow_only<1><<<gf, 256, 0, st>>>(a);
+        else fb_flow_only<2><<<gf, 256, 0, st>>>(a);
+        B2OF_LAUNCH_CHECK();
+        cur = dst; cur_pitch = dpitch; cur_stride = dstride;
+        continue;
+      }
+      if (final_out && stats && fast) {
+        // the last launch also reduces its flow field to the per-pair statistics (fixed-point partial sums)
+        B2OF_CUDA(cudaMemsetAsync(stats, 0, (size_t)pairs * B2OF_STATS_WIDTH * sizeof(float), st));
+        a.stats_acc = (unsigned long long*)stats;
+      }
       {
         // algorithmic bytes of this launch: R0 + R1 (20 B/px each), flow in (8 B/px, or 8 B per coarse px, or none),
         // flow out (8 B/px)
@@ -1469,9 +1517,15 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
           if (b.mode == 1 && b.in_pitch != L.pitch)     // the kernel indexes flow_in with the level's own pitch
             return fail(B2OF_E_BADARG, "internal: flow_in pitch %d != level pitch %d", b.in_pitch, L.pitch);
           dim3 gs(pairs, nstrips, cdiv(blocks, b.nb));
-          if (b.mode == 0) fb_iter_ws<0><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
-          else if (b.mode == 1) fb_iter_ws<1><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
-          else fb_iter_ws<2><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
+          if (b.stats_acc) {
+            if (b.mode == 0) fb_iter_ws<0, true><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
+            else if (b.mode == 1) fb_iter_ws<1, true><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
+            else fb_iter_ws<2, true><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
+          } else {
+            if (b.mode == 0) fb_iter_ws<0, false><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
+            else if (b.mode == 1) fb_iter_ws<1, false><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
+            else fb_iter_ws<2, false><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
+          }
         } else if (gauss) B2OF_ITER_LAUNCH(512, 0, 0, true);
         else B2OF_ITER_LAUNCH(512, 0, 0, false);
 #undef B2OF_ITER_LAUNCH
@@ -1482,22 +1536,27 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
     coarse = cur; cpitch = cur_pitch; cstride = cur_stride; cw = L.w; ch = L.h;
     lvl_off += plane;
   }
+  if (stats) {
+    if (fast && p.iterations > 0) return flow_stats_finalize_dev(stats, (size_t)pl->rows * pl->cols, pairs, st);
+    return flow_stats_dev(flow_out, pairs, pl->rows, pl->cols, stats, st);
+  }
   return B2OF_OK;
 }
 
 int farneback_dev(const uint8_t* prev, const uint8_t* next, size_t step, size_t frame_stride, int n_pairs, int shared,
-                  int rows, int cols, const b2of_farneback_params* p, float* flow, void* workspace,
+                  int rows, int cols, const b2of_farneback_params* p, float* flow, float* stats, void* workspace,
                   size_t workspace_bytes, cudaStream_t st) {
   int rc = check_params(rows, cols, p);
   if (rc) return rc;
   const char* fn = "calcOpticalFlowFarneback";
   B2OF_ASSERT(prev != nullptr && next != nullptr && flow != nullptr, fn);
   B2OF_ASSERT(step >= (size_t)cols, fn);
+  B2OF_ASSERT(stats == nullptr || ((uintptr_t)stats & 7) == 0, fn);
   if (n_pairs <= 0) return B2OF_OK;
   FbPlan* pl;
   rc = get_plan(rows, cols, *p, &pl);
   if (rc) return rc;
-  std::call_once(g_attr_once, set_func_attrs);
+  if (g_attr_once.first()) set_func_attrs();
   // largest chunk the workspace can hold
   FbWorkspace ws;
   int chunk = n_pairs;
@@ -1524,7 +1583,8 @@ int farneback_dev(const uint8_t* prev, const uint8_t* next, size_t step, size_t 
       rc = fb_frames(pl, ws, next + (size_t)p0 * frame_stride, step, frame_stride, np, 1, 2, frames, st);
       if (rc) return rc;
     }
-    rc = fb_pairs(pl, ws, np, shared ? 1 : 2, frames, flow + (size_t)p0 * flow_pair, *p, st);
+    rc = fb_pairs(pl, ws, np, shared ? 1 : 2, frames, flow + (size_t)p0 * flow_pair,
+                  stats ? stats + (size_t)p0 * B2OF_STATS_WIDTH : nullptr, *p, st);
     if (rc) return rc;
   }
   return B2OF_OK;

@@ -274,11 +274,9 @@ int gftt_dev(const uint8_t* img, const uint8_t* mask, size_t step, size_t frame_
   const int bs = p->block_size;
   const int E = GF_T + bs - 1;
   size_t smem = (size_t)((3 * E * E + 1) & ~1) * sizeof(float) + (size_t)3 * E * GF_T * sizeof(double);
-  static std::atomic<size_t> max_set{0};
-  if (smem > 48 * 1024 && smem > max_set.load()) {
+  static PerDeviceMax max_set;
+  if (smem > 48 * 1024 && max_set.raise(smem))
     B2OF_CUDA(cudaFuncSetAttribute(gftt_mineig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    max_set.store(smem);
-  }
   float scale = (float)(1.0 / ((double)(1 << (p->gradient_size - 1)) * bs * 255.0));
   dim3 g1(cdiv(cols, GF_T), cdiv(rows, GF_T), batch);
   gftt_mineig<<<g1, 256, smem, st>>>(img, mask, step, frame_stride, cols, rows, bs, scale, p->use_harris, (float)p->k,

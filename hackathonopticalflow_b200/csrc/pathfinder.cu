@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(PF_THREADS) pathfinder_filter(const float* __r
                                                                  uint8_t* __restrict__ danger_v,
                                                                  uint8_t* __restrict__ mask_out,
                                                                  int32_t* __restrict__ n_kept,
-                                                                 float* __restrict__ stats, int np2) {
+                                                                 float* __restrict__ stats, int np2, int mode) {
   extern __shared__ float s_key[];  // the n moduli
   __shared__ unsigned int s_hist[256];
   __shared__ unsigned int s_sel;
@@ -138,7 +138,9 @@ __global__ void __launch_bounds__(PF_THREADS) pathfinder_filter(const float* __r
       qy = (int)(__fadd_rn(__fadd_rn(y, gy), 0.5f));
       px = (int)(x + 0.5f);
       py = (int)(y + 0.5f);
-      keep = (med < m2) && (m2 < p99);
+      // mode 0: the viewer's band  median < m < p99 (pathfinder_viewer.py:171);
+      // mode 1: the development script's  m > 1.2 * median  (DenseOF.py:228; float32 product, as numpy 2 computes it)
+      keep = mode == 1 ? m2 > __fmul_rn(med, 1.2f) : (med < m2) && (m2 < p99);
       mask_out[(size_t)b * n + i] = keep ? 1 : 0;
     }
     unsigned int ballot = __ballot_sync(0xffffffffu, keep);
@@ -189,23 +191,22 @@ __global__ void __launch_bounds__(PF_THREADS) pathfinder_filter(const float* __r
 }
 
 int pathfinder_filter_dev(const float* pts, size_t pts_bstride, const float* next_pts, int n_pts, int batch, int width,
-                          int height, int32_t* kept_pts, int32_t* kept_flow, uint8_t* danger_v, uint8_t* mask,
+                          int height, int mode, int32_t* kept_pts, int32_t* kept_flow, uint8_t* danger_v, uint8_t* mask,
                           int32_t* n_kept, float* stats, cudaStream_t st) {
   const char* fn = "pathfinder_filter";
   B2OF_ASSERT(n_pts >= 1 && batch >= 0 && width > 0 && height > 0, fn);
+  B2OF_ASSERT(mode == B2OF_FILTER_VIEWER || mode == B2OF_FILTER_DENSEOF, fn);
   B2OF_ASSERT(pts && next_pts && kept_pts && kept_flow && danger_v && mask && n_kept && stats, fn);
   if (n_pts > PF_MAX_PTS) return fail(B2OF_E_UNSUPPORTED, "more than %d points per frame", PF_MAX_PTS);
   if (batch == 0) return B2OF_OK;
   int np2 = 1;
   while (np2 < n_pts) np2 <<= 1;
   size_t smem = (size_t)np2 * sizeof(float);
-  static std::atomic<size_t> max_set{0};
-  if (smem > 48 * 1024 && smem > max_set.load()) {
+  static PerDeviceMax max_set;
+  if (smem > 48 * 1024 && max_set.raise(smem))
     B2OF_CUDA(cudaFuncSetAttribute(pathfinder_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    max_set.store(smem);
-  }
   pathfinder_filter<<<batch, PF_THREADS, smem, st>>>(pts, pts_bstride, next_pts, n_pts, width, height, kept_pts,
-                                                     kept_flow, danger_v, mask, n_kept, stats, np2);
+                                                     kept_flow, danger_v, mask, n_kept, stats, np2, mode);
   B2OF_LAUNCH_CHECK();
   return B2OF_OK;
 }
@@ -354,6 +355,14 @@ int flow_hsv_dev(const float* flow, int n_pairs, int rows, int cols, uint8_t* bg
   B2OF_ASSERT(flow != nullptr && bgr != nullptr, fn);
   const size_t n_px = (size_t)n_pairs * rows * cols;
   flow_hsv_bgr<<<(unsigned)((n_px + 255) / 256), 256, 0, st>>>((const float2*)flow, n_px, bgr);
+  B2OF_LAUNCH_CHECK();
+  return B2OF_OK;
+}
+
+// second half of flow_stats for accumulators filled elsewhere (the last fb_iter_ws launch of a pass)
+int flow_stats_finalize_dev(float* stats, size_t n_px, int n_pairs, cudaStream_t st) {
+  if (n_pairs <= 0) return B2OF_OK;
+  flow_stats_final<<<cdiv(n_pairs, 128), 128, 0, st>>>(stats, n_px, n_pairs);
   B2OF_LAUNCH_CHECK();
   return B2OF_OK;
 }

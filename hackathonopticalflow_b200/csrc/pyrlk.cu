@@ -478,11 +478,9 @@ int pyrlk_dev(const uint8_t* prev, const uint8_t* next, size_t step, size_t fram
   a.min_eig_thr = (float)p->min_eig_threshold;
   size_t per_warp = lk_patch_bytes(p->win_w, p->win_h);
   size_t smem = per_warp * LK_WARPS;
-  static std::atomic<size_t> max_set{0};
-  if (smem > 48 * 1024 && smem > max_set.load()) {
+  static PerDeviceMax max_set;
+  if (smem > 48 * 1024 && max_set.raise(smem))
     B2OF_CUDA(cudaFuncSetAttribute(lk_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    max_set.store(smem);
-  }
   dim3 grid(cdiv(n_pts, LK_WARPS), batch);
   {
     // algorithmic bytes: both pyramids once (u8) + derivatives of the first (4 B/px) + 21 B per point

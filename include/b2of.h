@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define B2OF_VERSION 100
+#define B2OF_VERSION 101
 
 #define B2OF_OK 0
 #define B2OF_E_BADARG (-215) /* cv2's StsAssert code: same meaning */
@@ -50,6 +50,9 @@ extern "C" {
 
 int b2of_version(void);
 const char* b2of_last_error(void);
+/* frees everything the library caches between calls (host-call streams / events / staging buffers of every device,
+ * Farneback plans and their device tables).  No call may be in flight; later calls rebuild what they need. */
+int b2of_release(void);
 /* number of kernel launches issued by this library in this process (all threads) */
 unsigned long long b2of_launch_count(void);
 
@@ -106,6 +109,13 @@ int b2of_farneback_pairs_dev(const uint8_t* prev_dev, const uint8_t* next_dev, s
 int b2of_farneback_sequence_dev(const uint8_t* frames_dev, size_t step, size_t frame_stride, int n_frames, int rows,
                                 int cols, const b2of_farneback_params* p, float* flow_dev, void* workspace_dev,
                                 size_t workspace_bytes, void* stream);
+
+/* b2of_farneback_sequence_dev plus the per-pair flow statistics of b2of_flow_stats_dev (float32 (n_frames-1, 8),
+ * 8-byte aligned), reduced inside the last iteration kernel instead of by a second pass over the flow fields.
+ * stats_dev may be NULL. */
+int b2of_farneback_sequence_stats_dev(const uint8_t* frames_dev, size_t step, size_t frame_stride, int n_frames,
+                                      int rows, int cols, const b2of_farneback_params* p, float* flow_dev,
+                                      float* stats_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* the cv2 call itself: host prev/next in, host flow out (flow must not be NULL; the
  * Python shim allocates it when the caller passed None, as cv2 does). */
@@ -173,10 +183,15 @@ int b2of_gftt_host(const uint8_t* img, const uint8_t* mask, size_t step, size_t 
  *   stats float32 (batch, 8): mean|flow|, max|flow|, mean dx, mean dy,
  *                             median modulus, p99 modulus, n_kept, sum danger V. */
 #define B2OF_STATS_WIDTH 8
+/* mode: which of the reference's two mask rules is applied to the normalised moduli m
+ *   B2OF_FILTER_VIEWER   median(m) < m < percentile(m, 99)      viewer.py:171
+ *   B2OF_FILTER_DENSEOF  m > 1.2 * median(m)                    DenseOF.py:228 */
+#define B2OF_FILTER_VIEWER 0
+#define B2OF_FILTER_DENSEOF 1
 int b2of_pathfinder_filter_dev(const float* pts_dev, size_t pts_batch_stride, const float* next_pts_dev, int n_pts,
-                               int batch, int width, int height, int32_t* kept_pts_dev, int32_t* kept_flow_dev,
-                               uint8_t* danger_v_dev, uint8_t* mask_dev, int32_t* n_kept_dev, float* stats_dev,
-                               void* stream);
+                               int batch, int width, int height, int mode, int32_t* kept_pts_dev,
+                               int32_t* kept_flow_dev, uint8_t* danger_v_dev, uint8_t* mask_dev, int32_t* n_kept_dev,
+                               float* stats_dev, void* stream);
 
 /* dense flow sampled on a point set (the grid): next_pts[b][i] = pts[i] + flow[b][int(y_i)][int(x_i)], float32
  * (batch, n_pts, 2) -- feeds b2of_pathfinder_filter_dev with the dense field instead of LK (what draw_flow samples,
