@@ -598,6 +598,129 @@ static void launch_level_regular(const LevelRegArgs& ra, int frames, cudaStream_
 
 
 // ----------------------------------------------------------------------------------------------
+// K3 (coarse levels in one pass): the reference's pyramid (pyr_scale 0.5, three coarse levels) filters the SAME
+// full-resolution frame three times with the regular (K, S) forms (4, 2), (10, 4), (20, 8).  One CTA stages the
+// source region of an 8 x 8 tile of the coarsest level once -- as floats, one conversion per byte instead of one per
+// tap -- and produces that tile together with the 16 x 16 and 32 x 32 tiles of the two finer levels that the same
+// 64 x 64 source pixels feed: the frame is read once instead of three times and 65 x 3 launches of tiny tiles become
+// one.  Per level the arithmetic is fb_level_regular's (same taps, same fused multiply-add order): bit-identical.
+// ----------------------------------------------------------------------------------------------
+constexpr int LC_REG = 76;                // source region edge: rows [64 by - 6, 64 by + 70), same for columns
+constexpr int LC_LPAD = 2;                // columns of left padding: the staged region starts at 64 bx - 8 (word aligned)
+constexpr int LC_RP = 84;                 // region pitch in floats: 16-byte rows, and 84 * 4 B = 80 (mod 128) puts the
+                                          // eight rows of a quarter warp on eight different 16-byte bank groups
+constexpr int LC_NT = 288;                // 9 warps: three per level in the horizontal pass
+struct LevelCoarseArgs {
+  const uint8_t* frames; size_t step, frame_stride; int W, H;
+  float* I[3];                             // level images, S = 2, 4, 8
+  int wk[3], hk[3], pitch[3];
+  size_t i_frame_stride[3];
+  float c2[4], c4[10], c8[20];             // combined taps
+};
+
+// horizontal pass of one region row for outputs [X0, X1) of one level: the row segment is read once, as aligned
+// 16-byte loads, into registers; every tap of every output is then a register operand (the first version read one
+// shared-memory word per tap and was bound by the number of LDS instructions)
+template <int K, int S, int COFF, int P, int X0, int X1>
+__device__ __forceinline__ void lc_hrow(const float* __restrict__ row, float* __restrict__ sh_row,
+                                        const float* __restrict__ c) {
+  constexpr int A0 = (COFF + S * X0) & ~3, A1 = (COFF + S * (X1 - 1) + K + 3) & ~3, NV = (A1 - A0) / 4;
+  float v[4 * NV];
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    const float4 f = *(const float4*)(row + A0 + 4 * q);
+    v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+  }
+#pragma unroll
+  for (int x = X0; x < X1; ++x) {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc = fmaf(c[j], v[COFF + S * x + j - A0], acc);
+    sh_row[x] = acc;
+  }
+}
+
+template <int K, int S, int T, int P>
+__device__ __forceinline__ void lc_vpass(const float* __restrict__ sh, const float* __restrict__ c, int idx,
+                                         float* __restrict__ out, int x0, int y0, int wk, int hk, int pitch) {
+  const int y = idx / T, x = idx - y * T;            // lanes run along x
+  if (x0 + x >= wk || y0 + y >= hk) return;
+  const float* p = sh + (S * y) * P + x;
+  float v = 0.f;
+#pragma unroll
+  for (int j = 0; j < K; ++j) v = fmaf(c[j], p[j * P], v);
+  out[(size_t)(y0 + y) * pitch + x0 + x] = v;
+}
+
+__global__ void __launch_bounds__(LC_NT) fb_levels_coarse(LevelCoarseArgs a) {
+  __shared__ __align__(16) float s_src[LC_REG * LC_RP];   // source region as floats
+  __shared__ float s_h1[66 * 33], s_h2[70 * 17], s_h3[76 * 9];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int gx0 = 64 * blockIdx.x - 8, gy0 = 64 * blockIdx.y - 6;
+  constexpr int NW = (LC_LPAD + LC_REG + 3) / 4;      // 20 words per region row
+  const uint8_t* fb = a.frames + blockIdx.z * a.frame_stride;
+  const bool inside = gx0 >= 0 && gy0 >= 0 && gx0 + 4 * NW <= a.W && gy0 + LC_REG <= a.H &&
+                      ((a.step | (size_t)fb) & 3) == 0;
+  if (inside) {
+    // aligned 4-byte loads, all of them in flight before the first conversion
+    constexpr int PER = (LC_REG * NW + LC_NT - 1) / LC_NT;
+    uint32_t wv[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int i = t + LC_NT * k;
+      const int rr = i / NW, wc = i - rr * NW;
+      wv[k] = i < LC_REG * NW ? __ldg((const uint32_t*)(fb + (size_t)(gy0 + rr) * a.step + gx0) + wc) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int i = t + LC_NT * k;
+      const int rr = i / NW, wc = i - rr * NW;
+      if (i < LC_REG * NW)
+        *(float4*)(s_src + rr * LC_RP + 4 * wc) = make_float4((float)(wv[k] & 255u), (float)((wv[k] >> 8) & 255u),
+                                                              (float)((wv[k] >> 16) & 255u), (float)(wv[k] >> 24));
+    }
+  } else {
+    for (int rr = warp; rr < LC_REG; rr += LC_NT / 32) {
+      const uint8_t* row = fb + (size_t)reflect101(gy0 + rr, a.H) * a.step;
+      for (int cc = lane; cc < 4 * NW; cc += 32) s_src[rr * LC_RP + cc] = (float)row[reflect101(gx0 + cc, a.W)];
+    }
+  }
+  __syncthreads();
+  // horizontal passes, thread = (level, region row): warps 0-2 the S = 8 level (76 rows), 3-5 S = 4 (70 rows from
+  // region row 3), 6-8 S = 2 (66 rows from region row 5); column offsets = c0 - g0 + LPAD = 2, 5, 7
+  {
+    const int lv = warp / 3, r = t - lv * 96;
+    if (lv == 0) {
+      if (r < 76) {
+        lc_hrow<20, 8, 2, 9, 0, 4>(s_src + r * LC_RP, s_h3 + r * 9, a.c8);
+        lc_hrow<20, 8, 2, 9, 4, 8>(s_src + r * LC_RP, s_h3 + r * 9, a.c8);
+      }
+    } else if (lv == 1) {
+      if (r < 70) {
+        lc_hrow<10, 4, 5, 17, 0, 8>(s_src + (r + 3) * LC_RP, s_h2 + r * 17, a.c4);
+        lc_hrow<10, 4, 5, 17, 8, 16>(s_src + (r + 3) * LC_RP, s_h2 + r * 17, a.c4);
+      }
+    } else if (r < 66) {
+      lc_hrow<4, 2, 7, 33, 0, 16>(s_src + (r + 5) * LC_RP, s_h1 + r * 33, a.c2);
+      lc_hrow<4, 2, 7, 33, 16, 32>(s_src + (r + 5) * LC_RP, s_h1 + r * 33, a.c2);
+    }
+  }
+  __syncthreads();
+  constexpr int V1 = 32 * 32, V2 = 16 * 16, V3 = 8 * 8;
+  for (int i = t; i < V1 + V2 + V3; i += LC_NT) {
+    if (i < V1)
+      lc_vpass<4, 2, 32, 33>(s_h1, a.c2, i, a.I[0] + blockIdx.z * a.i_frame_stride[0], 32 * blockIdx.x,
+                             32 * blockIdx.y, a.wk[0], a.hk[0], a.pitch[0]);
+    else if (i < V1 + V2)
+      lc_vpass<10, 4, 16, 17>(s_h2, a.c4, i - V1, a.I[1] + blockIdx.z * a.i_frame_stride[1], 16 * blockIdx.x,
+                              16 * blockIdx.y, a.wk[1], a.hk[1], a.pitch[1]);
+    else
+      lc_vpass<20, 8, 8, 9>(s_h3, a.c8, i - V1 - V2, a.I[2] + blockIdx.z * a.i_frame_stride[2], 8 * blockIdx.x,
+                            8 * blockIdx.y, a.wk[2], a.hk[2], a.pitch[2]);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // K4: polynomial expansion. 64x32 output tile per CTA; the (32+2n)x(64+2n) input tile and the three
 // vertically filtered rows live in shared memory; REPLICATE borders.
 // Output layout per frame and level: Ra = float4 plane (ch0..3) followed by Rb = float plane (ch4), so the
@@ -1293,6 +1416,47 @@ static int fb_frames(const FbPlan* pl, const FbWorkspace& ws, const uint8_t* fra
   const int W = pl->cols, H = pl->rows;
   size_t pitch0 = align_up(W, 32);
   size_t lvl_off = 0;
+  // the reference's three coarse levels ((K, S) = (4, 2), (10, 4), (20, 8)) come out of one pass over the frame
+  bool fused_level[8] = {};
+  {
+    int idx[3] = {-1, -1, -1};
+    const int wantK[3] = {4, 10, 20}, wantS[3] = {2, 4, 8};
+    for (size_t li = 0; li < pl->lv.size() && li < 8; ++li)
+      for (int q = 0; q < 3; ++q)
+        if (pl->lv[li].r_K == wantK[q] && pl->lv[li].r_S == wantS[q]) idx[q] = (int)li;
+    if (idx[0] >= 0 && idx[1] >= 0 && idx[2] >= 0) {
+      LevelCoarseArgs ca{};
+      ca.frames = frames_dev; ca.step = step; ca.frame_stride = frame_stride; ca.W = W; ca.H = H;
+      size_t off = 0;
+      std::vector<size_t> lvoff(pl->lv.size());
+      for (size_t li = 0; li < pl->lv.size(); ++li) { lvoff[li] = off; off += (size_t)pl->lv[li].h * pl->lv[li].pitch; }
+      int gx = 1, gy = 1;
+      const int wantC0[3] = {-1, -3, -6};          // the kernel's region offsets are compiled in for these
+      bool ok = true;
+      for (int q = 0; q < 3; ++q) {
+        const FbLevel& L = pl->lv[idx[q]];
+        const size_t plane = (size_t)L.h * L.pitch;
+        ca.I[q] = ws.I + (size_t)total_slots * lvoff[idx[q]] + (size_t)slot0 * plane;
+        ca.wk[q] = L.w; ca.hk[q] = L.h; ca.pitch[q] = L.pitch; ca.i_frame_stride[q] = plane * slot_step;
+        ok = ok && L.r_c0 == wantC0[q];
+        const int T = 64 / wantS[q];
+        gx = std::max(gx, cdiv(L.w, T)); gy = std::max(gy, cdiv(L.h, T));
+      }
+      memcpy(ca.c2, pl->lv[idx[0]].r_c, sizeof ca.c2);
+      memcpy(ca.c4, pl->lv[idx[1]].r_c, sizeof ca.c4);
+      memcpy(ca.c8, pl->lv[idx[2]].r_c, sizeof ca.c8);
+      if (ok) {
+        double bytes = (double)W * H;
+        for (int q = 0; q < 3; ++q) bytes += 4.0 * ca.wk[q] * ca.hk[q];
+        {
+          ProfScope ps(PT_FB_LEVEL_H, st, (double)frames * bytes);
+          fb_levels_coarse<<<dim3(gx, gy, frames), LC_NT, 0, st>>>(ca);
+        }
+        B2OF_LAUNCH_CHECK();
+        for (int q = 0; q < 3; ++q) fused_level[idx[q]] = true;
+      }
+    }
+  }
   for (size_t li = 0; li < pl->lv.size(); ++li) {
     const FbLevel& L = pl->lv[li];
     size_t plane = (size_t)L.h * L.pitch;
@@ -1300,7 +1464,9 @@ static int fb_frames(const FbPlan* pl, const FbWorkspace& ws, const uint8_t* fra
     float* Ib = ws.I + (size_t)total_slots * lvl_off + (size_t)slot0 * plane;
     float* Rb = ws.R + (size_t)total_slots * 5 * lvl_off + (size_t)slot0 * 5 * plane;
     size_t t_stride = (size_t)H * pitch0 * slot_step, i_stride = plane * slot_step, r_stride = 5 * plane * slot_step;
-    if (L.r_K) {
+    if (li < 8 && fused_level[li]) {
+      // level image already written by fb_levels_coarse
+    } else if (L.r_K) {
       LevelRegArgs ra{};
       ra.frames = frames_dev; ra.step = step; ra.frame_stride = frame_stride; ra.W = W; ra.H = H;
       ra.I = Ib; ra.wk = L.w; ra.hk = L.h; ra.pitch = L.pitch; ra.i_frame_stride = i_stride;
