@@ -172,14 +172,14 @@ def pyrlk(prev, next, prev_pts, next_pts=None, winSize=(21, 21), maxLevel=3, cri
 
 
 def gftt(img, mask=None, maxCorners=20, qualityLevel=0.3, minDistance=10, blockSize=7, useHarrisDetector=False,
-         k=0.04, cap=None, workspace=None):
+         k=0.04, cap=None, workspace=None, gradientSize=3):
     """Batched cv2.goodFeaturesToTrack: uint8 (B,H,W) [+ mask (B,H,W)] -> corners float32 (B,cap,2), count int32 (B)."""
     _check_u8_frames(img, "img")
     if mask is not None:
         _check_u8_frames(mask, "mask")
         assert mask.shape == img.shape
     b, h, w = img.shape
-    p = GFTTParams(int(maxCorners), float(qualityLevel), float(minDistance), int(blockSize), 3,
+    p = GFTTParams(int(maxCorners), float(qualityLevel), float(minDistance), int(blockSize), int(gradientSize),
                    int(bool(useHarrisDetector)), float(k))
     if cap is None:
         cap = int(maxCorners) if maxCorners > 0 else 4096

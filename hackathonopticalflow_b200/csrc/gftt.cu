@@ -20,6 +20,15 @@ __device__ __forceinline__ float ord2f(unsigned int k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// Sobel taps of cv2.getDerivKernels for ksize 5 and 7 (derivative, smoothing)
+__constant__ float c_sobel_d[2][7] = {{-1, -2, 0, 2, 1, 0, 0}, {-1, -4, -5, 0, 5, 4, 1}};
+__constant__ float c_sobel_s[2][7] = {{1, 4, 6, 4, 1, 0, 0}, {1, 6, 15, 20, 15, 6, 1}};
+
+// KS = 3: the reference's path (3x3 Sobel straight from the image).  KS = 5 / 7 (cv2's gradientSize): the tile's source
+// pixels are staged in shared memory, the float32 row filters of cv2's separable Sobel run once per tile row and the
+// column filters once per halo pixel -- same taps, same fused multiply-add order as opencv's sepFilter2D
+// (oracle/gftt.py::sobel_f32, probed against cv2.Sobel bit for bit).
+template <int KS>
 __global__ void __launch_bounds__(256) gftt_mineig(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask,
                                                     size_t step, size_t frame_stride, int w, int h, int bs,
                                                     float scale, int harris, float hk, float* __restrict__ eig,
@@ -32,6 +41,62 @@ __global__ void __launch_bounds__(256) gftt_mineig(const uint8_t* __restrict__ i
   const int x0 = blockIdx.x * GF_T, y0 = blockIdx.y * GF_T;
   const uint8_t* ib = img + blockIdx.z * frame_stride;
   const int t = threadIdx.x;
+  if (KS != 3) {
+    constexpr int RS = KS / 2;
+    // halo pixel (iy, ix) sits at image position (reflect(y0 - r + iy), reflect(x0 - r + ix)); its Sobel window is
+    // taken around THAT position (cv2 filters the whole image, then box-filters with REFLECT_101), so the staged
+    // source rows / columns are the image range those positions and their windows touch
+    int px_lo = w, px_hi = -1, py_lo = h, py_hi = -1;
+    for (int i = 0; i < E; ++i) {
+      const int px = reflect101(x0 - r + i, w), py = reflect101(y0 - r + i, h);
+      px_lo = min(px_lo, px); px_hi = max(px_hi, px); py_lo = min(py_lo, py); py_hi = max(py_hi, py);
+    }
+    const int sx_lo = max(px_lo - RS, 0), sx_hi = min(px_hi + RS, w - 1);
+    const int sy_lo = max(py_lo - RS, 0), sy_hi = min(py_hi + RS, h - 1);
+    const int SW = sx_hi - sx_lo + 1, SH = sy_hi - sy_lo + 1;          // <= E + 2 RS each
+    float* sT = (float*)(sH + 3 * E * GF_T);       // [SH][E] derivative row filter (exact integers)
+    float* sR = sT + (E + 2 * RS) * E;             // [SH][E] scaled smoothing row filter
+    uint8_t* sU = (uint8_t*)(sR + (E + 2 * RS) * E);   // [SH][SW] source pixels
+    for (int i = t; i < SH * SW; i += 256) {
+      const int yy = i / SW, xx = i - yy * SW;
+      sU[i] = ib[(size_t)(sy_lo + yy) * step + sx_lo + xx];
+    }
+    __syncthreads();
+    float ks_[KS], kd_[KS];
+#pragma unroll
+    for (int j = 0; j < KS; ++j) {
+      kd_[j] = c_sobel_d[KS == 5 ? 0 : 1][j];
+      ks_[j] = __fmul_rn(c_sobel_s[KS == 5 ? 0 : 1][j], scale);
+    }
+    for (int i = t; i < SH * E; i += 256) {
+      const int yy = i / E, ix = i - yy * E;
+      const int px = reflect101(x0 - r + ix, w);
+      const uint8_t* row = sU + yy * SW - sx_lo;
+      float tt = 0.f, rr = 0.f;
+#pragma unroll
+      for (int j = 0; j < KS; ++j) {
+        const float v = (float)row[reflect101(px + j - RS, w)];
+        tt = __fmaf_rn(kd_[j], v, tt);                      // integers: exact in any order
+        rr = j == 0 ? __fmul_rn(v, ks_[0]) : __fmaf_rn(v, ks_[j], rr);
+      }
+      sT[i] = tt; sR[i] = rr;
+    }
+    __syncthreads();
+    for (int i = t; i < E * E; i += 256) {
+      const int iy = i / E, ix = i - iy * E;
+      const int py = reflect101(y0 - r + iy, h);
+      auto rowi = [&](int j) { return (reflect101(py + j, h) - sy_lo) * E + ix; };
+      float fx = __fmul_rn(sT[rowi(0)], ks_[RS]);
+#pragma unroll
+      for (int j = 1; j <= RS; ++j) fx = __fmaf_rn(__fadd_rn(sT[rowi(j)], sT[rowi(-j)]), ks_[RS + j], fx);
+      float fy = __fmul_rn(__fsub_rn(sR[rowi(1)], sR[rowi(-1)]), kd_[RS + 1]);
+#pragma unroll
+      for (int j = 2; j <= RS; ++j) fy = __fmaf_rn(__fsub_rn(sR[rowi(j)], sR[rowi(-j)]), kd_[RS + j], fy);
+      sC[i] = __fmul_rn(fx, fx);
+      sC[E * E + i] = __fmul_rn(fx, fy);
+      sC[2 * E * E + i] = __fmul_rn(fy, fy);
+    }
+  } else
   for (int i = t; i < E * E; i += 256) {
     int iy = i / E, ix = i - iy * E;
     int x = reflect101(x0 - r + ix, w), y = reflect101(y0 - r + iy, h);
@@ -75,7 +140,9 @@ __global__ void __launch_bounds__(256) gftt_mineig(const uint8_t* __restrict__ i
     }
     float c0 = (float)s0, c1 = (float)s1, c2 = (float)s2, v;
     if (harris) {
-      v = __fsub_rn(__fsub_rn(__fmul_rn(c0, c2), __fmul_rn(c1, c1)), __fmul_rn(__fmul_rn(hk, __fadd_rn(c0, c2)), __fadd_rn(c0, c2)));
+      // cv2's calcHarris as its SIMD body rounds it (probed bit for bit): (a c - b b) - k ((a + c)(a + c)), float32
+      const float tr = __fadd_rn(c0, c2);
+      v = __fsub_rn(__fsub_rn(__fmul_rn(c0, c2), __fmul_rn(c1, c1)), __fmul_rn(hk, __fmul_rn(tr, tr)));
     } else {
       float a = c0 * 0.5f, b = c1, c = c2 * 0.5f;
       float d = __fsub_rn(a, c);
@@ -140,7 +207,8 @@ __global__ void __launch_bounds__(256) gftt_nms_compact(const float* __restrict_
 // 3x3 neighbourhood; candidates are visited strictly in sorted order, as featureselect.cpp does).
 __global__ void __launch_bounds__(1024) gftt_select(unsigned long long* __restrict__ cand, int cand_cap,
                                                      const int* __restrict__ cand_count, int w, int h,
-                                                     int max_corners, float min_dist, int* __restrict__ cell_head,
+                                                     int max_corners, int cell, double md2,
+                                                     int* __restrict__ cell_head,
                                                      int* __restrict__ next_in_cell, float* __restrict__ corners,
                                                      int corners_cap, int* __restrict__ n_corners) {
   const int b = blockIdx.x;
@@ -166,7 +234,9 @@ __global__ void __launch_bounds__(1024) gftt_select(unsigned long long* __restri
     }
   }
   float* out = corners + (size_t)b * corners_cap * 2;
-  if (min_dist < 1.f) {
+  // cell == 0: cv2's minDistance < 1 branch (no distance test).  The host decides with cv2's own double
+  // arithmetic (minDistance >= 1, cvRound) and passes the cell size and the squared distance down.
+  if (cell == 0) {
     int total = (max_corners > 0 && n > max_corners) ? max_corners : n;
     for (int i = threadIdx.x; i < total && i < corners_cap; i += blockDim.x) {
       unsigned int idx = (unsigned int)(keys[i] & 0xffffffffull);
@@ -176,7 +246,6 @@ __global__ void __launch_bounds__(1024) gftt_select(unsigned long long* __restri
     if (threadIdx.x == 0) n_corners[b] = total;
     return;
   }
-  const int cell = __float2int_rn(min_dist);
   const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
   int* head = cell_head + (size_t)b * gw * gh;
   int* nxt = next_in_cell + (size_t)b * cand_cap;
@@ -184,7 +253,6 @@ __global__ void __launch_bounds__(1024) gftt_select(unsigned long long* __restri
   __syncthreads();
   if (threadIdx.x >= 32) return;
   const int lane = threadIdx.x;
-  const float md2 = min_dist * min_dist;
   int accepted = 0;
   for (int i = 0; i < n; ++i) {
     unsigned int idx = (unsigned int)(keys[i] & 0xffffffffull);
@@ -197,7 +265,7 @@ __global__ void __launch_bounds__(1024) gftt_select(unsigned long long* __restri
         for (int q = head[yy * gw + xx]; q >= 0; q = nxt[q]) {
           unsigned int qi = (unsigned int)(keys[q] & 0xffffffffull);
           float dx = (float)(x - (int)(qi % w)), dy = (float)(y - (int)(qi / w));
-          if (dx * dx + dy * dy < md2) { bad = true; break; }
+          if ((double)(dx * dx + dy * dy) < md2) { bad = true; break; }
         }
       }
     }
@@ -220,14 +288,15 @@ static int gftt_check(int rows, int cols, const b2of_gftt_params* p) {
   B2OF_ASSERT(rows > 0 && cols > 0, fn);
   B2OF_ASSERT(p->quality_level > 0 && p->min_distance >= 0 && p->max_corners >= 0, fn);
   B2OF_ASSERT(p->block_size >= 1, fn);
-  if (p->gradient_size != 3) return fail(B2OF_E_UNSUPPORTED, "gradientSize != 3 is not supported");
+  if (p->gradient_size != 3 && p->gradient_size != 5 && p->gradient_size != 7)
+    return fail(B2OF_E_BADARG, "(-215:Assertion failed) ksize == 3 || ksize == 5 || ksize == 7 in function 'Sobel'");
   if (p->block_size > 31) return fail(B2OF_E_UNSUPPORTED, "blockSize > 31 is not supported");
   return B2OF_OK;
 }
 
 struct GfLayout {
   float* eig; unsigned long long* cand; int* next_in_cell; int* cell_head; unsigned int* max_key; int* cand_count;
-  int cand_cap; size_t cells; size_t bytes;
+  int cand_cap; int cell; size_t cells; size_t bytes;
 };
 
 static void gf_layout(int rows, int cols, const b2of_gftt_params* p, int batch, void* base, size_t cap, GfLayout* L) {
@@ -238,6 +307,7 @@ static void gf_layout(int rows, int cols, const b2of_gftt_params* p, int batch, 
   L->cand_cap = cc;
   int cell = p->min_distance >= 1 ? cv_round(p->min_distance) : 1;
   if (cell < 1) cell = 1;
+  L->cell = p->min_distance >= 1 ? cell : 0;
   L->cells = (size_t)cdiv(cols, cell) * cdiv(rows, cell);
   L->eig = ar.take<float>(n * batch);
   L->cand = ar.take<unsigned long long>((size_t)cc * batch);
@@ -273,21 +343,34 @@ int gftt_dev(const uint8_t* img, const uint8_t* mask, size_t step, size_t frame_
   B2OF_CUDA(cudaMemsetAsync(L.cand_count, 0, sizeof(int) * batch, st));
   const int bs = p->block_size;
   const int E = GF_T + bs - 1;
+  const int ks = p->gradient_size;
   size_t smem = (size_t)((3 * E * E + 1) & ~1) * sizeof(float) + (size_t)3 * E * GF_T * sizeof(double);
-  static PerDeviceMax max_set;
-  if (smem > 48 * 1024 && max_set.raise(smem))
-    B2OF_CUDA(cudaFuncSetAttribute(gftt_mineig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (ks != 3) smem += (size_t)2 * (E + ks - 1) * E * sizeof(float) + (size_t)(E + ks - 1) * (E + ks - 1) + 16;
+  static PerDeviceMax max_set[3];
+  if (smem > 48 * 1024 && max_set[ks == 3 ? 0 : ks == 5 ? 1 : 2].raise(smem)) {
+    if (ks == 3) B2OF_CUDA(cudaFuncSetAttribute(gftt_mineig<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else if (ks == 5) B2OF_CUDA(cudaFuncSetAttribute(gftt_mineig<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else B2OF_CUDA(cudaFuncSetAttribute(gftt_mineig<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   float scale = (float)(1.0 / ((double)(1 << (p->gradient_size - 1)) * bs * 255.0));
   dim3 g1(cdiv(cols, GF_T), cdiv(rows, GF_T), batch);
-  gftt_mineig<<<g1, 256, smem, st>>>(img, mask, step, frame_stride, cols, rows, bs, scale, p->use_harris, (float)p->k,
-                                     L.eig, L.max_key);
+  if (ks == 3)
+    gftt_mineig<3><<<g1, 256, smem, st>>>(img, mask, step, frame_stride, cols, rows, bs, scale, p->use_harris,
+                                          (float)p->k, L.eig, L.max_key);
+  else if (ks == 5)
+    gftt_mineig<5><<<g1, 256, smem, st>>>(img, mask, step, frame_stride, cols, rows, bs, scale, p->use_harris,
+                                          (float)p->k, L.eig, L.max_key);
+  else
+    gftt_mineig<7><<<g1, 256, smem, st>>>(img, mask, step, frame_stride, cols, rows, bs, scale, p->use_harris,
+                                          (float)p->k, L.eig, L.max_key);
   B2OF_LAUNCH_CHECK();
   dim3 g2(cdiv(cols, 32), cdiv(rows, 8), batch);
   gftt_nms_compact<<<g2, 256, 0, st>>>(L.eig, mask, step, frame_stride, cols, rows, p->quality_level, L.max_key, L.cand,
                                        L.cand_cap, L.cand_count);
   B2OF_LAUNCH_CHECK();
-  gftt_select<<<batch, 1024, 0, st>>>(L.cand, L.cand_cap, L.cand_count, cols, rows, p->max_corners,
-                                      (float)p->min_distance, L.cell_head, L.next_in_cell, corners, cap, n_corners);
+  gftt_select<<<batch, 1024, 0, st>>>(L.cand, L.cand_cap, L.cand_count, cols, rows, p->max_corners, L.cell,
+                                      p->min_distance * p->min_distance, L.cell_head, L.next_in_cell, corners,
+                                      cap, n_corners);
   B2OF_LAUNCH_CHECK();
   return B2OF_OK;
 }

@@ -27,6 +27,12 @@ TERM_CRITERIA_EPS = 2
 OPTFLOW_USE_INITIAL_FLOW = 4
 OPTFLOW_LK_GET_MIN_EIGENVALS = 8
 OPTFLOW_FARNEBACK_GAUSSIAN = 256
+ALGO_HINT_DEFAULT, ALGO_HINT_ACCURATE, ALGO_HINT_APPROX = 0, 1, 2
+
+
+def release():
+    """Free what the library caches between calls (per-device streams and staging buffers, Farneback plans)."""
+    _lib.check(_lib.lib().b2of_release())
 
 
 def _assert(cond, text, fn):
@@ -59,7 +65,26 @@ def _new_host(shape, dtype):
     return np.empty(shape, dtype)
 
 
-def cvtColor(src, code, dst=None, dstCn=0):
+def _out_buffer(buf, shape, dtype, fn, holds_input=False):
+    """A caller-supplied result array is used only if the D2H copy can land in it as is (exact shape, dtype,
+    C-contiguous); anything else gets a fresh array -- with the caller's values copied in when the buffer is also an
+    input (OPTFLOW_USE_INITIAL_FLOW).  A wrong-sized buffer that must hold an input is the caller's error."""
+    ok = (isinstance(buf, np.ndarray) and buf.shape == tuple(shape) and buf.dtype == dtype and buf.flags.c_contiguous
+          and buf.flags.writeable)
+    if ok:
+        return buf
+    if holds_input:
+        _assert(isinstance(buf, np.ndarray) and buf.shape == tuple(shape) and buf.dtype == dtype,
+                "flow0.size() == prev0.size() && flow0.type() == CV_32FC2", fn)
+    out = _new_host(shape, dtype)
+    if holds_input:
+        out[...] = buf
+    return out
+
+
+def cvtColor(src, code, dst=None, dstCn=0, hint=0):
+    """``cv2.cvtColor(src, code[, dst[, dstCn[, hint]]])``; ``hint`` (cv2.AlgorithmHint) selects between cv2's exact and
+    approximate colour paths and does not change BGR2GRAY, so it is accepted and ignored."""
     fn = "cvtColor"
     if code != COLOR_BGR2GRAY:
         raise error(-213, f"only COLOR_BGR2GRAY ({COLOR_BGR2GRAY}) is on the reference's path; got code {code}")
@@ -102,6 +127,8 @@ def calcOpticalFlowFarneback(prev, next, flow, pyr_scale, levels, winsize, itera
     if not (isinstance(out, np.ndarray) and out.shape == (h, w, 2) and out.dtype == np.float32
             and out.flags.c_contiguous):
         out = _new_host((h, w, 2), np.float32)
+        if flags & OPTFLOW_USE_INITIAL_FLOW:
+            out[...] = flow          # a strided initial estimate (cv2 accepts any Mat step): upload its values
     p = FarnebackParams(float(pyr_scale), int(levels), int(winsize), int(iterations), int(poly_n), float(poly_sigma),
                         int(flags))
     _lib.check(_lib.lib().b2of_farneback_host(_ptr(prev), _ptr(next), prev.strides[0], h, w, C.byref(p), _ptr(out)))
@@ -116,8 +143,7 @@ def calcOpticalFlowFarnebackBatch(prev, next, pyr_scale=0.5, levels=3, winsize=1
             "prev0.size() == next0.size()", fn)
     prev, next = np.ascontiguousarray(prev), np.ascontiguousarray(next)
     b, h, w = prev.shape
-    if flow is None:
-        flow = _new_host((b, h, w, 2), np.float32)
+    flow = _out_buffer(flow, (b, h, w, 2), np.float32, fn, bool(flags & OPTFLOW_USE_INITIAL_FLOW))
     p = FarnebackParams(float(pyr_scale), int(levels), int(winsize), int(iterations), int(poly_n), float(poly_sigma),
                         int(flags))
     _lib.check(_lib.lib().b2of_farneback_pairs_host(_ptr(prev), _ptr(next), w, h * w, b, h, w, C.byref(p),
@@ -135,8 +161,7 @@ def calcOpticalFlowFarnebackSequence(frames, pyr_scale=0.5, levels=3, winsize=15
             "prev0.type() == CV_8UC1", fn)
     frames = np.ascontiguousarray(frames)
     f, h, w = frames.shape
-    if flow is None:
-        flow = _new_host((max(f - 1, 0), h, w, 2), np.float32)
+    flow = _out_buffer(flow, (max(f - 1, 0), h, w, 2), np.float32, fn, bool(flags & OPTFLOW_USE_INITIAL_FLOW))
     p = FarnebackParams(float(pyr_scale), int(levels), int(winsize), int(iterations), int(poly_n), float(poly_sigma),
                         int(flags))
     _lib.check(_lib.lib().b2of_farneback_sequence_host(_ptr(frames), w, h * w, f, h, w, C.byref(p), _ptr(flow)))
@@ -157,16 +182,24 @@ def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts, status=None, err=No
     shape = prevPts.shape
     pts = np.ascontiguousarray(prevPts.reshape(-1, 2))
     n = len(pts)
+    # cv2 writes into caller-supplied nextPts / status / err of the right size and type and returns those objects
+    def _reuse(buf, want_shape, dtype):
+        return (isinstance(buf, np.ndarray) and buf.dtype == dtype and buf.shape == tuple(want_shape)
+                and buf.flags.c_contiguous and buf.flags.writeable)
     if flags & OPTFLOW_USE_INITIAL_FLOW:
         _assert(isinstance(nextPts, np.ndarray) and nextPts.dtype == np.float32 and nextPts.size == pts.size,
                 "nextPtsMat.checkVector(2, CV_32F, true) == npoints", fn)
-        nxt = np.ascontiguousarray(nextPts.reshape(-1, 2)).copy()
+    if _reuse(nextPts, shape, np.float32):
+        nxt_ret, nxt = nextPts, nextPts.reshape(-1, 2)
     else:
         nxt = np.empty((n, 2), np.float32)
-    st = np.empty((n, 1), np.uint8)
-    er = np.empty((n, 1), np.float32)
+        if flags & OPTFLOW_USE_INITIAL_FLOW:
+            nxt[...] = nextPts.reshape(-1, 2)
+        nxt_ret = nxt.reshape(shape)
+    st = status if _reuse(status, (n, 1), np.uint8) else np.empty((n, 1), np.uint8)
+    er = err if _reuse(err, (n, 1), np.float32) else np.empty((n, 1), np.float32)
     if n == 0:
-        return nxt.reshape(shape), st, er
+        return nxt_ret, st, er
     if prevImg.strides[0] != nextImg.strides[0]:
         prevImg, nextImg = np.ascontiguousarray(prevImg), np.ascontiguousarray(nextImg)
     h, w = prevImg.shape
@@ -174,7 +207,7 @@ def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts, status=None, err=No
                  float(criteria[2]), int(flags), float(minEigThreshold))
     _lib.check(_lib.lib().b2of_pyrlk_host(_ptr(prevImg), _ptr(nextImg), prevImg.strides[0], h, w, _ptr(pts), n,
                                           _ptr(nxt), _ptr(st), _ptr(er), C.byref(p)))
-    return nxt.reshape(shape), st, er
+    return nxt_ret, st, er
 
 
 def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, corners=None, mask=None, blockSize=3,
@@ -195,8 +228,7 @@ def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, corners=No
                 "_mask.empty() || (_mask.type() == CV_8UC1 && _mask.sameSize(_image))", fn)
         mask = _image_u8(mask, "mask", fn)
         mask_step = mask.strides[0]
-    if gradientSize != 3:
-        raise error(-213, "gradientSize != 3 is not supported (the reference uses the default)")
+    _assert(gradientSize in (3, 5, 7), "ksize == 3 || ksize == 5 || ksize == 7", "Sobel")
     p = GFTTParams(int(maxCorners), float(qualityLevel), float(minDistance), int(blockSize), int(gradientSize),
                    int(bool(useHarrisDetector)), float(k))
     cap = int(maxCorners) if maxCorners > 0 else h * w // 4 + 1
@@ -210,4 +242,9 @@ def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, corners=No
         cap = n_out.value
     if n_out.value == 0:
         return None
-    return buf[:n_out.value].copy()
+    res = buf[:n_out.value]
+    if (isinstance(corners, np.ndarray) and corners.dtype == np.float32 and corners.shape == res.shape
+            and corners.flags.c_contiguous and corners.flags.writeable):
+        corners[...] = res           # cv2 reuses a caller-supplied array of exactly the result's size
+        return corners
+    return res.copy()

@@ -27,19 +27,24 @@ def grid_points(width, height, step=30):
     return pts.reshape(-1, 2)
 
 
-def get_flow_lk(img1, img2, points_, device="cuda"):
+def get_flow_lk(img1, img2, points_, device="cuda", rule=batch.FILTER_VIEWER):
     """img1: previous gray, img2: current gray, points_: float32 (N,2) (all numpy, as the reference passes them).
 
-    Returns (flow int32 (M,2), points int32 (M,2)) -- the reference's second and third return values.
+    Returns the reference's 3-tuple ``(frame_layer, flow, points_)`` (pathfinder_viewer.py:144-193, unpacked at
+    :285): frame_layer uint8 (H,W,3), flow int32 (M,2), points int32 (M,2).  ``rule=batch.FILTER_DENSEOF`` applies the
+    development script's mask (DenseOF.py:228) instead of the viewer's.
     """
     height, width = img1.shape
     prev = torch.from_numpy(np.ascontiguousarray(img1)).to(device)[None]
     cur = torch.from_numpy(np.ascontiguousarray(img2)).to(device)[None]
     pts = torch.from_numpy(np.ascontiguousarray(points_, dtype=np.float32)).to(device)
     nxt, _status, _err = batch.pyrlk(cur, prev, pts, **batch.LK_GRID_DEFAULTS)
-    out = batch.pathfinder_filter(pts, nxt, width, height)
+    out = batch.pathfinder_filter(pts, nxt, width, height, mode=rule)
     m = int(out["n_kept"][0])
-    return out["kept_flow"][0, :m].cpu().numpy(), out["kept_pts"][0, :m].cpu().numpy()
+    # frame_layer is the reference's drawing of the kept vectors (cv2.polylines / cv2.circle, :179-191): drawing is
+    # out of scope for the hot path (SURVEY 8f.4), the layer is returned black so that callers can unpack three values
+    frame_layer = np.zeros((height, width, 3), np.uint8)
+    return frame_layer, out["kept_flow"][0, :m].cpu().numpy(), out["kept_pts"][0, :m].cpu().numpy()
 
 
 def draw_sparse_lamps(flow_, points_):

@@ -49,12 +49,46 @@ def sobel3_f32(img, scale):
     return dx, dy
 
 
+SOBEL_TAPS = {3: ([-1, 0, 1], [1, 2, 1]), 5: ([-1, -2, 0, 2, 1], [1, 4, 6, 4, 1]),
+              7: ([-1, -4, -5, 0, 5, 4, 1], [1, 6, 15, 20, 15, 6, 1])}
+
+
+def sobel_f32(img, ksize, scale):
+    """cv2.Sobel(CV_32F, ksize in {3, 5, 7}, scale) as opencv's separable filter computes it (probed bit for bit
+    against cv2 4.13 on widths without a scalar tail).  cv::Sobel scales the SMOOTHING kernel (float32 taps times
+    float32 scale); sepFilter2D then runs a float32 row filter and a symmetric / antisymmetric column filter:
+        Dx: row = derivative taps (integers: exact), column = k[r] * t[y], then fma(t[y+j] + t[y-j], k[r+j], .)
+        Dy: row = scaled smoothing taps, fused multiply-adds left to right; column = (r[y+1] - r[y-1]) * d[r+1],
+            then fma(r[y+j] - r[y-j], d[r+j], .)"""
+    d, sm = SOBEL_TAPS[ksize]
+    r = ksize // 2
+    h, w = img.shape
+    s = img.astype(f32)
+    ys, xs = np.arange(h), np.arange(w)
+    cols = [reflect101(xs + j - r, w) for j in range(ksize)]
+    rows = [reflect101(ys + j - r, h) for j in range(ksize)]
+    k = [f32(f32(v) * f32(scale)) for v in sm]
+    t = np.zeros((h, w), f32)
+    for j in range(ksize):
+        t = t + f32(d[j]) * s[:, cols[j]]
+    dx = t * k[r]
+    for j in range(1, r + 1):
+        dx = _fma(t[rows[r + j]] + t[rows[r - j]], k[r + j], dx)
+    rr = s[:, cols[0]] * k[0]
+    for j in range(1, ksize):
+        rr = _fma(s[:, cols[j]], k[j], rr)
+    dy = (rr[rows[r + 1]] - rr[rows[r - 1]]) * f32(d[r + 1])
+    for j in range(2, r + 1):
+        dy = _fma(rr[rows[r + j]] - rr[rows[r - j]], f32(d[r + j]), dy)
+    return dx, dy
+
+
 def min_eig_map(img, block_size=3, gradient_size=3, harris=False, k=0.04):
     """cornerMinEigenVal / cornerHarris response, float32 (H,W)."""
-    assert gradient_size == 3
+    assert gradient_size in (3, 5, 7)
     h, w = img.shape
     scale = f32(1.0 / ((1 << (gradient_size - 1)) * block_size * 255.0))
-    Dx, Dy = sobel3_f32(img, scale)
+    Dx, Dy = sobel3_f32(img, scale) if gradient_size == 3 else sobel_f32(img, gradient_size, scale)
     cov = np.stack([Dx * Dx, Dx * Dy, Dy * Dy], -1).astype(np.float64)
     r = block_size // 2
     ys, xs = np.arange(h), np.arange(w)
@@ -67,7 +101,8 @@ def min_eig_map(img, block_size=3, gradient_size=3, harris=False, k=0.04):
     o = o.astype(f32)
     if harris:
         a, b, c = o[..., 0], o[..., 1], o[..., 2]
-        return (a * c - b * b - f32(k) * (a + c) * (a + c)).astype(f32)
+        # calcHarris as cv2's SIMD body rounds it (probed bit for bit): float32, k times the SQUARED trace
+        return ((a * c - b * b) - f32(k) * ((a + c) * (a + c))).astype(f32)
     a = o[..., 0] * f32(0.5)
     b = o[..., 1]
     c = o[..., 2] * f32(0.5)

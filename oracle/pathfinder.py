@@ -27,8 +27,10 @@ def grid_points(width, height, step=30):
     return np.array(pts).astype(np.float32).reshape(-1, 2)
 
 
-def vector_filter(next_pts, points_, width, height):
-    """pathfinder_viewer.py:159-178.  Returns (flow int32 (M,2), points int32 (M,2), mask bool (N,), modulus f32 (N,))."""
+def vector_filter(next_pts, points_, width, height, rule="viewer"):
+    """pathfinder_viewer.py:159-178 (rule="viewer") or the development script's variant DenseOF.py:194-242
+    (rule="denseof": the only difference is the mask, :228).
+    Returns (flow int32 (M,2), points int32 (M,2), mask bool (N,), modulus f32 (N,))."""
     half_width = int(width / 2)
     half_height = int(height / 2)
     flow_ = next_pts - points_
@@ -43,7 +45,10 @@ def vector_filter(next_pts, points_, width, height):
     nxt = np.vstack([x + fx, y + fy]).T
     nxt = np.int32(nxt + 0.5)
     pts = np.int32(points_ + 0.5)
-    mask = (np.median(modulus) * 1.0 < modulus) & (modulus < np.percentile(modulus, 99))
+    if rule == "denseof":
+        mask = np.greater(modulus, np.median(modulus) * 1.2)                      # DenseOF.py:228
+    else:
+        mask = (np.median(modulus) * 1.0 < modulus) & (modulus < np.percentile(modulus, 99))
     pts_k, nxt_k = pts[mask], nxt[mask]
     return nxt_k - pts_k, pts_k, mask, modulus
 

@@ -41,7 +41,7 @@ for (h, w) in [(360, 640), (720, 1280), (1080, 1920)]:
     # viewer filter
     nxt, st, err = cv2.calcOpticalFlowPyrLK(fr[1], fr[0], pts, None, **ref.LK_GRID_PARAMS)
     flow_o, pts_o, mask_o, mod_o = opf.vector_filter(nxt, pts, w, h)
-    flow_m, pts_m = pf.get_flow_lk(fr[0], fr[1], pts)
+    _layer, flow_m, pts_m = pf.get_flow_lk(fr[0], fr[1], pts)
     out = batch.pathfinder_filter(torch.from_numpy(pts).cuda(), torch.from_numpy(nxt).cuda()[None], w, h)
     mask_same = (out["mask"][0].cpu().numpy().astype(bool) == mask_o).mean()
     k = int(out["n_kept"][0])

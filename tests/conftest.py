@@ -29,6 +29,17 @@ def synth_small():
     return np.load(os.path.join(GOLDEN, "synth_small.npz"))
 
 
+@pytest.fixture(scope="session")
+def ref_funcs():
+    """Outputs of the reference's OWN functions (cut out of its scripts with ast, tests/golden/make_golden_ref.py)."""
+    return np.load(os.path.join(GOLDEN, "reference_funcs.npz"))
+
+
+@pytest.fixture(scope="session")
+def extras():
+    return np.load(os.path.join(GOLDEN, "extras.npz"))
+
+
 def epe(a, b):
     d = np.sqrt(((a.astype(np.float64) - b.astype(np.float64)) ** 2).sum(-1))
     return float(d.mean()), float(d.max())

@@ -160,3 +160,81 @@ def test_hsv2bgr_restatement_exhaustive_and_draw_hsv_vs_reference_formula():
         body = wid - wid % 32
         assert not diff[:, :body].any(), (hgt, wid)
         assert diff.max() <= 1
+
+
+# ------------------------------------------------------------------ the reference's own functions (ast-extracted)
+CASES = [("full", 1920, 1080)] + [(f"crop{i}", 640, 360) for i in range(4)]
+
+
+def _lk_next(name, crops, full1080):
+    return full1080["lk_next"] if name == "full" else crops[f"lk_next_{name[-1]}"]
+
+
+@pytest.mark.parametrize("name,w,h", CASES)
+def test_vector_filter_and_lamps_equal_the_reference_functions(ref_funcs, crops, full1080, name, w, h):
+    """oracle.pathfinder is pinned to what pathfinder_viewer.py's get_flow_lk / draw_sparse_lamps themselves return
+    (tests/golden/make_golden_ref.py runs the unmodified function bodies)."""
+    pts = opf.grid_points(w, h, 30)
+    flow, kept, mask, _ = opf.vector_filter(_lk_next(name, crops, full1080), pts, w, h)
+    assert np.array_equal(flow, ref_funcs[f"{name}_kept_flow"])
+    assert np.array_equal(kept, ref_funcs[f"{name}_kept_pts"])
+    assert np.array_equal(opf.danger_intensity(flow, kept), ref_funcs[f"{name}_danger_v"])
+
+
+@pytest.mark.parametrize("name,w,h", CASES)
+def test_denseof_filter_rule_equals_the_reference_function(ref_funcs, crops, full1080, name, w, h):
+    pts = opf.grid_points(w, h, 30)
+    flow, kept, _, _ = opf.vector_filter(_lk_next(name, crops, full1080), pts, w, h, rule="denseof")
+    assert np.array_equal(flow, ref_funcs[f"{name}_denseof_kept_flow"])
+    assert np.array_equal(kept, ref_funcs[f"{name}_denseof_kept_pts"])
+
+
+def test_draw_hsv_equals_the_reference_function(ref_funcs, full1080):
+    got, _ = opf.draw_hsv(np.ascontiguousarray(full1080["flow_s8"]))
+    want = ref_funcs["hsv_of_flow_s8"]
+    w = want.shape[1]
+    body = slice(0, w - w % 32)            # cv2's scalar tail columns round differently (see hsv2bgr_u8)
+    assert (got[:, body] != want[:, body]).any(-1).mean() <= 1e-4
+    assert np.abs(got.astype(int) - want.astype(int)).max() <= 9
+
+
+# ------------------------------------------------------------------ options the reference leaves at their defaults
+@pytest.mark.parametrize("i", range(4))
+@pytest.mark.parametrize("tag,kw", [
+    ("harris", dict(harris=True, k=0.04)),
+    ("harris_dense", dict(max_corners=500, quality=0.01, min_dist=5, block_size=3, harris=True, k=0.06)),
+    ("grad5", dict(gradient_size=5)), ("grad7", dict(gradient_size=7)),
+    ("grad5_harris", dict(gradient_size=5, harris=True, k=0.04))])
+def test_gftt_harris_and_gradient_sizes(crops, extras, i, tag, kw):
+    p = dict(max_corners=20, quality=0.3, min_dist=10, block_size=7)
+    p.update(kw)
+    got = ogf.good_features_to_track(crops[f"gray0_{i}"], p.pop("max_corners"), p.pop("quality"), p.pop("min_dist"),
+                                     None, **p)
+    want = extras[f"gftt_{tag}_{i}"]
+    if len(want) == 0:
+        assert got is None
+    else:
+        assert got is not None and np.array_equal(got, want), (tag, i)
+
+
+@pytest.mark.parametrize("i", [0, 3])
+def test_lk_min_eigenvals_flag(crops, extras, i):
+    g0, g1 = crops[f"gray0_{i}"], crops[f"gray1_{i}"]
+    pts = opf.grid_points(640, 360, 30)
+    for tag, win, thr in (("lk_mineig", (45, 45), 1e-4), ("lk_mineig15", (15, 15), 1e-3)):
+        nxt, st, err = olk.pyrlk(g1, g0, pts, None, win=win, max_level=2, criteria=(3, 10, 0.03), flags=8,
+                                 min_eig_threshold=thr)
+        ws, we = extras[f"{tag}_status_{i}"], extras[f"{tag}_err_{i}"]
+        assert (st == ws).mean() >= 0.995
+        ok = (st.ravel() == 1) & (ws.ravel() == 1)
+        close = np.abs(nxt - extras[f"{tag}_next_{i}"]).max(-1) < 0.05     # a min-eig at the threshold of one pyramid
+        assert (~close[ok]).sum() <= max(1, int(0.005 * ok.sum()))         # level can flip that level's update
+        assert np.allclose(err.ravel()[ok & close], we.ravel()[ok & close], rtol=1e-3, atol=1e-6)
+
+
+def test_farneback_zero_iterations(synth_small, extras):
+    f0, f1 = synth_small["f0"], synth_small["f1"]
+    assert np.array_equal(ofb.farneback(f0, f1, None, 0.5, 3, 15, 0, 5, 1.2, 0), extras["fb_iter0"])
+    got = ofb.farneback(f0, f1, extras["fb_iter0_init_in"].copy(), 0.5, 3, 15, 0, 5, 1.2, 4)
+    mean, mx = epe(got, extras["fb_iter0_init"])
+    assert mean < 1e-6 and mx < 1e-4, (mean, mx)
