@@ -154,6 +154,126 @@ def run_reference(args):
     return 0
 
 
+def decode_png(buf):
+    """PNG bytes (numpy uint8) -> uint8 (H,W).  Fixture decoding only."""
+    from io import BytesIO
+    import numpy as np
+    from PIL import Image
+    return np.array(Image.open(BytesIO(buf.tobytes())))
+
+
+def pcie_ceiling(dev, h2d_bytes, d2h_bytes, world, reps=3):
+    """Bare pinned copies of one end-to-end step's bytes (H2D of the frames, D2H of the flow fields, on two streams,
+    every rank at once): the rate no implementation that returns float32 flow fields to the host can exceed."""
+    import torch
+    import torch.distributed as tdist
+    from hackathonopticalflow_b200 import dist as b2dist
+    hin = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    hout = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    din = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
+    dout = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    best = None
+    for i in range(reps + 1):
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            din.copy_(hin, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hout.copy_(dout, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = b2dist.max_over_ranks(time.perf_counter() - t0, dev)
+        if i > 0:
+            best = dt if best is None else min(best, dt)
+    return best
+
+
+def real_1080p_record(batch, dev, pairs):
+    """The committed real 1080p pair (tests/golden/real_1080p.npz, footage from the reference's own clips) replicated to
+    `pairs` pairs (frames a b a b ...: flows a->b and b->a alternate): throughput on real content (large motions,
+    discontinuities) and the error of pair 0 against the committed cv2 result."""
+    import numpy as np
+    import torch
+    from hackathonopticalflow_b200 import _lib
+    path = os.path.join(ROOT, "tests", "golden", "real_1080p.npz")
+    if not os.path.exists(path):
+        return {"unavailable": "tests/golden/real_1080p.npz missing"}
+    z = np.load(path)
+    a, b = decode_png(z["png0"]), decode_png(z["png1"])
+    frames = torch.from_numpy(np.ascontiguousarray(np.stack([a, b] * (pairs // 2 + 1))[:pairs + 1])).to(dev)
+    eng = batch.FarnebackEngine(H, W, chunk_pairs=pairs, device=dev, **PARAMS)
+    flow = torch.empty((pairs, H, W, 2), dtype=torch.float32, device=dev)
+    for _ in range(2):
+        eng.flow_sequence(frames, flow)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 5
+    e0.record()
+    for _ in range(n):
+        eng.flow_sequence(frames, flow)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    got = flow[0, ::8, ::8].cpu().numpy().astype(np.float64)
+    d = np.sqrt(((got - z["flow_s8"].astype(np.float64)) ** 2).sum(-1))
+    mag = np.sqrt((z["flow_s8"].astype(np.float64) ** 2).sum(-1))
+    del eng, flow, frames
+    return {"pairs_per_s": pairs / (ms * 1e-3), "ms_per_step": ms, "pairs_per_step": pairs,
+            "epe_mean_vs_cv2": float(d.mean()), "epe_max_vs_cv2": float(d.max()),
+            "flow_mean_px": float(mag.mean()), "flow_max_px": float(mag.max()),
+            "source": "tests/golden/real_1080p.npz (reference clip, frames 120-121), cv2 flow sampled every 8th px"}
+
+
+def pipeline_4k_record(rank, world, dev, pairs=8, steps=3):
+    """BASELINE configs[4]: the full pathfinder per-frame pipeline on synthetic 3840x2160 batches, every rank its own
+    shard, per-pair stats gathered to rank 0 (outside the timed headline)."""
+    import numpy as np
+    import torch
+    import torch.distributed as tdist
+    from hackathonopticalflow_b200 import _lib, dist as b2dist, pathfinder, synth
+    h, w = 2160, 3840
+    base = synth.sequence(h, w, 3, seed=2000 + rank, gray=False)
+    idx = ([0, 1, 2, 1] * (pairs // 4 + 1))[:pairs + 1]
+    bgr = torch.from_numpy(np.ascontiguousarray(base[idx])).to(dev)
+    pipe = pathfinder.PathfinderPipeline(h, w, dense=True, chunk_pairs=pairs, device=dev)
+    n_frames_global = world * pairs + 1
+
+    def step():
+        out = pipe.run(bgr)
+        st = torch.cat([out["flow_stats"][:, :4], out["stats"][:, 4:]], 1).contiguous()
+        return out, b2dist.gather_stats(st, n_frames_global, rank, world)
+
+    for _ in range(2):
+        out, st = step()
+    if world > 1:
+        tdist.barrier()
+    torch.cuda.synchronize()
+    _lib.profile(True, reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out, st = step()
+    e1.record()
+    if world > 1:
+        tdist.barrier()
+    torch.cuda.synchronize()
+    ms = b2dist.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+    prof = _lib.profile()
+    _lib.profile(False, reset=True)
+    rec = {"pairs_per_s": world * pairs / (ms * 1e-3), "ms_per_step": ms, "pairs_per_gpu_per_step": pairs,
+           "n_gpus": world, "height": h, "width": w, "grid_points": int(pipe.points.shape[0]),
+           "n_kept_first_pair": int(out["n_kept"][0]), "lk_tracked_fraction": float(out["status"].float().mean()),
+           "stats_rows_on_rank0": int(st.shape[0]) if st is not None else None,
+           "kernel_ms_per_step": {k: round(v["ms"] / steps, 3) for k, v in prof.items()},
+           "workload": "configs[4]: BGR -> gray -> 9216-point grid LK 45x45 (current -> previous) -> vector filter + "
+                       "danger points + dense Farneback + stats, synthetic 3840x2160"}
+    del pipe, bgr, out
+    torch.cuda.empty_cache()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,6 +284,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=CHUNK_PAIRS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the sub-records measured outside the timed headline (real_1080p, pipeline_4k, xrank_check)")
     ap.add_argument("--separate-stats", action="store_true",
                     help="A/B only: per-pair statistics by a second pass over the flow fields (b2of_flow_stats_dev)")
     args = ap.parse_args()
@@ -243,6 +365,28 @@ def main():
     torch.cuda.synchronize()
     e2e_ms = b2dist.max_over_ranks((time.perf_counter() - te0) * 1e3, dev)
     e2e_value = world * E * e2e_steps / (e2e_ms * 1e-3) if e2e_steps else None
+    ceiling_s = None if args.no_e2e else pcie_ceiling(dev, (E + 1) * H * W, E * H * W * 8, world)
+
+    # ---- outside the timed headline -------------------------------------------------------------------------------
+    xrank = None
+    if world > 1 and not args.no_extras:
+        # rank 0 regenerates the LAST rank's shard (seeds are 1000 + rank), runs the same step on its own GPU and
+        # compares its statistics rows bit for bit with the rows that arrived through the NCCL gather
+        if rank == 0:
+            other = torch.from_numpy(synthetic_frames(P + 1, 1000 + world - 1)).to(dev)
+            mine = torch.empty((P, 8), dtype=torch.float32, device=dev)
+            eng.flow_sequence(other, flow, stats=mine)
+            got = stats[(world - 1) * P:world * P]
+            xrank = "ok" if torch.equal(mine, got) else "MISMATCH: %d of %d rows differ" % (
+                int((mine != got).any(1).sum()), P)
+            del other
+    extras = {}
+    if not args.no_extras:
+        del flow
+        torch.cuda.empty_cache()
+        if rank == 0:
+            extras["real_1080p"] = real_1080p_record(batch, dev, P)
+        extras["pipeline_4k"] = pipeline_4k_record(rank, world, dev)
 
     if rank != 0:
         if world > 1:
@@ -271,12 +415,17 @@ def main():
                    "frames_per_gpu": P + 1, "chunk_pairs": args.chunk, "input_form": "consecutive frames "
                    "(per-frame work reused, B_stream accounting)", "sharding": f"frames x{world} contiguous + 1-frame halo",
                    "l2": "inputs (135 MB/GPU) and intermediates (13 GB/GPU) exceed the 126 MB L2; no explicit flush",
-                   "step_includes": "flow_sequence + flow_stats + gather of per-pair stats to rank 0"},
+                   "step_includes": "flow_sequence with the per-pair statistics reduced inside its last kernel + gather "
+                                    "of the stats rows to rank 0"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": (E + 1) * H * W,
                 "d2h_bytes_per_step": E * H * W * 8, "pairs_per_step": E, "steps": e2e_steps,
                 "api": "cv2compat.calcOpticalFlowFarnebackSequence -> b2of_farneback_sequence_host (pinned host buffers; "
-                       "H2D of the frames and D2H of every flow field inside the timed region)"},
+                       "H2D of the frames and D2H of every flow field inside the timed region)",
+                "pcie_ceiling_pairs_per_s": world * E / ceiling_s if ceiling_s else None,
+                "pcie_ceiling_note": "bare pinned H2D + D2H of one step's bytes on two streams, every rank at once "
+                                     "(max over ranks): the ranks of a node share the host's PCIe uplinks, so this "
+                                     "ceiling, not NCCL, is what the host-buffer number scales with"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "fb_iter_ws @ finest level (warp-specialised fused UpdateMatrices + 15x15 box + 2x2 solve)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
@@ -300,6 +449,9 @@ def main():
         line["cpu_baseline"] = None
     if stats is not None:
         line["stats_rows_on_rank0"] = int(stats.shape[0])
+    if xrank is not None:
+        line["xrank_check"] = xrank
+    line.update(extras)
     print(json.dumps(line))
     if world > 1:
         tdist.barrier()
