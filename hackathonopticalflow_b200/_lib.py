@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 # B2OF_LIB: developer override used by scripts/ab_variants.py to A/B alternative builds of the same sources
 LIB_PATH = os.environ.get("B2OF_LIB") or os.path.join(CSRC, "libb2of.so")
-SOURCES = ["api.cu", "gray_pyr.cu", "farneback.cu", "pyrlk.cu", "gftt.cu", "pathfinder.cu"]
+SOURCES = ["api.cu", "gray_pyr.cu", "farneback.cu", "pyrlk.cu", "gftt.cu", "pathfinder.cu", "overlay.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -73,7 +73,10 @@ SIGNATURES = {
     "b2of_gftt_workspace_bytes": (_sz, [_i, _i, _PG, _i]),
     "b2of_gftt_dev": (_i, [_vp, _vp, _sz, _sz, _i, _i, _i, _PG, _vp, _i, _vp, _vp, _sz, _vp]),
     "b2of_gftt_host": (_i, [_vp, _vp, _sz, _sz, _i, _i, _PG, _vp, _i, _vp]),
-    "b2of_pathfinder_filter_dev": (_i, [_vp, _sz, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b2of_pathfinder_filter_dev": (_i, [_vp, _sz, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                        _vp]),
+    "b2of_overlay_vectors_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "b2of_overlay_lamps_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "b2of_flow_sample_dev": (_i, [_vp, _i, _i, _i, _vp, _sz, _i, _vp, _vp]),
     "b2of_flow_hsv_dev": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "b2of_flow_stats_dev": (_i, [_vp, _i, _i, _i, _vp, _vp]),

@@ -200,12 +200,14 @@ def gftt(img, mask=None, maxCorners=20, qualityLevel=0.3, minDistance=10, blockS
 FILTER_VIEWER, FILTER_DENSEOF = 0, 1
 
 
-def pathfinder_filter(pts, next_pts, width, height, mode=FILTER_VIEWER):
+def pathfinder_filter(pts, next_pts, width, height, mode=FILTER_VIEWER, all_points=False):
     """The viewer's vector filter + danger intensity (pathfinder_viewer.py:159-178, :210-217) per frame.
 
     pts float32 (N,2) shared grid or (B,N,2); next_pts float32 (B,N,2).
     mode: FILTER_VIEWER keeps median < m < p99 (pathfinder_viewer.py:171); FILTER_DENSEOF keeps m > 1.2 * median
     (the development script's rule, DenseOF.py:228).
+    all_points=True adds all_pts / all_next int32 (B,N,2): every point and its normalised end point as the reference
+    rounds them (what :func:`overlay_vectors` draws).
     Returns dict(kept_pts int32 (B,N,2), kept_flow int32 (B,N,2), danger_v uint8 (B,N), mask uint8 (B,N),
                  n_kept int32 (B), stats float32 (B,8)); rows [0, n_kept[b]) of the kept_* arrays are valid.
     """
@@ -222,12 +224,38 @@ def pathfinder_filter(pts, next_pts, width, height, mode=FILTER_VIEWER):
                mask=torch.zeros((b, n), dtype=torch.uint8, device=dev),
                n_kept=torch.zeros((b,), dtype=torch.int32, device=dev),
                stats=torch.zeros((b, 8), dtype=torch.float32, device=dev))
+    if all_points:
+        out["all_pts"] = torch.empty((b, n, 2), dtype=torch.int32, device=dev)
+        out["all_next"] = torch.empty((b, n, 2), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().b2of_pathfinder_filter_dev(_p(pts), 0 if shared else n, _p(next_pts), n, b, int(width),
                                                          int(height), int(mode), _p(out["kept_pts"]), _p(out["kept_flow"]),
                                                          _p(out["danger_v"]), _p(out["mask"]), _p(out["n_kept"]),
-                                                         _p(out["stats"]), _stream()))
+                                                         _p(out["stats"]), _p(out.get("all_pts")),
+                                                         _p(out.get("all_next")), _stream()))
     return out
+
+
+def overlay_vectors(filt, height, width, draw_bad=True):
+    """The reference's vector layer (pathfinder_viewer.py:179-191) from a :func:`pathfinder_filter` result computed with
+    ``all_points=True``: uint8 (B,H,W,3) BGR, pixel for pixel what cv2.polylines / cv2.circle draw."""
+    b, n, _ = filt["all_pts"].shape
+    layer = torch.empty((b, int(height), int(width), 3), dtype=torch.uint8, device=filt["all_pts"].device)
+    with torch.cuda.device(layer.device):
+        _lib.check(_lib.lib().b2of_overlay_vectors_dev(_p(filt["all_pts"]), _p(filt["all_next"]), _p(filt["mask"]), n, b,
+                                                       int(height), int(width), int(bool(draw_bad)), _p(layer),
+                                                       _stream()))
+    return layer
+
+
+def overlay_lamps(filt, height, width):
+    """The reference's danger-lamp layer (draw_sparse_lamps, pathfinder_viewer.py:196-223): uint8 (B,H,W,3) BGR."""
+    b, n, _ = filt["kept_pts"].shape
+    bgr = torch.empty((b, int(height), int(width), 3), dtype=torch.uint8, device=filt["kept_pts"].device)
+    with torch.cuda.device(bgr.device):
+        _lib.check(_lib.lib().b2of_overlay_lamps_dev(_p(filt["kept_pts"]), _p(filt["danger_v"]), _p(filt["n_kept"]), n, b,
+                                                     int(height), int(width), _p(bgr), _stream()))
+    return bgr
 
 
 def flow_sample(flow, pts):

@@ -62,7 +62,9 @@ size_t gftt_workspace_bytes(int, int, const b2of_gftt_params*, int);
 int gftt_dev(const uint8_t*, const uint8_t*, size_t, size_t, int, int, int, const b2of_gftt_params*, float*, int, int*,
              void*, size_t, cudaStream_t);
 int pathfinder_filter_dev(const float*, size_t, const float*, int, int, int, int, int, int32_t*, int32_t*, uint8_t*,
-                          uint8_t*, int32_t*, float*, cudaStream_t);
+                          uint8_t*, int32_t*, float*, int32_t*, int32_t*, cudaStream_t);
+int overlay_vectors_dev(const int32_t*, const int32_t*, const uint8_t*, int, int, int, int, int, uint8_t*, cudaStream_t);
+int overlay_lamps_dev(const int32_t*, const uint8_t*, const int32_t*, int, int, int, int, uint8_t*, cudaStream_t);
 int flow_stats_dev(const float*, int, int, int, float*, cudaStream_t);
 int flow_sample_dev(const float*, int, int, int, const float*, size_t, int, float*, cudaStream_t);
 int flow_hsv_dev(const float*, int, int, int, uint8_t*, cudaStream_t);
@@ -489,9 +491,21 @@ int b2of_gftt_host(const uint8_t* img, const uint8_t* mask, size_t step, size_t 
 // ---- K12 ----
 int b2of_pathfinder_filter_dev(const float* pts, size_t pts_batch_stride, const float* next_pts, int n_pts, int batch,
                                int width, int height, int mode, int32_t* kept_pts, int32_t* kept_flow,
-                               uint8_t* danger_v, uint8_t* mask, int32_t* n_kept, float* stats, void* stream) {
+                               uint8_t* danger_v, uint8_t* mask, int32_t* n_kept, float* stats, int32_t* all_pts,
+                               int32_t* all_next, void* stream) {
   return pathfinder_filter_dev(pts, pts_batch_stride, next_pts, n_pts, batch, width, height, mode, kept_pts, kept_flow,
-                               danger_v, mask, n_kept, stats, (cudaStream_t)stream);
+                               danger_v, mask, n_kept, stats, all_pts, all_next, (cudaStream_t)stream);
+}
+
+int b2of_overlay_vectors_dev(const int32_t* all_pts, const int32_t* all_next, const uint8_t* mask, int n_pts, int batch,
+                             int rows, int cols, int draw_bad, uint8_t* layer_bgr, void* stream) {
+  return overlay_vectors_dev(all_pts, all_next, mask, n_pts, batch, rows, cols, draw_bad, layer_bgr,
+                             (cudaStream_t)stream);
+}
+
+int b2of_overlay_lamps_dev(const int32_t* kept_pts, const uint8_t* danger_v, const int32_t* n_kept, int n_pts, int batch,
+                           int rows, int cols, uint8_t* bgr, void* stream) {
+  return overlay_lamps_dev(kept_pts, danger_v, n_kept, n_pts, batch, rows, cols, bgr, (cudaStream_t)stream);
 }
 
 int b2of_flow_sample_dev(const float* flow, int n_pairs, int rows, int cols, const float* pts, size_t pts_batch_stride,

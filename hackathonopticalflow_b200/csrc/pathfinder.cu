@@ -74,7 +74,9 @@ __global__ void __launch_bounds__(PF_THREADS) pathfinder_filter(const float* __r
                                                                  uint8_t* __restrict__ danger_v,
                                                                  uint8_t* __restrict__ mask_out,
                                                                  int32_t* __restrict__ n_kept,
-                                                                 float* __restrict__ stats, int np2, int mode) {
+                                                                 float* __restrict__ stats, int np2, int mode,
+                                                                 int32_t* __restrict__ all_pts,
+                                                                 int32_t* __restrict__ all_next) {
   extern __shared__ float s_key[];  // the n moduli
   __shared__ unsigned int s_hist[256];
   __shared__ unsigned int s_sel;
@@ -142,6 +144,11 @@ __global__ void __launch_bounds__(PF_THREADS) pathfinder_filter(const float* __r
       // mode 1: the development script's  m > 1.2 * median  (DenseOF.py:228; float32 product, as numpy 2 computes it)
       keep = mode == 1 ? m2 > __fmul_rn(med, 1.2f) : (med < m2) && (m2 < p99);
       mask_out[(size_t)b * n + i] = keep ? 1 : 0;
+      if (all_pts) {                      // every point as the reference rounds it (:169-170): the overlay's input
+        const size_t oa = ((size_t)b * n + i) * 2;
+        all_pts[oa] = px; all_pts[oa + 1] = py;
+        all_next[oa] = qx; all_next[oa + 1] = qy;
+      }
     }
     unsigned int ballot = __ballot_sync(0xffffffffu, keep);
     int lane = t & 31, wid = t >> 5;
@@ -192,10 +199,11 @@ __global__ void __launch_bounds__(PF_THREADS) pathfinder_filter(const float* __r
 
 int pathfinder_filter_dev(const float* pts, size_t pts_bstride, const float* next_pts, int n_pts, int batch, int width,
                           int height, int mode, int32_t* kept_pts, int32_t* kept_flow, uint8_t* danger_v, uint8_t* mask,
-                          int32_t* n_kept, float* stats, cudaStream_t st) {
+                          int32_t* n_kept, float* stats, int32_t* all_pts, int32_t* all_next, cudaStream_t st) {
   const char* fn = "pathfinder_filter";
   B2OF_ASSERT(n_pts >= 1 && batch >= 0 && width > 0 && height > 0, fn);
   B2OF_ASSERT(mode == B2OF_FILTER_VIEWER || mode == B2OF_FILTER_DENSEOF, fn);
+  B2OF_ASSERT((all_pts == nullptr) == (all_next == nullptr), fn);
   B2OF_ASSERT(pts && next_pts && kept_pts && kept_flow && danger_v && mask && n_kept && stats, fn);
   if (n_pts > PF_MAX_PTS) return fail(B2OF_E_UNSUPPORTED, "more than %d points per frame", PF_MAX_PTS);
   if (batch == 0) return B2OF_OK;
@@ -206,7 +214,8 @@ int pathfinder_filter_dev(const float* pts, size_t pts_bstride, const float* nex
   if (smem > 48 * 1024 && max_set.raise(smem))
     B2OF_CUDA(cudaFuncSetAttribute(pathfinder_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   pathfinder_filter<<<batch, PF_THREADS, smem, st>>>(pts, pts_bstride, next_pts, n_pts, width, height, kept_pts,
-                                                     kept_flow, danger_v, mask, n_kept, stats, np2, mode);
+                                                     kept_flow, danger_v, mask, n_kept, stats, np2, mode,
+                                                     all_pts, all_next);
   B2OF_LAUNCH_CHECK();
   return B2OF_OK;
 }

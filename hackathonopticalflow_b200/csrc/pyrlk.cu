@@ -4,8 +4,12 @@
 // oracle/pyrlk.py): u8 pyrDown chain, int16 Scharr derivatives, 14-bit fixed-point bilinear patches, float32
 // 2x2 normal equations, <= maxCount Newton steps.
 //
-// One warp per feature, all pyramid levels inside one launch; the template patch (Iw, Ixw, Iyw as int16)
-// lives in shared memory, window sums are exact integers reduced with warp shuffles.
+// LK_SPLIT warps per feature (each owns a share of the window's rows, of the template patch and of every window sum),
+// all pyramid levels inside one launch; the template patch (Iw, Ixw, Iyw as int16) lives in shared memory, window sums
+// are exact 64-bit integers reduced with warp shuffles (and, for LK_SPLIT > 1, one shared-memory exchange between the
+// feature's warps), so the result does not depend on the split.  Shipped: one warp per feature.  Two warps per feature
+// -- twice the resident warps on the same 12 KB patches -- was measured 5-9 % SLOWER (profiles/README.md): half
+// windows of 22 rows leave the four-rows-per-step walk less to overlap and every Newton step pays a named barrier.
 #include <math.h>
 #include <string.h>
 
@@ -16,7 +20,12 @@ namespace b2of {
 int pyrdown_dev(const uint8_t*, int, int, size_t, size_t, uint8_t*, size_t, size_t, int, cudaStream_t);
 
 constexpr int LK_MAX_LEVELS = 12;
-constexpr int LK_WARPS = 4;
+constexpr int LK_WARPS = 4;          // warps per CTA
+#ifndef B2OF_LK_SPLIT
+#define B2OF_LK_SPLIT 1
+#endif
+constexpr int LK_SPLIT = B2OF_LK_SPLIT;   // warps per feature
+constexpr int LK_FEATS = LK_WARPS / LK_SPLIT;   // features per CTA
 
 struct LkLevels {
   int n;  // number of levels (effective maxLevel + 1)
@@ -131,10 +140,10 @@ __host__ __device__ inline size_t lk_patch_bytes(int ww, int wh) {
 // aligned pairs.  Window sums are exact 64-bit integers, so the result does not depend on the split.
 struct LkStrips {
   int S, G, RG;
-  __device__ __forceinline__ LkStrips(int ww, int wh) {
+  __device__ __forceinline__ LkStrips(int ww, int nrows) {   // nrows = rows of this warp's share of the window
     S = lk_wwp(ww) >> 1;
     G = S <= 16 ? 32 / S : 1;
-    RG = (wh + G - 1) / G;
+    RG = (nrows + G - 1) / G;
   }
 };
 
@@ -144,15 +153,15 @@ struct LkStrips {
 template <bool ABS, bool INSIDE>
 __device__ __forceinline__ void lk_window_strips(const uint8_t* __restrict__ J, size_t step, int w, int h, int ix,
                                                  int iy, int w00, int w01, int w10, int w11, const short* sI,
-                                                 const short2* sD, int ww, int wh, int lane, long long& s1,
+                                                 const short2* sD, int ww, int ya, int yb, int lane, long long& s1,
                                                  long long& s2) {
   const int wwp = lk_wwp(ww);
-  const LkStrips st(ww, wh);
+  const LkStrips st(ww, yb - ya);
   for (int u = lane; u < st.S * st.G; u += 32) {
     const int g = u / st.S, sx = u - g * st.S;
     const int x0 = 2 * sx;
     const bool two = x0 + 1 < ww;
-    const int y0 = g * st.RG, y1 = min(wh, y0 + st.RG);
+    const int y0 = ya + g * st.RG, y1 = min(yb, y0 + st.RG);
     int c0 = ix + x0, c1 = c0 + 1, c2 = c0 + 2;
     if (!INSIDE) { c0 = reflect101(c0, w); c1 = reflect101(c1, w); c2 = reflect101(c2, w); }
     auto rowp = [&](int y) { return J + (size_t)(INSIDE ? iy + y : reflect101(iy + y, h)) * step; };
@@ -207,12 +216,12 @@ __device__ __forceinline__ void lk_window_strips(const uint8_t* __restrict__ J, 
 template <bool ABS>
 __device__ __forceinline__ void lk_window_pass(const uint8_t* __restrict__ J, size_t step, int w, int h, int ix,
                                                int iy, int w00, int w01, int w10, int w11, const short* sI,
-                                               const short2* sD, int ww, int wh, int lane, long long& o1,
-                                               long long& o2) {
+                                               const short2* sD, int ww, int wh, int ya, int yb, int lane,
+                                               long long& o1, long long& o2) {
   const bool inside = ix >= 0 && iy >= 0 && ix + ww < w && iy + wh < h;
   long long s1 = 0, s2 = 0;
-  if (inside) lk_window_strips<ABS, true>(J, step, w, h, ix, iy, w00, w01, w10, w11, sI, sD, ww, wh, lane, s1, s2);
-  else lk_window_strips<ABS, false>(J, step, w, h, ix, iy, w00, w01, w10, w11, sI, sD, ww, wh, lane, s1, s2);
+  if (inside) lk_window_strips<ABS, true>(J, step, w, h, ix, iy, w00, w01, w10, w11, sI, sD, ww, ya, yb, lane, s1, s2);
+  else lk_window_strips<ABS, false>(J, step, w, h, ix, iy, w00, w01, w10, w11, sI, sD, ww, ya, yb, lane, s1, s2);
   o1 = warp_sum_ll(s1);
   o2 = ABS ? 0 : warp_sum_ll(s2);
 }
@@ -222,15 +231,15 @@ __device__ __forceinline__ void lk_window_pass(const uint8_t* __restrict__ J, si
 template <bool INSIDE>
 __device__ __forceinline__ void lk_patch_strips(const uint8_t* __restrict__ I, const short2* __restrict__ D, size_t step,
                                                 int W, int H, int ipx, int ipy, int w00, int w01, int w10, int w11,
-                                                short* sI, short2* sD, int ww, int wh, int lane, long long& sA11,
-                                                long long& sA12, long long& sA22) {
+                                                short* sI, short2* sD, int ww, int ya, int yb, int lane,
+                                                long long& sA11, long long& sA12, long long& sA22) {
   const int wwp = lk_wwp(ww);
-  const LkStrips st(ww, wh);
+  const LkStrips st(ww, yb - ya);
   for (int u = lane; u < st.S * st.G; u += 32) {
     const int g = u / st.S, sx = u - g * st.S;
     const int x0 = 2 * sx;
     const bool two = x0 + 1 < ww;
-    const int y0 = g * st.RG, y1 = min(wh, y0 + st.RG);
+    const int y0 = ya + g * st.RG, y1 = min(yb, y0 + st.RG);
     const int a0 = ipx + x0;                     // unreflected columns a0, a0 + 1, a0 + 2
     int c0 = a0, c1 = a0 + 1, c2 = a0 + 2;
     bool v0 = true, v1 = true, v2 = two;         // derivative columns inside the frame
@@ -282,13 +291,37 @@ __device__ __forceinline__ void lk_patch_strips(const uint8_t* __restrict__ I, c
 __global__ void __launch_bounds__(LK_WARPS * 32) lk_track(LkArgs a) {
   extern __shared__ __align__(16) unsigned char lk_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pt = blockIdx.x * LK_WARPS + warp;
+  const int feat = warp / LK_SPLIT, half = warp - feat * LK_SPLIT;
+  const int pt = blockIdx.x * LK_FEATS + feat;
   const int b = blockIdx.y;
-  if (pt >= a.n_pts) return;
+  if (pt >= a.n_pts) return;                                       // both warps of a feature leave together
   const int ww = a.ww, wh = a.wh;
   const int wwp = lk_wwp(ww);
   const size_t per_warp = lk_patch_bytes(ww, wh);
-  short* sI = (short*)(lk_smem + warp * per_warp);                 // [wh][wwp] int16
+  // this warp's rows of the window (and of the patch: a warp only ever reads the patch rows it wrote itself)
+  const int ya = (wh * half) / LK_SPLIT, yb = (wh * (half + 1)) / LK_SPLIT;
+  // exchange of the partial window sums between the feature's warps: [parity][warp of the feature][3]
+  long long* xch = (long long*)(lk_smem + LK_FEATS * per_warp) + feat * (2 * LK_SPLIT * 3);
+  int xpar = 0;
+  auto feature_sum = [&](long long& v0, long long& v1, long long& v2, int n) {
+    if (LK_SPLIT == 1) return;
+    long long* slot = xch + xpar * (LK_SPLIT * 3);
+    if (lane == 0) {
+      slot[half * 3] = v0;
+      if (n > 1) slot[half * 3 + 1] = v1;
+      if (n > 2) slot[half * 3 + 2] = v2;
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + feat), "n"(LK_SPLIT * 32) : "memory");
+    v0 = 0; v1 = 0; v2 = 0;
+#pragma unroll
+    for (int k = 0; k < LK_SPLIT; ++k) {
+      v0 += slot[k * 3];
+      if (n > 1) v1 += slot[k * 3 + 1];
+      if (n > 2) v2 += slot[k * 3 + 2];
+    }
+    xpar ^= 1;        // the next exchange uses the other slot: this one is re-written only after another barrier
+  };
+  short* sI = (short*)(lk_smem + feat * per_warp);                 // [wh][wwp] int16
   short2* sD = (short2*)(sI + (((size_t)wwp * wh + 3) & ~(size_t)3));   // [wh][wwp] (Ixw, Iyw), 8-byte aligned
   const uint8_t* PI = a.pyr_i + (size_t)b * a.L.pyr_bytes;
   const uint8_t* PJ = a.pyr_j + (size_t)b * a.L.pyr_bytes;
@@ -333,10 +366,11 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_track(LkArgs a) {
     {
       const bool inside = ipx >= 0 && ipy >= 0 && ipx + ww < W && ipy + wh < H;
       __syncwarp();
-      if (inside) lk_patch_strips<true>(I, D, step, W, H, ipx, ipy, w00, w01, w10, w11, sI, sD, ww, wh, lane, sA11, sA12, sA22);
-      else lk_patch_strips<false>(I, D, step, W, H, ipx, ipy, w00, w01, w10, w11, sI, sD, ww, wh, lane, sA11, sA12, sA22);
+      if (inside) lk_patch_strips<true>(I, D, step, W, H, ipx, ipy, w00, w01, w10, w11, sI, sD, ww, ya, yb, lane, sA11, sA12, sA22);
+      else lk_patch_strips<false>(I, D, step, W, H, ipx, ipy, w00, w01, w10, w11, sI, sD, ww, ya, yb, lane, sA11, sA12, sA22);
       sA11 = warp_sum_ll(sA11); sA12 = warp_sum_ll(sA12); sA22 = warp_sum_ll(sA22);
       __syncwarp();
+      feature_sum(sA11, sA12, sA22, 3);
     }
     float A11 = __fmul_rn((float)sA11, FLT_SCALE), A12 = __fmul_rn((float)sA12, FLT_SCALE),
           A22 = __fmul_rn((float)sA22, FLT_SCALE);
@@ -360,8 +394,9 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_track(LkArgs a) {
         break;
       }
       lk_weights(qx - ix, qy - iy, w00, w01, w10, w11);
-      long long s1, s2;
-      lk_window_pass<false>(J, step, W, H, ix, iy, w00, w01, w10, w11, sI, sD, ww, wh, lane, s1, s2);
+      long long s1, s2, s3 = 0;
+      lk_window_pass<false>(J, step, W, H, ix, iy, w00, w01, w10, w11, sI, sD, ww, wh, ya, yb, lane, s1, s2);
+      feature_sum(s1, s2, s3, 2);
       float b1 = __fmul_rn((float)s1, FLT_SCALE), b2 = __fmul_rn((float)s2, FLT_SCALE);
       float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), Dt);
       float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), Dt);
@@ -381,13 +416,14 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_track(LkArgs a) {
         status = 0;
       } else {
         lk_weights(ex - ix, ey - iy, w00, w01, w10, w11);
-        long long s1, s2;
-        lk_window_pass<true>(J, step, W, H, ix, iy, w00, w01, w10, w11, sI, sD, ww, wh, lane, s1, s2);
+        long long s1, s2, s3 = 0;
+        lk_window_pass<true>(J, step, W, H, ix, iy, w00, w01, w10, w11, sI, sD, ww, wh, ya, yb, lane, s1, s2);
+        feature_sum(s1, s2, s3, 1);
         err = __fmul_rn((float)s1, 1.f / (float)(32 * ww * wh));
       }
     }
   }
-  if (lane == 0) {
+  if (lane == 0 && half == 0) {
     a.next_pts[2 * oidx] = nx;
     a.next_pts[2 * oidx + 1] = ny;
     a.status[oidx] = (uint8_t)status;
@@ -401,7 +437,7 @@ static int lk_check(int rows, int cols, const b2of_lk_params* p) {
   B2OF_ASSERT(rows > 0 && cols > 0, fn);
   B2OF_ASSERT(p->max_level >= 0 && p->win_w > 2 && p->win_h > 2, fn);
   size_t per_warp = lk_patch_bytes(p->win_w, p->win_h);
-  if (per_warp * LK_WARPS > 200 * 1024)
+  if (per_warp * LK_FEATS + 1024 > 200 * 1024)
     return fail(B2OF_E_UNSUPPORTED, "winSize %dx%d needs more shared memory than one SM has", p->win_w, p->win_h);
   return B2OF_OK;
 }
@@ -477,11 +513,11 @@ int pyrlk_dev(const uint8_t* prev, const uint8_t* next, size_t step, size_t fram
   a.flags = p->flags;
   a.min_eig_thr = (float)p->min_eig_threshold;
   size_t per_warp = lk_patch_bytes(p->win_w, p->win_h);
-  size_t smem = per_warp * LK_WARPS;
+  size_t smem = per_warp * LK_FEATS + (size_t)LK_FEATS * 2 * LK_SPLIT * 3 * sizeof(long long);
   static PerDeviceMax max_set;
   if (smem > 48 * 1024 && max_set.raise(smem))
     B2OF_CUDA(cudaFuncSetAttribute(lk_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(cdiv(n_pts, LK_WARPS), batch);
+  dim3 grid(cdiv(n_pts, LK_FEATS), batch);
   {
     // algorithmic bytes: both pyramids once (u8) + derivatives of the first (4 B/px) + 21 B per point
     double px = 0;

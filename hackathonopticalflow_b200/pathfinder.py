@@ -5,8 +5,8 @@ Same names and argument meaning as the reference's functions, minus the drawing 
 * ``grid_points``      -- the measurement grid, pathfinder_viewer.py:255-267 (DenseOF.py:166-180)
 * ``get_flow_lk``      -- pathfinder_viewer.py:144-193: LK from the current frame back to the previous one
                           (note the argument order at :156), modulus normalisation, median/p99 filter, int rounding
-* ``draw_sparse_lamps``-- pathfinder_viewer.py:196-223: returns the danger intensity V per kept point
-                          (what :210-217 writes) instead of a drawn image
+* ``draw_sparse_lamps``-- pathfinder_viewer.py:196-223: the lamp layer (filled discs of radius 6 whose brightness is
+                          the danger intensity), drawn on the device; ``lamp_intensity`` is the V value alone
 * ``draw_hsv``         -- pathfinder_viewer.py:124-141: dense flow -> BGR picture (hue = direction, value = length)
 """
 import numpy as np
@@ -27,6 +27,9 @@ def grid_points(width, height, step=30):
     return pts.reshape(-1, 2)
 
 
+draw_bad_flow = True          # the reference's module-level switch (pathfinder_viewer.py:14)
+
+
 def get_flow_lk(img1, img2, points_, device="cuda", rule=batch.FILTER_VIEWER):
     """img1: previous gray, img2: current gray, points_: float32 (N,2) (all numpy, as the reference passes them).
 
@@ -39,19 +42,29 @@ def get_flow_lk(img1, img2, points_, device="cuda", rule=batch.FILTER_VIEWER):
     cur = torch.from_numpy(np.ascontiguousarray(img2)).to(device)[None]
     pts = torch.from_numpy(np.ascontiguousarray(points_, dtype=np.float32)).to(device)
     nxt, _status, _err = batch.pyrlk(cur, prev, pts, **batch.LK_GRID_DEFAULTS)
-    out = batch.pathfinder_filter(pts, nxt, width, height, mode=rule)
+    out = batch.pathfinder_filter(pts, nxt, width, height, mode=rule, all_points=True)
     m = int(out["n_kept"][0])
-    # frame_layer is the reference's drawing of the kept vectors (cv2.polylines / cv2.circle, :179-191): drawing is
-    # out of scope for the hot path, the layer is returned black so that callers can unpack three values
-    frame_layer = np.zeros((height, width, 3), np.uint8)
+    # frame_layer: the kept vectors in red with magenta start points, the rejected ones in cyan when draw_bad_flow is
+    # set (:179-191), rasterised on the device exactly as cv2.polylines / cv2.circle do
+    frame_layer = batch.overlay_vectors(out, height, width, draw_bad=draw_bad_flow)[0].cpu().numpy()
     return frame_layer, out["kept_flow"][0, :m].cpu().numpy(), out["kept_pts"][0, :m].cpu().numpy()
 
 
-def draw_sparse_lamps(flow_, points_):
+def lamp_intensity(flow_):
     """Danger intensity per kept point: uint8 V = min(50 + 2*|flow|, 255) (pathfinder_viewer.py:210-217)."""
     f = torch.from_numpy(np.ascontiguousarray(flow_)).to(torch.float64)
     m = torch.sqrt(f[:, 0] * f[:, 0] + f[:, 1] * f[:, 1])
     return torch.clamp(50 + m * 2, max=255).to(torch.uint8).numpy()
+
+
+def draw_sparse_lamps(flow_, points_, height, width, device="cuda"):
+    """flow_ int32 (M,2), points_ int32 (M,2) as get_flow_lk returns them -> uint8 (H,W,3) BGR lamp layer
+    (pathfinder_viewer.py:196-223; the reference reads height / width from module globals)."""
+    m = len(points_)
+    filt = dict(kept_pts=torch.from_numpy(np.ascontiguousarray(points_, dtype=np.int32)).to(device).reshape(1, m, 2),
+                danger_v=torch.from_numpy(lamp_intensity(flow_)).to(device).reshape(1, m),
+                n_kept=torch.tensor([m], dtype=torch.int32, device=device))
+    return batch.overlay_lamps(filt, height, width)[0].cpu().numpy()
 
 
 def draw_hsv(flow_, device="cuda"):

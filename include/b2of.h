@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define B2OF_VERSION 101
+#define B2OF_VERSION 102
 
 #define B2OF_OK 0
 #define B2OF_E_BADARG (-215) /* cv2's StsAssert code: same meaning */
@@ -188,10 +188,25 @@ int b2of_gftt_host(const uint8_t* img, const uint8_t* mask, size_t step, size_t 
  *   B2OF_FILTER_DENSEOF  m > 1.2 * median(m)                    DenseOF.py:228 */
 #define B2OF_FILTER_VIEWER 0
 #define B2OF_FILTER_DENSEOF 1
+/* all_pts_dev / all_next_dev (both NULL or both given): int32 (batch, n_pts, 2), EVERY point and its normalised end
+ * point as the reference rounds them (viewer.py:169-170) -- what the overlay (b2of_overlay_vectors_dev) draws. */
 int b2of_pathfinder_filter_dev(const float* pts_dev, size_t pts_batch_stride, const float* next_pts_dev, int n_pts,
                                int batch, int width, int height, int mode, int32_t* kept_pts_dev,
                                int32_t* kept_flow_dev, uint8_t* danger_v_dev, uint8_t* mask_dev, int32_t* n_kept_dev,
-                               float* stats_dev, void* stream);
+                               float* stats_dev, int32_t* all_pts_dev, int32_t* all_next_dev, void* stream);
+
+/* ---- overlay layers, composited on the device (the reference's drawing calls) ------------------------
+ * vector layer, viewer.py:179-191: cv2.polylines of the kept vectors (mask == 1) in BGR (0,0,255), cv2.circle of
+ * radius 1 in (255,0,255) at their start points, then -- draw_bad != 0, the reference's draw_bad_flow -- the rejected
+ * vectors and their start points in (255,255,0).  layer_bgr_dev: uint8 (batch, rows, cols, 3), cleared first.
+ * Pixel for pixel what cv2 draws (clipLine + 8-connected LineIterator, midpoint circle). */
+int b2of_overlay_vectors_dev(const int32_t* all_pts_dev, const int32_t* all_next_dev, const uint8_t* mask_dev, int n_pts,
+                             int batch, int rows, int cols, int draw_bad, uint8_t* layer_bgr_dev, void* stream);
+/* lamp layer, viewer.py:210-222 (draw_sparse_lamps): HSV (0,255,V) at every kept point converted as
+ * cv2.cvtColor(HSV2BGR) does, then a filled cv2.circle of radius 6 in the point's own colour.
+ * kept_pts_dev / danger_v_dev / n_kept_dev are b2of_pathfinder_filter_dev's outputs. */
+int b2of_overlay_lamps_dev(const int32_t* kept_pts_dev, const uint8_t* danger_v_dev, const int32_t* n_kept_dev,
+                           int n_pts, int batch, int rows, int cols, uint8_t* bgr_dev, void* stream);
 
 /* dense flow sampled on a point set (the grid): next_pts[b][i] = pts[i] + flow[b][int(y_i)][int(x_i)], float32
  * (batch, n_pts, 2) -- feeds b2of_pathfinder_filter_dev with the dense field instead of LK (what draw_flow samples,

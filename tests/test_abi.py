@@ -26,7 +26,7 @@ def test_header_symbols_exported_and_bound():
 def test_version_and_error_channel_without_gpu():
     from hackathonopticalflow_b200 import _lib
     l = _lib.lib()
-    assert l.b2of_version() == 101
+    assert l.b2of_version() == 102
     # argument checks fire before any CUDA call and mirror cv2's assertion text
     rc = l.b2of_bgr2gray_u8_dev(None, 4, 4, 2, 0, None, 4, 0, 1, None)
     assert rc == -215

@@ -45,6 +45,15 @@ def _decode_png(buf):
     return np.array(Image.open(BytesIO(buf.tobytes())))
 
 
+def _decode_png_bgr(buf):
+    if have_cv2():
+        import cv2
+        return cv2.imdecode(buf, cv2.IMREAD_COLOR)
+    from io import BytesIO
+    from PIL import Image
+    return np.ascontiguousarray(np.array(Image.open(BytesIO(buf.tobytes())).convert("RGB"))[..., ::-1])
+
+
 def test_native_library_is_the_one_in_tree(b2):
     import os
     from hackathonopticalflow_b200 import _lib
@@ -621,8 +630,16 @@ def test_get_flow_lk_and_lamps_equal_the_reference_functions(ref_funcs, crops, f
     if np.array_equal(kept, want_p):
         same = (flow == want_f).all(1)
         assert same.mean() >= MASK_TOL
-        v = pathfinder.draw_sparse_lamps(flow, kept)
+        v = pathfinder.lamp_intensity(flow)
         assert (v[same] == ref_funcs[f"{name}_danger_v"][same]).all()
+    # the drawn layers: pixel for pixel the reference's cv2.polylines / cv2.circle output wherever the
+    # vectors themselves agree (they do on these fixtures: LK positions differ from cv2 by < 0.005 px)
+    if np.array_equal(kept, want_p) and np.array_equal(flow, want_f):
+        want_layer = _decode_png_bgr(ref_funcs[f"{name}_layer_png"])
+        assert layer.shape == want_layer.shape
+        assert (layer != want_layer).any(-1).mean() <= 1e-4          # a rejected vector off by one pixel, if any
+        lamps = pathfinder.draw_sparse_lamps(flow, kept, h, w)
+        assert np.array_equal(lamps, _decode_png_bgr(ref_funcs[f"{name}_lamps_png"]))
 
 
 @pytest.mark.parametrize("name,w,h", REF_CASES)
@@ -794,3 +811,27 @@ def test_two_devices_in_one_process_if_present(batch, synth_small):
             eng = batch.FarnebackEngine(135, 241, chunk_pairs=1, device=f"cuda:{d}")
             outs.append(eng.flow_sequence(torch.from_numpy(frames).to(f"cuda:{d}")).cpu())
     assert torch.equal(outs[0], outs[1])
+
+
+def test_overlay_layers_vs_oracle_restatement(batch, ref_funcs, crops, full1080):
+    """Overlay kernels against oracle/overlay.py (itself equal to the reference's drawn layers, tests/test_oracle_golden)
+    on the golden cv2 LK results, with vectors that leave the frame (clipLine) added."""
+    import torch
+    from hackathonopticalflow_b200 import pathfinder
+    from oracle import overlay as ov
+    for name, w, h in REF_CASES:
+        nxt = (full1080["lk_next"] if name == "full" else crops[f"lk_next_{name[-1]}"]).copy()
+        pts = pathfinder.grid_points(w, h, 30)
+        nxt[::7] += np.float32([[900.0, -700.0]])            # long vectors that cross the frame border
+        nxt[3::11] -= np.float32([[1300.0, 40.0]])
+        filt = batch.pathfinder_filter(torch.from_numpy(pts).cuda(), torch.from_numpy(nxt).cuda()[None], w, h,
+                                       all_points=True)
+        ap, an = filt["all_pts"][0].cpu().numpy(), filt["all_next"][0].cpu().numpy()
+        mask = filt["mask"][0].cpu().numpy().astype(bool)
+        for bad in (True, False):
+            got = batch.overlay_vectors(filt, h, w, draw_bad=bad)[0].cpu().numpy()
+            assert np.array_equal(got, ov.vector_layer(ap, an, mask, w, h, bad)), (name, bad)
+        k = int(filt["n_kept"][0])
+        got = batch.overlay_lamps(filt, h, w)[0].cpu().numpy()
+        want = ov.lamp_layer(filt["kept_flow"][0, :k].cpu().numpy(), filt["kept_pts"][0, :k].cpu().numpy(), w, h)
+        assert np.array_equal(got, want), name

@@ -238,3 +238,43 @@ def test_farneback_zero_iterations(synth_small, extras):
     got = ofb.farneback(f0, f1, extras["fb_iter0_init_in"].copy(), 0.5, 3, 15, 0, 5, 1.2, 4)
     mean, mx = epe(got, extras["fb_iter0_init"])
     assert mean < 1e-6 and mx < 1e-4, (mean, mx)
+
+
+@pytest.mark.parametrize("name,w,h", CASES)
+def test_overlay_restatement_equals_the_reference_drawings(ref_funcs, crops, full1080, name, w, h):
+    """oracle/overlay.py against the layers the reference's own get_flow_lk / draw_sparse_lamps drew (cv2.polylines,
+    cv2.circle): identical images."""
+    if not have_cv2():
+        pytest.skip("PNG fixtures are decoded with cv2")
+    import cv2
+    from oracle import overlay as ov
+    nxt = _lk_next(name, crops, full1080)
+    pts = opf.grid_points(w, h, 30)
+    flow, kept, mask, _ = opf.vector_filter(nxt, pts, w, h)
+    fl = nxt - pts
+    ang = np.arctan2(fl[:, 1], fl[:, 0])
+    mod = np.sqrt(fl[:, 0] * fl[:, 0] + fl[:, 1] * fl[:, 1])
+    mod = mod / (5 + np.sqrt(np.sqrt((int(w / 2) - pts[:, 0]) ** 2 + (int(h / 2) - pts[:, 1]) ** 2))) * 30
+    all_next = np.int32(np.vstack([pts[:, 0] + mod * np.cos(ang), pts[:, 1] + mod * np.sin(ang)]).T + 0.5)
+    layer = ov.vector_layer(np.int32(pts + 0.5), all_next, mask, w, h, True)
+    assert np.array_equal(layer, cv2.imdecode(ref_funcs[f"{name}_layer_png"], cv2.IMREAD_COLOR))
+    lamps = ov.lamp_layer(flow, kept, w, h)
+    assert np.array_equal(lamps, cv2.imdecode(ref_funcs[f"{name}_lamps_png"], cv2.IMREAD_COLOR))
+
+
+def test_line_rasteriser_vs_cv2_random_segments():
+    if not have_cv2():
+        pytest.skip("live cv2 comparison")
+    import cv2
+    from oracle import overlay as ov
+    rng = np.random.default_rng(3)
+    W, H = 97, 61
+    for t in range(3000):
+        p1 = (int(rng.integers(-40, W + 40)), int(rng.integers(-40, H + 40)))
+        p2 = (int(rng.integers(-40, W + 40)), int(rng.integers(-40, H + 40)))
+        want = np.zeros((H, W), np.uint8)
+        cv2.line(want, p1, p2, 255, 1)
+        got = np.zeros((H, W), np.uint8)
+        for x, y in ov.line_pixels(W, H, p1, p2):
+            got[y, x] = 255
+        assert np.array_equal(got, want), (p1, p2)
