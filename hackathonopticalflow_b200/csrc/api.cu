@@ -28,7 +28,8 @@ std::vector<ProfRec> g_prof_recs;
 std::vector<cudaEvent_t> g_prof_pool;
 const char* const kProfNames[PT_COUNT] = {"bgr2gray", "pyrdown", "fb_level_hpass", "fb_level_vpass", "fb_polyexp",
                                           "fb_iter_finest", "fb_iter_coarse", "lk_scharr", "lk_track", "gftt_mineig",
-                                          "gftt_nms_compact", "gftt_select", "pathfinder_filter", "flow_stats"};
+                                          "gftt_nms_compact", "gftt_select", "pathfinder_filter", "flow_stats",
+                                          "fb_upsample"};
 cudaEvent_t prof_event() {
   if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
   cudaEvent_t e;

@@ -69,7 +69,7 @@ inline int cv_round(double v) { return (int)nearbyint(v); }
 // ---- optional per-kernel timing (CUDA events on the launching stream); off by default ----
 enum ProfTag {
   PT_GRAY = 0, PT_PYRDOWN, PT_FB_LEVEL_H, PT_FB_LEVEL_V, PT_FB_POLYEXP, PT_FB_ITER_FINEST, PT_FB_ITER_COARSE,
-  PT_LK_SCHARR, PT_LK_TRACK, PT_GFTT_MINEIG, PT_GFTT_NMS, PT_GFTT_SELECT, PT_FILTER, PT_STATS, PT_COUNT
+  PT_LK_SCHARR, PT_LK_TRACK, PT_GFTT_MINEIG, PT_GFTT_NMS, PT_GFTT_SELECT, PT_FILTER, PT_STATS, PT_FB_UPSAMPLE, PT_COUNT
 };
 extern std::atomic<int> g_prof_on;
 void prof_mark(int tag, cudaStream_t st, bool end, double bytes);

@@ -914,6 +914,7 @@ struct IterArgs {
   const int *ux0, *ux1, *uy0, *uy1;
   const float *ufx, *ufy;
   float up_mult;
+  int up_exact2;           // mode 2: this level is exactly twice the coarser one in both axes
   float2* flow_out;
   size_t flow_out_pair_stride;
   int out_pitch;           // in float2
@@ -1001,8 +1002,18 @@ __device__ __forceinline__ float2 fetch_flow_m(const IterArgs& a, const float2* 
                                                float ufx) {
   if (MODE == 0) return make_float2(0.f, 0.f);
   if (MODE == 1) return ldg_f2(fin + o);
-  int ya = a.uy0[y], yb = a.uy1[y];
-  float fy = a.ufy[y];
+  int ya, yb;
+  float fy;
+  if (a.up_exact2) {
+    // exact x2 upsample (the reference's pyr_scale 0.5 on even sizes): cv2's linear-resize row table in closed form
+    // (source position y / 2 - 0.25, clamped at both ends) instead of three table loads per row
+    if (y & 1) { ya = y >> 1; yb = min(ya + 1, a.ch - 1); fy = ya >= a.ch - 1 ? 0.f : 0.25f; }
+    else if (y == 0) { ya = 0; yb = min(1, a.ch - 1); fy = 0.f; }
+    else { ya = (y >> 1) - 1; yb = ya + 1; fy = 0.75f; }
+  } else {
+    ya = a.uy0[y]; yb = a.uy1[y];
+    fy = a.ufy[y];
+  }
   float2 p00 = fin[ya * a.in_pitch + xa], p01 = fin[ya * a.in_pitch + xb];
   float2 p10 = fin[yb * a.in_pitch + xa], p11 = fin[yb * a.in_pitch + xb];
   float tx0 = p00.x * (1.f - ufx) + p01.x * ufx, ty0 = p00.y * (1.f - ufx) + p01.y * ufx;
@@ -1362,6 +1373,40 @@ __global__ void __launch_bounds__(256) fb_flow_only(IterArgs a) {
       fetch_flow_m<MODE>(a, fin, y * a.pitch + x, y, xa, xb, fx);
 }
 
+// Exact x2 upsample of the coarser level's flow (the reference's pyr_scale 0.5 on even sizes) as its own pass:
+// thread (i, j) owns the coarse cell between columns i, i + 1 and rows j, j + 1 -- four loads -- and writes the four
+// fine pixels that interpolate inside it (x = 2i + 1, 2i + 2; y = 2j + 1, 2j + 2; fractions 0.25 / 0.75, 0 at the
+// clamped ends).  Same expression as fetch_flow_m<2>, same bits; a quarter of its loads per pixel and no tables.
+__global__ void __launch_bounds__(256) fb_upsample2x(IterArgs a) {
+  const int i = blockIdx.x * 64 + (threadIdx.x & 63) - 1, j = blockIdx.y * 4 + (threadIdx.x >> 6) - 1;
+  const int pair = blockIdx.z;
+  if (i >= a.cw || j >= a.ch) return;
+  const float2* fin = a.flow_in + (size_t)pair * a.flow_in_pair_stride;
+  // cv2's linear-resize table in closed form: x = 0 -> (0, 1, 0); x = 2k + 1 -> (k, k + 1, 0.25), clamped to
+  // (n - 1, n - 1, 0) at the end; x = 2k + 2 -> (k, k + 1, 0.75).  Cell -1 is the pair (0, 1) that pixel 0 reads.
+  const int ia = max(i, 0), ib = i < 0 ? min(1, a.cw - 1) : min(i + 1, a.cw - 1);
+  const int ja = max(j, 0), jb = j < 0 ? min(1, a.ch - 1) : min(j + 1, a.ch - 1);
+  const float2 p00 = fin[ja * a.in_pitch + ia], p01 = fin[ja * a.in_pitch + ib];
+  const float2 p10 = fin[jb * a.in_pitch + ia], p11 = fin[jb * a.in_pitch + ib];
+  float2* out = a.flow_out + (size_t)pair * a.flow_out_pair_stride;
+#pragma unroll
+  for (int dy = 1; dy <= 2; ++dy) {
+    const int y = 2 * j + dy;
+    if (y < 0 || y >= a.h) continue;
+    const float fy = y == 0 ? 0.f : (y & 1) ? ((y >> 1) >= a.ch - 1 ? 0.f : 0.25f) : 0.75f;
+#pragma unroll
+    for (int dx = 1; dx <= 2; ++dx) {
+      const int x = 2 * i + dx;
+      if (x < 0 || x >= a.w) continue;
+      const float fx = x == 0 ? 0.f : (x & 1) ? ((x >> 1) >= a.cw - 1 ? 0.f : 0.25f) : 0.75f;
+      const float tx0 = p00.x * (1.f - fx) + p01.x * fx, ty0 = p00.y * (1.f - fx) + p01.y * fx;
+      const float tx1 = p10.x * (1.f - fx) + p11.x * fx, ty1 = p10.y * (1.f - fx) + p11.y * fx;
+      out[(size_t)y * a.out_pitch + x] =
+          make_float2((tx0 * (1.f - fy) + tx1 * fy) * a.up_mult, (ty0 * (1.f - fy) + ty1 * fy) * a.up_mult);
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // host driver
 // ----------------------------------------------------------------------------------------------
@@ -1622,6 +1667,7 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
           a.mode = 1; a.flow_in = B; a.flow_in_pair_stride = plane; a.in_pitch = L.pitch;
         } else if (coarse) {
           a.mode = 2; a.flow_in = coarse; a.flow_in_pair_stride = cstride; a.in_pitch = cpitch; a.cw = cw; a.ch = ch;
+          a.up_exact2 = L.h == 2 * ch && L.w == 2 * cw && ch >= 2;
         } else {
           a.mode = 0; a.flow_in = nullptr;
         }
@@ -1639,6 +1685,26 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
       }
       a.flow_out = dst; a.out_pitch = dpitch; a.flow_out_pair_stride = dstride;
       a.stats_acc = nullptr;
+#ifndef FB_SEPARATE_UPSAMPLE
+#define FB_SEPARATE_UPSAMPLE 1
+#endif
+      if (FB_SEPARATE_UPSAMPLE && fast && !flow_only && a.mode == 2) {
+        // The x(1/pyr_scale) upsample of the coarser level's flow as its own small pass into the level's second
+        // flow buffer (free during the first iteration), so that the first iteration reads its flow the way the
+        // others do.  Folded into the fused kernel (four gathers and a second dependent load per pixel in step A)
+        // the first launch of a level took 27 % longer than the later ones: 2.29 vs 1.81 ms at 1080p x 64 pairs,
+        // against 0.2 ms for this pass.  Same arithmetic (fetch_flow_m<2>), same bits.
+        IterArgs u = a;
+        u.flow_out = B; u.out_pitch = L.pitch; u.flow_out_pair_stride = plane;
+        dim3 gf(cdiv(L.w, 256), L.h, pairs);
+        {
+          ProfScope ps(PT_FB_UPSAMPLE, st, pairs * (8.0 * cw * ch + 8.0 * L.w * L.h));
+          if (u.up_exact2) fb_upsample2x<<<dim3(cdiv(cw + 1, 64), cdiv(ch + 1, 4), pairs), 256, 0, st>>>(u);
+          else fb_flow_only<2><<<gf, 256, 0, st>>>(u);
+        }
+        B2OF_LAUNCH_CHECK();
+        a.mode = 1; a.flow_in = B; a.flow_in_pair_stride = plane; a.in_pitch = L.pitch;
+      }
       if (flow_only) {
         dim3 gf(cdiv(L.w, 256), L.h, pairs);
         if (a.mode == 0) fb_flow_only<0><<<gf, 256, 0, st>>>(a);

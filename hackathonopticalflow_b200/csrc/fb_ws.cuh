@@ -62,6 +62,9 @@ constexpr int FBW_REFRESH_ROWS = 64;                    // rows between restarts
 constexpr int FBW_REFRESH = FBW_REFRESH_ROWS / FBW_RB;  // ... in blocks
 constexpr int FBW_NT = (FBW_A_WARPS + FBW_B_WARPS + FBW_C_WARPS) * 32;
 constexpr int FBW_PF_BLOCKS = 64 / FBW_RB;              // L2 prefetch distance in blocks (64 rows)
+#ifndef FBW_UP_CARRY
+#define FBW_UP_CARRY 0  // 1: carry the interpolated coarse rows down a column in upsample mode -- measured 10 % SLOWER for
+#endif                  // those launches (the conditional loads no longer overlap with the previous row)
 #ifndef FBW_SKIP
 #define FBW_SKIP 0   // timing experiments only: bit 0 / 1 / 2 switches step A / B / C off
 #endif
@@ -264,12 +267,40 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
         int o_carry = -1 << 30;
         int yA, oA, yB = 0, oB = 0;
         next_row(yA, oA);
-        float2 dA = fetch_flow_m<MODE>(a, fi, oA, yA, uxa, uxb, ufx), dB = dA;
+#if FBW_UP_CARRY
+        // MODE 2 (flow = bilinear x(1/pyr_scale) upsample of the coarser level): walking down a column, consecutive
+        // rows read the same pair of coarse rows, or the pair one further down -- the horizontally interpolated
+        // coarse rows are carried (same arithmetic, same bits: 1 to 1.5 gathers per row instead of 4)
+        int u_ya = -1, u_yb = -1;
+        float2 u_ha = make_float2(0.f, 0.f), u_hb = u_ha;
+        auto coarse_row = [&](int r) {
+          const float2 p0 = fi[r * a.in_pitch + uxa], p1 = fi[r * a.in_pitch + uxb];
+          return make_float2(p0.x * (1.f - ufx) + p1.x * ufx, p0.y * (1.f - ufx) + p1.y * ufx);
+        };
+        auto fetch = [&](int o, int y) -> float2 {
+          if (MODE != 2) return fetch_flow_m<MODE>(a, fi, o, y, uxa, uxb, ufx);
+          const int ya = a.uy0[y], yb = a.uy1[y];
+          const float fy = a.ufy[y];
+          if (ya != u_ya) {
+            u_ha = ya == u_yb ? u_hb : coarse_row(ya);
+            u_ya = ya;
+          }
+          if (yb != u_yb) {
+            u_hb = yb == ya ? u_ha : coarse_row(yb);
+            u_yb = yb;
+          }
+          return make_float2((u_ha.x * (1.f - fy) + u_hb.x * fy) * a.up_mult,
+                             (u_ha.y * (1.f - fy) + u_hb.y * fy) * a.up_mult);
+        };
+#else
+        auto fetch = [&](int o, int y) -> float2 { return fetch_flow_m<MODE>(a, fi, o, y, uxa, uxb, ufx); };
+#endif
+        float2 dA = fetch(oA, yA), dB = dA;
         auto rowf = [&](const float2 d, float2& dn, const int y, int& yn, const int o, int& on, bool has_next,
                         FbCorner& top, FbCorner& bot) {
           const float4 q = ldg_f4<0>((const float4*)(rb + (unsigned)o * 16u));
           const float q4 = ldg_f1<0>((const float*)(rb + ((unsigned)o * 4u + c_r0b)));
-          if (has_next) { next_row(yn, on); dn = fetch_flow_m<MODE>(a, fi, on, yn, uxa, uxb, ufx); }
+          if (has_next) { next_row(yn, on); dn = fetch(on, yn); }
           float fx = xf + d.x, fy = (float)y + d.y;
           const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
           fx -= (float)x1; fy -= (float)y1;
