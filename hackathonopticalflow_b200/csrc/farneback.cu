@@ -797,18 +797,77 @@ __global__ void __launch_bounds__(256) fb_polyexp(const float* __restrict__ I, i
 //            three vertical filters come out of a register window, results to shared memory
 //   phase 2: thread = two adjacent x (8-byte LDS of the filtered rows), warps over rows; 32 B + 8 B stores per thread
 // ----------------------------------------------------------------------------------------------
-template <int N>
+// FUSE0: the level is the full-resolution one (the reference's level 0: 3-tap blur, no resampling) and its image is
+// computed here, from the uint8 frame, instead of being read back from HBM: the CTA stages the source pixels of its
+// halo tile, runs fb_level_regular<3, 1>'s two passes on them in shared memory (same taps, same fused multiply-add
+// order: same bits) and phase 1 takes its 18 rows from there.  Saves the level-image kernel and an 8 B/px round trip.
+struct Poly0Src {
+  const uint8_t* frames; size_t step, frame_stride;
+  float c[3];                               // combined taps of the regular (3, 1) level form
+};
+
+template <int N, bool FUSE0>
 __global__ void __launch_bounds__(320) fb_polyexp_n(const float* __restrict__ I, int w, int h, int pitch,
                                                      size_t i_frame_stride, float* __restrict__ R,
-                                                     size_t plane_stride, size_t r_frame_stride, PolyConst pc) {
+                                                     size_t plane_stride, size_t r_frame_stride, PolyConst pc,
+                                                     Poly0Src src) {
   constexpr int CW = PE_TW + 2 * N;        // halo columns (74 for N = 5)
   constexpr int CP = (CW + 7) / 8 * 8;     // phase-1 thread columns (80), also the smem pitch (even)
   constexpr int SEG = 8, NSEG = PE_TH / SEG;
   static_assert(CP * NSEG <= 320, "phase 1 does not fit the block");
   __shared__ __align__(16) float s_r[3][PE_TH][CP];
+  constexpr int IH = PE_TH + 2 * N;        // rows of the level-image halo tile (42)
+  __shared__ float s_i[FUSE0 ? IH * CP : 1];
   const int x0 = blockIdx.x * PE_TW, y0 = blockIdx.y * PE_TH;
   const float* ib = I + blockIdx.z * i_frame_stride;
   const int t = threadIdx.x;
+  if constexpr (FUSE0) {
+    // source tile: image rows y0 - N - 1 .. y0 + PE_TH + N, columns from the word boundary below x0 - N - 1; both
+    // scratch arrays live in s_r, which phase 1 only writes after the barrier that ends this block
+    constexpr int SH = IH + 2, LP = 2;     // x0 - N - 1 = x0 - 6: two columns above a multiple of four (x0 % 64 == 0)
+    constexpr int SWP = ((LP + CW + 2 + 3) / 4) * 4;      // 80 staged columns
+    static_assert(N == 5, "the staging offsets are written for poly_n = 5");
+    uint8_t* s_u = (uint8_t*)&s_r[0][0][0];               // [SH][SWP] uint8
+    float* s_h = (float*)(s_u + ((SH * SWP + 15) & ~15)); // [SH][CP] horizontal pass
+    static_assert(((SH * SWP + 15) & ~15) + SH * CP * 4 <= sizeof(s_r), "scratch does not fit s_r");
+    const uint8_t* fb = src.frames + blockIdx.z * src.frame_stride;
+    const int gx0 = x0 - N - 1 - LP, gy0 = y0 - N - 1;
+    const bool inside = gx0 >= 0 && gy0 >= 0 && gx0 + SWP <= w && gy0 + SH <= h && ((src.step | (size_t)fb) & 3) == 0;
+    if (inside) {
+      for (int i = t; i < SH * (SWP / 4); i += 320) {
+        const int rr = i / (SWP / 4), wc = i - rr * (SWP / 4);
+        ((uint32_t*)s_u)[rr * (SWP / 4) + wc] = __ldg((const uint32_t*)(fb + (size_t)(gy0 + rr) * src.step + gx0) + wc);
+      }
+    } else {
+      for (int i = t; i < SH * SWP; i += 320) {
+        const int rr = i / SWP, cc = i - rr * SWP;
+        s_u[i] = fb[(size_t)reflect101(gy0 + rr, h) * src.step + reflect101(gx0 + cc, w)];
+      }
+    }
+    __syncthreads();
+    // horizontal pass at the CLAMPED halo column (the expansion replicates the level image at its border, the level
+    // image itself reflects the frame: the staged tile holds reflect101 of every coordinate it covers)
+    for (int i = t; i < SH * CW; i += 320) {
+      const int rr = i / CW, c = i - rr * CW;
+      const int tc = clampi(x0 + c - N, 0, w - 1) - gx0;  // staged column of the halo column's own pixel
+      const uint8_t* pr = s_u + rr * SWP + tc - 1;
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) v = fmaf(src.c[j], (float)pr[j], v);
+      s_h[rr * CP + c] = v;
+    }
+    __syncthreads();
+    for (int i = t; i < IH * CW; i += 320) {
+      const int r = i / CW, c = i - r * CW;
+      const int tr = clampi(y0 + r - N, 0, h - 1) - gy0;
+      const float* ph = s_h + (tr - 1) * CP + c;
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) v = fmaf(src.c[j], ph[j * CP], v);
+      s_i[r * CP + c] = v;
+    }
+    __syncthreads();
+  }
   {
     const int seg = t / CP, c = t - seg * CP;
     if (seg < NSEG && c < CW) {
@@ -816,7 +875,8 @@ __global__ void __launch_bounds__(320) fb_polyexp_n(const float* __restrict__ I,
       const int yb = y0 + seg * SEG - N;
       float v[SEG + 2 * N];
 #pragma unroll
-      for (int j = 0; j < SEG + 2 * N; ++j) v[j] = ib[(size_t)clampi(yb + j, 0, h - 1) * pitch + gx];
+      for (int j = 0; j < SEG + 2 * N; ++j)
+        v[j] = FUSE0 ? s_i[(seg * SEG + j) * CP + c] : ib[(size_t)clampi(yb + j, 0, h - 1) * pitch + gx];
 #pragma unroll
       for (int j = 0; j < SEG; ++j) {
         float r0 = v[j + N] * pc.g[0], r1 = 0.f, r2 = 0.f;
@@ -1509,7 +1569,15 @@ static int fb_frames(const FbPlan* pl, const FbWorkspace& ws, const uint8_t* fra
     float* Ib = ws.I + (size_t)total_slots * lvl_off + (size_t)slot0 * plane;
     float* Rb = ws.R + (size_t)total_slots * 5 * lvl_off + (size_t)slot0 * 5 * plane;
     size_t t_stride = (size_t)H * pitch0 * slot_step, i_stride = plane * slot_step, r_stride = 5 * plane * slot_step;
-    if (li < 8 && fused_level[li]) {
+#ifndef FB_FUSE_LEVEL0
+#define FB_FUSE_LEVEL0 0   // measured: the level-image kernel goes (-0.27 ms per 65 frames) but the expansion, already
+#endif                     // issue-bound at 77 %, pays +0.46 ms for the two extra passes: off (profiles/README.md)
+    // the full-resolution level in its regular (3, 1) form with poly_n = 5: its image is computed inside the expansion
+    const bool fuse0 = FB_FUSE_LEVEL0 && L.r_K == 3 && L.r_S == 1 && L.r_c0 == -1 && pl->p.poly_n == 5 &&
+                       L.w == W && L.h == H && W >= 4 && H >= 4;
+    if (fuse0) {
+      // no level image in HBM at all
+    } else if (li < 8 && fused_level[li]) {
       // level image already written by fb_levels_coarse
     } else if (L.r_K) {
       LevelRegArgs ra{};
@@ -1560,8 +1628,13 @@ static int fb_frames(const FbPlan* pl, const FbWorkspace& ws, const uint8_t* fra
     dim3 g3(cdiv(L.w, PE_TW), cdiv(L.h, PE_TH), frames);
     {
       ProfScope ps(PT_FB_POLYEXP, st, (double)frames * 24.0 * L.w * L.h);
-      if (n == 5) fb_polyexp_n<5><<<g3, 320, 0, st>>>(Ib, L.w, L.h, L.pitch, i_stride, Rb, plane, r_stride, pl->pc);
-      else if (n == 7) fb_polyexp_n<7><<<g3, 320, 0, st>>>(Ib, L.w, L.h, L.pitch, i_stride, Rb, plane, r_stride, pl->pc);
+      Poly0Src ps0{};
+      if (fuse0) {
+        ps0.frames = frames_dev; ps0.step = step; ps0.frame_stride = frame_stride;
+        ps0.c[0] = L.r_c[0]; ps0.c[1] = L.r_c[1]; ps0.c[2] = L.r_c[2];
+        fb_polyexp_n<5, true><<<g3, 320, 0, st>>>(Ib, L.w, L.h, L.pitch, i_stride, Rb, plane, r_stride, pl->pc, ps0);
+      } else if (n == 5) fb_polyexp_n<5, false><<<g3, 320, 0, st>>>(Ib, L.w, L.h, L.pitch, i_stride, Rb, plane, r_stride, pl->pc, ps0);
+      else if (n == 7) fb_polyexp_n<7, false><<<g3, 320, 0, st>>>(Ib, L.w, L.h, L.pitch, i_stride, Rb, plane, r_stride, pl->pc, ps0);
       else fb_polyexp<<<g3, 256, smem, st>>>(Ib, L.w, L.h, L.pitch, i_stride, Rb, plane, r_stride, pl->pc, n);
     }
     B2OF_LAUNCH_CHECK();
