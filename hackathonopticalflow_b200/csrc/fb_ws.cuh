@@ -55,7 +55,15 @@ constexpr int FBS_M = 7;                  // window radius
 constexpr int FBS_PADL = 8;               // halo column 0 sits at image column x0 - 8 (8-pixel aligned)
 constexpr int FBS_TW = FBS_EW - 16;       // output columns per strip
 constexpr int FBS_ES = FBS_EW + 1;        // plane row stride in elements (odd)
-constexpr int FBS_HL = FBS_TW / 2;        // outputs [0,HL) are summed left->right, [HL,TW) right->left
+#ifndef FBS_HL_N
+#define FBS_HL_N (FBS_TW / 2)
+#endif
+// outputs [0,HL) are summed left->right, [HL,TW) right->left (stored 14 positions further right).  With HL = 56 the
+// 14-column jump in "where step B left column ct's sums" sits inside the second C warp, whose lanes 24-31 then share
+// banks with lanes 0-23 (one extra wavefront per ring read of that warp, 1.96 M of 13.8 M step-C wavefronts per
+// 16-pair launch); HL = 64 puts the jump between two warps and removes them -- and times the same (5.453 vs 5.455 ms
+// per 64 pairs x 3 launches), so the shorter left-half walk stays
+constexpr int FBS_HL = FBS_HL_N;
 constexpr int FBW_RUNS = FBW_A_WARPS * 32 / FBS_EW;     // row runs per block in step A
 constexpr int FBW_RB = 4 * FBW_RUNS;                    // rows per block: 4 rows per A thread
 constexpr int FBW_REFRESH_ROWS = 64;                    // rows between restarts of the vertical running sums
@@ -368,12 +376,14 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
     for (int s = 0; s < nblk; ++s) {
       const int nrows = s == 0 ? 2 * M + RB : RB;
       mbar_wait(s_bar + (s % FBW_STAGES) * 8, (unsigned)((s / FBW_STAGES) & 1));   // full_a[stage]
+      // float-type items go 16 to a warp (one half-row walker per row, left or right half): 32 of them in one
+      // 4-byte access would put the left and the right walkers of the same rows on the same banks every other step
       const int n2 = 4 * nrows, n1 = 2 * nrows;
-      const int u2 = (n2 + 31) >> 5, u1 = (n1 + 31) >> 5;
+      const int u2 = (n2 + 31) >> 5, u1 = (n1 + 15) >> 4;
       for (int u = bw; u < u2 + u1; u += FBW_B_WARPS) {
         const bool wide = u < u2;
-        const int i = (wide ? u : u - u2) * 32 + lane;
-        if (!(FBW_SKIP & 2) && i < (wide ? n2 : n1)) {
+        const int i = wide ? u * 32 + lane : (u - u2) * 16 + lane;
+        if (!(FBW_SKIP & 2) && i < (wide ? n2 : n1) && (wide || lane < 16)) {
           const int q = i / nrows, r = i - q * nrows;   // q = 2 * plane + half (float2 type) or half (float type)
           int pr = j0 + r;
           if (pr >= NR) pr -= NR;
