@@ -70,6 +70,9 @@ constexpr int FBW_REFRESH_ROWS = 64;                    // rows between restarts
 constexpr int FBW_REFRESH = FBW_REFRESH_ROWS / FBW_RB;  // ... in blocks
 constexpr int FBW_NT = (FBW_A_WARPS + FBW_B_WARPS + FBW_C_WARPS) * 32;
 constexpr int FBW_PF_BLOCKS = 64 / FBW_RB;              // L2 prefetch distance in blocks (64 rows)
+#ifndef FBW_ADDR_WIDE
+#define FBW_ADDR_WIDE 1
+#endif
 #ifndef FBW_UP_CARRY
 #define FBW_UP_CARRY 0  // 1: carry the interpolated coarse rows down a column in upsample mode -- measured 10 % SLOWER for
 #endif                  // those launches (the conditional loads no longer overlap with the previous row)
@@ -241,6 +244,23 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
     int pitb = h > 1 ? pitch : 0;                       // keeps the unused bottom-corner loads in bounds
     int thr = xb_border ? 0 : h - 10;                   // (unsigned)(y - 5) >= thr  <=>  border pixel
     pin(rb); pin(c_r0b); pin(c_r1a); pin(c_r1b); pin(fi); pin(wm1); pin(hm1); pin(pit); pin(pitb); pin(thr);
+#if FBW_ADDR_WIDE
+    // four 64-bit plane bases: every address is one IMAD.WIDE (FMA pipe) instead of LEA + IADD3 + IADD3.X (ALU pipe)
+    const float4* R0A = (const float4*)base0;
+    const float* R0E = base0 + 4 * a.plane_stride;
+    const float4* R1A = (const float4*)(base0 + a.r_frame_stride);
+    const float* R1E = base0 + a.r_frame_stride + 4 * a.plane_stride;
+    pin(R0A); pin(R0E); pin(R1A); pin(R1E);
+#define FB_R0A(o) (R0A + (unsigned)(o))
+#define FB_R0E(o) (R0E + (unsigned)(o))
+#define FB_R1A(o) (R1A + (unsigned)(o))
+#define FB_R1E(o) (R1E + (unsigned)(o))
+#else
+#define FB_R0A(o) ((const float4*)(rb + (unsigned)(o) * 16u))
+#define FB_R0E(o) ((const float*)(rb + ((unsigned)(o) * 4u + c_r0b)))
+#define FB_R1A(o) ((const float4*)(rb + ((unsigned)(o) * 16u + c_r1a)))
+#define FB_R1E(o) ((const float*)(rb + ((unsigned)(o) * 4u + c_r1b)))
+#endif
 
     int j0 = 0;                                         // ring row (mod NR) of the first new M row of the block
     for (int s = 0; s < nblk; ++s) {
@@ -306,8 +326,8 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
         float2 dA = fetch(oA, yA), dB = dA;
         auto rowf = [&](const float2 d, float2& dn, const int y, int& yn, const int o, int& on, bool has_next,
                         FbCorner& top, FbCorner& bot) {
-          const float4 q = ldg_f4<0>((const float4*)(rb + (unsigned)o * 16u));
-          const float q4 = ldg_f1<0>((const float*)(rb + ((unsigned)o * 4u + c_r0b)));
+          const float4 q = ldg_f4<0>(FB_R0A(o));
+          const float q4 = ldg_f1<0>(FB_R0E(o));
           if (has_next) { next_row(yn, on); dn = fetch(on, yn); }
           float fx = xf + d.x, fy = (float)y + d.y;
           const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
@@ -315,14 +335,14 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
           const bool inside = (unsigned)x1 < (unsigned)wm1 && (unsigned)y1 < (unsigned)hm1;
           const int ot = inside ? y1 * pit + x1 : 0;
           if (ot != o_carry) {
-            const float4* pa = (const float4*)(rb + ((unsigned)ot * 16u + c_r1a));
-            const float* pe = (const float*)(rb + ((unsigned)ot * 4u + c_r1b));
+            const float4* pa = FB_R1A(ot);
+            const float* pe = FB_R1E(ot);
             top.a0 = ldg_f4<0>(pa); top.a1 = ldg_f4<16>(pa); top.e0 = ldg_f1<0>(pe); top.e1 = ldg_f1<4>(pe);
           }
           const int ob = ot + pitb;
           {
-            const float4* pa = (const float4*)(rb + ((unsigned)ob * 16u + c_r1a));
-            const float* pe = (const float*)(rb + ((unsigned)ob * 4u + c_r1b));
+            const float4* pa = FB_R1A(ob);
+            const float* pe = FB_R1E(ob);
             bot.a0 = ldg_f4<0>(pa); bot.a1 = ldg_f4<16>(pa); bot.e0 = ldg_f1<0>(pe); bot.e1 = ldg_f1<4>(pe);
           }
           o_carry = ob;
