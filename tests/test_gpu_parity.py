@@ -14,6 +14,7 @@ from conftest import epe, have_cv2
 pytestmark = pytest.mark.gpu
 
 FB_MEAN_TOL, FB_MAX_TOL = 0.02, 0.5     # north_star tolerance
+REAL_MEAN_GUARD, REAL_MAX_GUARD = 2.5e-4, 0.07   # real footage (flows up to 96 px): about twice the measured worst case
 LK_STATUS_TOL, LK_POS_TOL = 0.995, 0.05
 MASK_TOL = 0.995
 REF_FB = (0.5, 3, 15, 3, 5, 1.2, 0)      # DenseOF.py:127-128
@@ -123,7 +124,8 @@ def test_farneback_golden_real_crops(b2, crops, i):
     assert flow.shape == (360, 640, 2) and flow.dtype == np.float32
     mean, mx = epe(flow[::4, ::4], crops[f"flow_s4_{i}"])
     assert mean <= FB_MEAN_TOL and mx <= FB_MAX_TOL, (mean, mx)
-    assert mean <= 1e-3 and mx <= 0.1, ("regression guard", mean, mx)
+    # measured on B200 (scripts/gpu_epe_report.py): mean 3.9e-6 .. 1.0e-4, max 4.8e-4 .. 0.030 px over the four crops
+    assert mean <= REAL_MEAN_GUARD and mx <= REAL_MAX_GUARD, ("regression guard", mean, mx)
 
 
 def test_farneback_golden_full_1080p(b2, full1080):
@@ -131,7 +133,7 @@ def test_farneback_golden_full_1080p(b2, full1080):
     flow = b2.calcOpticalFlowFarneback(g0, g1, None, *REF_FB)
     mean, mx = epe(flow[::8, ::8], full1080["flow_s8"])
     assert mean <= FB_MEAN_TOL and mx <= FB_MAX_TOL, (mean, mx)
-    assert mean <= 1e-3 and mx <= 0.1, ("regression guard", mean, mx)
+    assert mean <= REAL_MEAN_GUARD and mx <= REAL_MAX_GUARD, ("regression guard", mean, mx)   # measured 5.8e-5 / 0.031
 
 
 @pytest.mark.parametrize("name", ["ref", "gauss", "p08", "even", "sig0"])
