@@ -598,6 +598,77 @@ static void launch_level_regular(const LevelRegArgs& ra, int frames, cudaStream_
 
 
 // ----------------------------------------------------------------------------------------------
+// K3 (full-resolution level, streaming form): the regular (K, S) = (3, 1) level -- a 3-tap blur, no resampling -- is a
+// pure byte-in / float-out stream (N + 4 N bytes per frame), and the tile kernel above spends it on two shared-memory
+// passes and two barriers.  Here a thread owns four adjacent columns (one aligned 32-bit load per row, one 16-byte
+// store per row) and walks down L0_TH rows: the horizontal pass runs on the thread's own four bytes plus one byte
+// from each neighbour lane (shuffle; the first / last lane of a warp fetches the neighbouring word itself, at the
+// image border the reflected pixel is one of the thread's own bytes), the vertical pass on the three most recent
+// filtered rows in registers.  Eight row loads are in flight per thread.  Same taps and the same fused multiply-add
+// order as fb_level_regular<3, 1>: bit-identical.
+// ----------------------------------------------------------------------------------------------
+constexpr int L0_TH = 30;                 // output rows per thread (32 input rows = four groups of eight loads)
+constexpr int L0_WARPS = 5;               // warps per CTA, side by side: 640 columns (1920 = 3 x 640)
+struct Level0Args {
+  const uint8_t* frames; size_t step, frame_stride; int W, H;
+  float* I; int pitch; size_t i_frame_stride;
+  float c0, c1, c2;
+};
+
+__global__ void __launch_bounds__(32 * L0_WARPS) fb_level0_stream(Level0Args a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gx = (blockIdx.x * L0_WARPS + warp) * 128 + 4 * lane;    // first of this thread's four columns
+  if (gx - 4 * lane >= a.W) return;                                    // whole warp beyond the row
+  const int y0 = blockIdx.y * L0_TH;
+  const uint8_t* fb = a.frames + blockIdx.z * a.frame_stride;
+  float* ob = a.I + blockIdx.z * a.i_frame_stride + gx;
+  const bool live = gx < a.W;                                          // W % 4 == 0: a word is inside or outside
+  const int gxc = live ? gx : a.W - 4;                                 // idle lanes re-read the last word
+  const bool left_edge = gxc == 0, right_edge = gxc + 4 >= a.W;
+  const float c0 = a.c0, c1 = a.c1, c2 = a.c2;
+  float4 hA = make_float4(0.f, 0.f, 0.f, 0.f), hB = hA;
+#pragma unroll 1
+  for (int g = 0; g < (L0_TH + 2) / 8; ++g) {
+    uint32_t wv[8], we[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint8_t* row = fb + (size_t)reflect101(y0 - 1 + 8 * g + k, a.H) * a.step;
+      wv[k] = __ldg((const uint32_t*)(row + gxc));
+      we[k] = 0u;
+      if (lane == 0 && !left_edge) we[k] = __ldg((const uint32_t*)(row + gxc - 4));
+      if (lane == 31 && !right_edge) we[k] = __ldg((const uint32_t*)(row + gxc + 4));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t w = wv[k];
+      uint32_t wl = __shfl_up_sync(0xffffffffu, w, 1), wr = __shfl_down_sync(0xffffffffu, w, 1);
+      if (lane == 0) wl = we[k];
+      if (lane == 31) wr = we[k];
+      if (left_edge) wl = w << 16;                                     // reflect101: column -1 is column 1
+      if (right_edge) wr = w >> 16;                                    // column W is column W - 2
+      const float pm = (float)(wl >> 24), p0 = (float)(w & 255u), p1 = (float)((w >> 8) & 255u),
+                  p2 = (float)((w >> 16) & 255u), p3 = (float)(w >> 24), p4 = (float)(wr & 255u);
+      float4 hC;
+      hC.x = fmaf(c2, p1, fmaf(c1, p0, c0 * pm));
+      hC.y = fmaf(c2, p2, fmaf(c1, p1, c0 * p0));
+      hC.z = fmaf(c2, p3, fmaf(c1, p2, c0 * p1));
+      hC.w = fmaf(c2, p4, fmaf(c1, p3, c0 * p2));
+      const int i = 8 * g + k;                                         // input row y0 - 1 + i; output row y0 + i - 2
+      const int yo = y0 + i - 2;
+      if (i >= 2 && yo < a.H && live) {
+        float4 o;
+        o.x = fmaf(c2, hC.x, fmaf(c1, hB.x, c0 * hA.x));
+        o.y = fmaf(c2, hC.y, fmaf(c1, hB.y, c0 * hA.y));
+        o.z = fmaf(c2, hC.z, fmaf(c1, hB.z, c0 * hA.z));
+        o.w = fmaf(c2, hC.w, fmaf(c1, hB.w, c0 * hA.w));
+        *(float4*)(ob + (size_t)yo * a.pitch) = o;
+      }
+      hA = hB; hB = hC;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // K3 (coarse levels in one pass): the reference's pyramid (pyr_scale 0.5, three coarse levels) filters the SAME
 // full-resolution frame three times with the regular (K, S) forms (4, 2), (10, 4), (20, 8).  One CTA stages the
 // source region of an 8 x 8 tile of the coarsest level once -- as floats, one conversion per byte instead of one per
@@ -1587,7 +1658,11 @@ static int fb_frames(const FbPlan* pl, const FbWorkspace& ws, const uint8_t* fra
       memcpy(ra.c, L.r_c, sizeof ra.c);
       {
         ProfScope ps(PT_FB_LEVEL_H, st, (double)frames * ((double)W * H + 4.0 * L.h * L.w));
-        if (L.r_K == 3) launch_level_regular<3, 1>(ra, frames, st);
+        if (L.r_K == 3 && L.r_S == 1 && L.r_c0 == -1 && L.w == W && L.h == H && W % 4 == 0 && W >= 8 && H >= 2 &&
+            ((step | frame_stride | (size_t)frames_dev) & 3) == 0) {
+          Level0Args la{frames_dev, step, frame_stride, W, H, Ib, L.pitch, i_stride, L.r_c[0], L.r_c[1], L.r_c[2]};
+          fb_level0_stream<<<dim3(cdiv(W, 128 * L0_WARPS), cdiv(H, L0_TH), frames), 32 * L0_WARPS, 0, st>>>(la);
+        } else if (L.r_K == 3) launch_level_regular<3, 1>(ra, frames, st);
         else if (L.r_K == 4) launch_level_regular<4, 2>(ra, frames, st);
         else if (L.r_K == 10) launch_level_regular<10, 4>(ra, frames, st);
         else launch_level_regular<20, 8>(ra, frames, st);
@@ -1808,7 +1883,13 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
           // warp-specialised strip kernel: one CTA per SM, 112-column strips, nseg row segments of nb 16-row blocks
           // (at least two waves of CTAs when the batch is small)
           IterArgs b = a;
+#if FBW_PAIR
+          const int nstrips = 2 * cdiv(L.w, 2 * FBS_TW), blocks = cdiv(L.h, FBW_RB);   // CTA pairs (cluster 1 x 2 x 1)
+#elif defined(FBW_CLUSTER_ONLY)
+          const int nstrips = 2 * cdiv(cdiv(L.w, FBS_TW), 2), blocks = cdiv(L.h, FBW_RB);
+#else
           const int nstrips = cdiv(L.w, FBS_TW), blocks = cdiv(L.h, FBW_RB);
+#endif
           // row segments: the split that minimises (waves of CTAs) x (rows per CTA + the 30 rows of pipeline fill
           // and halo); nb is a multiple of the refresh period, so results do not depend on the split or the batch
           int best_nb = cdiv(blocks, FBW_REFRESH) * FBW_REFRESH;

@@ -46,15 +46,33 @@ constexpr int FBW_A_WARPS = 12;
 constexpr int FBW_B_WARPS = 2;
 constexpr int FBW_C_WARPS = 6;
 #else
-constexpr int FBS_EW = 128;
-constexpr int FBW_A_WARPS = 16;
+#ifndef FBW_EW_N
+#define FBW_EW_N 128
+#endif
+constexpr int FBS_EW = FBW_EW_N;
+constexpr int FBW_A_WARPS = FBW_EW_N / 8;  // four row runs of EW columns
 constexpr int FBW_B_WARPS = 4;
 constexpr int FBW_C_WARPS = 4;
 #endif
 constexpr int FBS_M = 7;                  // window radius
 constexpr int FBS_PADL = 8;               // halo column 0 sits at image column x0 - 8 (8-pixel aligned)
+#ifndef FBW_PAIR
+#define FBW_PAIR 0
+#endif
+// FBW_PAIR: two CTAs of a cluster share a 240-column strip.  Each computes UpdateMatrices for 128 columns (left CTA:
+// image columns [X0 - 8, X0 + 120), right CTA: [X0 + 120, X0 + 248)) and owns 120 output columns; the 7 columns of M
+// its horizontal sums need from the other side arrive in its ring through st.async (DSMEM) from the neighbour's A
+// warps, whose completion bytes are part of the block's full_a barrier.  1920 columns = 8 pairs = 16 CTAs per row of
+// strips instead of 18, and step A computes 256 columns per 240 outputs instead of 128 per 112.
+#if FBW_PAIR
+constexpr int FBS_TW = 120;               // output columns per CTA
+constexpr int FBS_HALO = 7;               // columns received from the neighbour
+constexpr int FBS_ES = FBS_EW + FBS_HALO; // 135: own columns at [7 * rank, 7 * rank + 128), the neighbour's 7 beside them
+static_assert(FBS_EW == 128 && (FBS_ES & 1), "pair geometry");
+#else
 constexpr int FBS_TW = FBS_EW - 16;       // output columns per strip
 constexpr int FBS_ES = FBS_EW + 1;        // plane row stride in elements (odd)
+#endif
 #ifndef FBS_HL_N
 #define FBS_HL_N (FBS_TW / 2)
 #endif
@@ -85,7 +103,10 @@ constexpr int FBW_PF_BLOCKS = 64 / FBW_RB;              // L2 prefetch distance 
 constexpr int FBW_STAGES = FBW_STAGES_N;                // blocks in flight between step A and step C
 constexpr int FBW_NR = 2 * FBS_M + FBW_STAGES * FBW_RB; // ring rows
 constexpr size_t FBW_PLANES = (size_t)FBW_NR * FBS_ES * 20;
-constexpr size_t FBW_SMEM = FBW_PLANES + 3 * FBW_STAGES * 8 + 16;   // + mbarriers
+#ifndef FBW_SMEM_PAD
+#define FBW_SMEM_PAD 0   // experiment: extra dynamic shared memory (pushes the carve-out to the next step: 64 -> 32 KB of L1)
+#endif
+constexpr size_t FBW_SMEM = FBW_PLANES + 3 * FBW_STAGES * 8 + 16 + FBW_SMEM_PAD;   // + mbarriers
 static_assert(FBW_A_WARPS * 32 % FBS_EW == 0, "step A: whole row runs");
 static_assert(FBS_TW <= FBW_C_WARPS * 32, "step C: one thread per output column");
 
@@ -112,6 +133,41 @@ __device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
       "@!p bra W_%=;\n"
       "D_%=: }" ::"r"(addr), "r"(parity), "n"(200) : "memory");
 }
+
+#if FBW_PAIR
+__device__ __forceinline__ unsigned cluster_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// this thread's arrival on a local mbarrier, announcing `bytes` of st.async traffic for the current phase
+__device__ __forceinline__ void mbar_arrive_expect(unsigned addr, unsigned bytes) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(addr), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(unsigned cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// store into the neighbour's shared memory; the bytes are counted on the neighbour's mbarrier when they land
+__device__ __forceinline__ void st_async_f2(unsigned cluster_addr, float x, float y, unsigned cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1,%2}, [%3];" ::"r"(
+                   cluster_addr), "f"(x), "f"(y), "r"(cluster_bar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_f1(unsigned cluster_addr, float x, unsigned cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(cluster_addr),
+               "f"(x), "r"(cluster_bar)
+               : "memory");
+}
+#endif
 
 __device__ __forceinline__ float rcp_approx(float x) {     // 1 ulp; the determinant is >= 1e-3 / inv_area^2 > 0
   float r;
@@ -186,8 +242,15 @@ __device__ __forceinline__ void hpass_half_row(T* rowp, bool right, int nv) {
   }
 }
 
+#ifdef FBW_MAXNREG
+#define FBW_BOUNDS __maxnreg__(FBW_MAXNREG)
+#elif FBW_PAIR || defined(FBW_CLUSTER_ONLY)
+#define FBW_BOUNDS __cluster_dims__(1, 2, 1) __launch_bounds__(FBW_NT, 1)
+#else
+#define FBW_BOUNDS __launch_bounds__(FBW_NT, 1)
+#endif
 template <int MODE, bool STATS>
-__global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
+__global__ void FBW_BOUNDS fb_iter_ws(IterArgs a) {
   extern __shared__ __align__(16) float smem[];
   constexpr int EW = FBS_EW, TW = FBS_TW, M = FBS_M, RB = FBW_RB, NR = FBW_NR, ES = FBS_ES, HL = FBS_HL;
   constexpr int NA = FBW_A_WARPS * 32, NB = FBW_B_WARPS * 32, NC = FBW_C_WARPS * 32;
@@ -199,23 +262,45 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
   const unsigned s_e = s_zw + NR * ES * 8;
   const unsigned s_bar = s_xy + (unsigned)FBW_PLANES;   // full_a[], full_b[], empty_c[]
   const int pair = blockIdx.x;                          // pair index fastest (frame p + 1 shared through L2)
+#if FBW_PAIR
+  const int rank = (int)cluster_rank();                 // 0: left CTA of the pair, 1: right (== blockIdx.y & 1)
+  const int x0 = (blockIdx.y >> 1) * (2 * TW) + rank * TW;          // first output column
+  const int xa = rank ? x0 : x0 - FBS_PADL;                         // image column of halo column 0
+  const int uoff = rank * FBS_HALO;                                 // ring index of halo column 0
+  const int woff = 1 - rank;                            // ring index where output 0's window starts
+#else
   const int x0 = blockIdx.y * TW;
+  const int xa = x0 - FBS_PADL;
+  constexpr int uoff = 0, woff = 1;
+#endif
   const int w = a.w, h = a.h, pitch = a.pitch;
   const int ys = blockIdx.z * a.nb * RB;                // rows [ys, ye) are this CTA's outputs
   const int ye = min(ys + a.nb * RB, h);
   const int nblk = (ye - ys + RB - 1) / RB;
   const int t = threadIdx.x;
-  const int nv = min(TW, w - x0);                       // outputs of this strip (the last strip of a row is narrower)
+  const int nv = max(min(TW, w - x0), 0);               // outputs of this strip (the last strip of a row is narrower)
 
   if (t == 0) {
     for (int i = 0; i < FBW_STAGES; ++i) {
       mbar_init(s_bar + i * 8, NA);                     // full_a: every A thread arrives
       mbar_init(s_bar + (FBW_STAGES + i) * 8, NB);      // full_b
+#if FBW_PAIR
+#ifdef FBW_PAIR_NOREMOTE   // timing experiment: the neighbour's step C is not waited for (racy)
+      mbar_init(s_bar + (2 * FBW_STAGES + i) * 8, NC);
+#else
+      mbar_init(s_bar + (2 * FBW_STAGES + i) * 8, NC + FBW_C_WARPS);   // empty_c: + one arrival per C warp next door
+#endif
+#else
       mbar_init(s_bar + (2 * FBW_STAGES + i) * 8, NC);  // empty_c
+#endif
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+#if FBW_PAIR
+  cluster_sync_all();                                   // both CTAs' barriers exist before anything is sent across
+#else
   __syncthreads();
+#endif
 
   if (t < NA) {
     // =========================== A warps: UpdateMatrices ===========================
@@ -225,8 +310,24 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
     const int run = t / EW, cx = t - run * EW;
     // halo columns [PADL - M, PADL + nv + M) feed this strip's outputs: a warp whose 32 columns lie beyond them only
     // passes the barriers on (last strip of a row)
+#if FBW_PAIR
+    // columns 121..127 of the left CTA / 0..6 of the right one are also the neighbour's halo: their warps always work
+#ifdef FBW_PAIR_NOPUSH   // timing experiment: nothing is sent (wrong results)
+    const bool a_push = false;
+#else
+    const bool a_push = rank ? cx < FBS_HALO : cx >= EW - FBS_HALO;
+#endif
+    const bool a_on = rank ? (cx < 32 || (cx & ~31) < nv + FBS_M) : (cx >= EW - 32 || (cx & ~31) < FBS_PADL + nv + FBS_M);
+    const unsigned nbr = (unsigned)(rank ^ 1);
+    // neighbour's ring element = mine +- 121; its shared-memory window is laid out like this CTA's, so one mapped
+    // base serves the three planes and the barriers
+    const unsigned r_xy = mapa_u32(s_xy, nbr) + (rank ? 8 * (EW - FBS_HALO) : -8 * (EW - FBS_HALO));
+    const unsigned r_e = mapa_u32(s_e, nbr) + (rank ? 4 * (EW - FBS_HALO) : -4 * (EW - FBS_HALO));
+    const unsigned r_bar = mapa_u32(s_bar, nbr);
+#else
     const bool a_on = (cx & ~31) < FBS_PADL + nv + FBS_M;
-    const int x = clampi(x0 - FBS_PADL + cx, 0, w - 1);
+#endif
+    const int x = clampi(xa + cx, 0, w - 1);
     const float xf = (float)x;
     const bool xb_border = (unsigned)(x - 5) >= (unsigned)(w - 10);   // cv2's own (unsigned) test
     const float bwx = border_w(x, w);
@@ -276,8 +377,11 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
       if (!(FBW_SKIP & 1) && n > 0 && a_on) {
         int pr = j0 + l0;
         if (pr >= NR) pr -= NR;
-        unsigned sa = (unsigned)(pr * ES + cx);         // element index into the planes
-        const unsigned sa_end = (unsigned)(NR * ES + cx);
+        unsigned sa = (unsigned)(pr * ES + cx + uoff);  // element index into the planes
+        const unsigned sa_end = (unsigned)(NR * ES + cx + uoff);
+#if FBW_PAIR
+        const unsigned r_full = r_bar + (s % FBW_STAGES) * 8;   // the neighbour's full_a[stage]
+#endif
         int yu = y_first + l0;                          // unclamped image row of the row being set up
 
         auto next_row = [&](int& y, int& o) {
@@ -369,9 +473,18 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
             const float sc = bwx * border_w(y, h);
             r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
           }
-          sts_f2(s_xy + sa * 8, r4 * r4 + r6 * r6, (r4 + r5) * r6);
-          sts_f2(s_zw + sa * 8, r5 * r5 + r6 * r6, r4 * r2 + r6 * r3);
-          sts_f1(s_e + sa * 4, r6 * r2 + r5 * r3);
+          const float m0 = r4 * r4 + r6 * r6, m1 = (r4 + r5) * r6, m2 = r5 * r5 + r6 * r6, m3 = r4 * r2 + r6 * r3;
+          const float m4 = r6 * r2 + r5 * r3;
+          sts_f2(s_xy + sa * 8, m0, m1);
+          sts_f2(s_zw + sa * 8, m2, m3);
+          sts_f1(s_e + sa * 4, m4);
+#if FBW_PAIR
+          if (a_push) {
+            st_async_f2(r_xy + sa * 8, m0, m1, r_full);
+            st_async_f2(r_xy + sa * 8 + NR * ES * 8, m2, m3, r_full);
+            st_async_f1(r_e + sa * 4, m4, r_full);
+          }
+#endif
           sa += ES;
           if (sa == sa_end) sa -= NR * ES;
         };
@@ -382,6 +495,15 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
         }
         if (k < n) rowf(dA, dB, yA, yB, oA, oB, false, cA, cB);
       }
+#if FBW_PAIR
+      // thread 0's arrival also announces the neighbour's 7 columns x nrows x 20 bytes
+#ifdef FBW_PAIR_NOPUSH
+      if (t == 0) mbar_arrive(s_bar + (s % FBW_STAGES) * 8);
+#else
+      if (t == 0) mbar_arrive_expect(s_bar + (s % FBW_STAGES) * 8, (unsigned)(FBS_HALO * 20 * nrows));
+#endif
+      else
+#endif
       mbar_arrive(s_bar + (s % FBW_STAGES) * 8);        // full_a[stage]: block s is in the ring
       j0 += nrows;
       if (j0 >= NR) j0 -= NR;
@@ -409,11 +531,11 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
           if (pr >= NR) pr -= NR;
           const bool right = q & 1;
           if (nv == TW) {
-            if (wide) hpass_half_row<float2, true>((q & 2 ? Pzw : Pxy) + pr * ES + 1, right, nv);
-            else hpass_half_row<float, true>(Pe + pr * ES + 1, right, nv);
+            if (wide) hpass_half_row<float2, true>((q & 2 ? Pzw : Pxy) + pr * ES + woff, right, nv);
+            else hpass_half_row<float, true>(Pe + pr * ES + woff, right, nv);
           } else {
-            if (wide) hpass_half_row<float2, false>((q & 2 ? Pzw : Pxy) + pr * ES + 1, right, nv);
-            else hpass_half_row<float, false>(Pe + pr * ES + 1, right, nv);
+            if (wide) hpass_half_row<float2, false>((q & 2 ? Pzw : Pxy) + pr * ES + woff, right, nv);
+            else hpass_half_row<float, false>(Pe + pr * ES + woff, right, nv);
           }
         }
       }
@@ -425,7 +547,10 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
     // =========================== C warps: vertical running sums + solve ===========================
     const int ct = t - NA - NB;
     const bool act = ct < TW && x0 + ct < w;
-    const int col = 1 + (ct < HL ? ct : ct + 2 * M);    // where step B left this column's sums
+    const int col = woff + (ct < HL ? ct : ct + 2 * M); // where step B left this column's sums
+#if FBW_PAIR
+    const unsigned r_empty = mapa_u32(s_bar + 2 * FBW_STAGES * 8, (unsigned)(rank ^ 1));   // the neighbour's empty_c[]
+#endif
     float2* __restrict__ fo = a.flow_out + (size_t)pair * a.flow_out_pair_stride;
     float2 vxy = make_float2(0.f, 0.f), vzw = vxy;
     float ve = 0.f;
@@ -441,11 +566,11 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
     const char* pf_r0 = (const char*)(a.R + (size_t)pair * a.pair_frame_step * a.r_frame_stride);
     const char* pf_fl = MODE == 1 ? (const char*)(a.flow_in + (size_t)pair * a.flow_in_pair_stride) : nullptr;
     const size_t pf_r1 = (size_t)4 * a.r_frame_stride, pf_e = (size_t)16 * a.plane_stride;
-    const int pf_xs = max(x0 - FBS_PADL, 0);
+    const int pf_xs = max(xa, 0);
     const int pf_cols = min(EW, pitch - pf_xs);
     const int cwu = __shfl_sync(0xffffffffu, ct >> 5, 0);
     auto prefetch_block = [&](int sb) {                 // rows of M that block sb adds: image rows [y0, y0 + nrows)
-      if (sb >= nblk || (ct & 31) != 0) return;
+      if (sb >= nblk || (ct & 31) != 0 || pf_cols <= 0) return;
       const int nrows = sb == 0 ? 2 * M + RB : RB;
       const int y0 = sb == 0 ? ys - M : ys + sb * RB + M;
       for (int r = cwu; r < nrows; r += FBW_C_WARPS) {
@@ -537,6 +662,14 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
         }
       }
       mbar_arrive(s_bar + (2 * FBW_STAGES + s % FBW_STAGES) * 8);   // empty_c[stage]: its oldest rows may be reused
+#if FBW_PAIR
+      // ... and the neighbour's step A may overwrite the halo columns it sent for this block (step B read them before
+      // it released full_b): one arrival per C warp on the neighbour's empty_c[stage]
+      __syncwarp();
+#ifndef FBW_PAIR_NOREMOTE
+      if ((ct & 31) == 0) mbar_arrive_remote(r_empty + (s % FBW_STAGES) * 8);
+#endif
+#endif
       prefetch_block(s + FBW_PF_BLOCKS);
       po += RB;
       if (po >= NR) po -= NR;
@@ -578,4 +711,7 @@ __global__ void __launch_bounds__(FBW_NT, 1) fb_iter_ws(IterArgs a) {
       }
     }
   }
+#if FBW_PAIR
+  cluster_sync_all();                                   // neither CTA leaves while the other may still send to it
+#endif
 }

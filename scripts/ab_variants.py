@@ -42,10 +42,14 @@ def main():
         env = dict(os.environ)
         if name != "default":
             env["B2OF_LIB"] = vpath(name)
-        r1 = subprocess.run([sys.executable, "-c", CHECK], env=env, capture_output=True, text=True)
+        try:
+            r1 = subprocess.run([sys.executable, "-c", CHECK], env=env, capture_output=True, text=True, timeout=180)
+        except subprocess.TimeoutExpired:
+            print(json.dumps({"name": name, "err": "parity check timed out (hang?)"}))
+            continue
         par = [l for l in r1.stdout.splitlines() if l.startswith("PARITY")]
         r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", steps, "--warmup", "3", "--no-cpu",
-                             "--no-e2e"], env=env, capture_output=True, text=True)
+                             "--no-e2e", "--no-extras"], env=env, capture_output=True, text=True, timeout=300)
         line = None
         for l in r2.stdout.splitlines():
             if l.startswith("{"):
