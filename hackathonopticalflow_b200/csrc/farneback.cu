@@ -627,17 +627,22 @@ __global__ void __launch_bounds__(32 * L0_WARPS) fb_level0_stream(Level0Args a) 
   const bool left_edge = gxc == 0, right_edge = gxc + 4 >= a.W;
   const float c0 = a.c0, c1 = a.c1, c2 = a.c2;
   float4 hA = make_float4(0.f, 0.f, 0.f, 0.f), hB = hA;
-#pragma unroll 1
-  for (int g = 0; g < (L0_TH + 2) / 8; ++g) {
-    uint32_t wv[8], we[8];
+  uint32_t wv[8], we[8], wn[8], wen[8];
+  auto load_group = [&](int g, uint32_t* dv, uint32_t* de) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const uint8_t* row = fb + (size_t)reflect101(y0 - 1 + 8 * g + k, a.H) * a.step;
-      wv[k] = __ldg((const uint32_t*)(row + gxc));
-      we[k] = 0u;
-      if (lane == 0 && !left_edge) we[k] = __ldg((const uint32_t*)(row + gxc - 4));
-      if (lane == 31 && !right_edge) we[k] = __ldg((const uint32_t*)(row + gxc + 4));
+      dv[k] = __ldg((const uint32_t*)(row + gxc));
+      de[k] = 0u;
+      if (lane == 0 && !left_edge) de[k] = __ldg((const uint32_t*)(row + gxc - 4));
+      if (lane == 31 && !right_edge) de[k] = __ldg((const uint32_t*)(row + gxc + 4));
     }
+  };
+  load_group(0, wv, we);
+  constexpr int NG = (L0_TH + 2) / 8;
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    if (g + 1 < NG) load_group(g + 1, wn, wen);          // the next eight rows are in flight while these are filtered
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const uint32_t w = wv[k];
@@ -665,6 +670,8 @@ __global__ void __launch_bounds__(32 * L0_WARPS) fb_level0_stream(Level0Args a) 
       }
       hA = hB; hB = hC;
     }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { wv[k] = wn[k]; we[k] = wen[k]; }
   }
 }
 
@@ -730,17 +737,30 @@ __global__ void __launch_bounds__(LC_NT) fb_levels_coarse(LevelCoarseArgs a) {
   const int gx0 = 64 * blockIdx.x - 8, gy0 = 64 * blockIdx.y - 6;
   constexpr int NW = (LC_LPAD + LC_REG + 3) / 4;      // 20 words per region row
   const uint8_t* fb = a.frames + blockIdx.z * a.frame_stride;
-  const bool inside = gx0 >= 0 && gy0 >= 0 && gx0 + 4 * NW <= a.W && gy0 + LC_REG <= a.H &&
-                      ((a.step | (size_t)fb) & 3) == 0;
-  if (inside) {
-    // aligned 4-byte loads, all of them in flight before the first conversion
+  // aligned 4-byte loads, all of them in flight before the first conversion.  Rows are reflected per word (in range:
+  // one compare); a word with a column outside the frame (the first two / last few words of a region row in the
+  // CTAs of the first / last column of the grid) is assembled from four reflected byte loads.  (The first version
+  // sent every CTA that touches the frame border -- 18 % of them at 1080p -- down a byte-per-thread path with a full
+  // reflect per byte, which cost more than all the interior CTAs' staging together.)
+  {
+    const bool aligned = ((a.step | (size_t)fb) & 3) == 0;
     constexpr int PER = (LC_REG * NW + LC_NT - 1) / LC_NT;
     uint32_t wv[PER];
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
       const int i = t + LC_NT * k;
       const int rr = i / NW, wc = i - rr * NW;
-      wv[k] = i < LC_REG * NW ? __ldg((const uint32_t*)(fb + (size_t)(gy0 + rr) * a.step + gx0) + wc) : 0u;
+      wv[k] = 0u;
+      if (i < LC_REG * NW) {
+        const uint8_t* row = fb + (size_t)reflect101(gy0 + rr, a.H) * a.step;
+        const int gx = gx0 + 4 * wc;
+        if (aligned && gx >= 0 && gx + 4 <= a.W) {
+          wv[k] = __ldg((const uint32_t*)(row + gx));
+        } else {
+          wv[k] = (uint32_t)row[reflect101(gx, a.W)] | ((uint32_t)row[reflect101(gx + 1, a.W)] << 8) |
+                  ((uint32_t)row[reflect101(gx + 2, a.W)] << 16) | ((uint32_t)row[reflect101(gx + 3, a.W)] << 24);
+        }
+      }
     }
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
@@ -749,11 +769,6 @@ __global__ void __launch_bounds__(LC_NT) fb_levels_coarse(LevelCoarseArgs a) {
       if (i < LC_REG * NW)
         *(float4*)(s_src + rr * LC_RP + 4 * wc) = make_float4((float)(wv[k] & 255u), (float)((wv[k] >> 8) & 255u),
                                                               (float)((wv[k] >> 16) & 255u), (float)(wv[k] >> 24));
-    }
-  } else {
-    for (int rr = warp; rr < LC_REG; rr += LC_NT / 32) {
-      const uint8_t* row = fb + (size_t)reflect101(gy0 + rr, a.H) * a.step;
-      for (int cc = lane; cc < 4 * NW; cc += 32) s_src[rr * LC_RP + cc] = (float)row[reflect101(gx0 + cc, a.W)];
     }
   }
   __syncthreads();
@@ -1012,6 +1027,175 @@ __global__ void __launch_bounds__(320) fb_polyexp_n(const float* __restrict__ I,
         *(float2*)(rb1 + o) = make_float2(ob[0], ob[1]);   // o is even: pitch % 32 == 0, gx even
       } else {
         rb1[o] = ob[0];
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K4 (packed form, the one that runs for poly_n = 5 / 7): fb_polyexp_n is issue-bound (77 % of the issue slots, more
+// than half of them FFMA / FADD), so this form does the same arithmetic two rows at a time in packed f32x2
+// instructions (FFMA2 / FADD2 / FMUL2: one issue slot, two IEEE operations -- same operations, same order, same bits).
+// The pairing is across ROWS r and r + 16 of the 64 x 32 tile, because a pair of rows slides through both filters
+// together (pairing adjacent columns or adjacent rows would need the window at two alignments):
+//   phase 1: thread = (halo column, 8-row segment of the upper AND of the lower half tile); the 2 x 18 input values
+//            are loaded as the two halves of 18 register pairs, the three vertical filters run packed, results go
+//            to shared memory as (row r, row r + 16) pairs: layout [channel][r & 15][column][r >> 4]
+//   phase 2: thread = two adjacent columns x (row r, row r + 16): six 16-byte LDS per channel bring the 12 window
+//            positions as ready-made register pairs; horizontal filters packed; the final scaling and the stores are
+//            scalar (a float4 of one row takes one half of four different pairs).
+// ----------------------------------------------------------------------------------------------
+#ifndef FB_POLY_MINB
+#define FB_POLY_MINB 4     // CTAs per SM the register allocation aims at (64 registers)
+#endif
+__device__ __forceinline__ float2 f2_bc(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 f2_neg(float2 v) { return make_float2(-v.x, -v.y); }
+
+template <int N>
+__global__ void __launch_bounds__(256, FB_POLY_MINB) fb_polyexp_p(const float* __restrict__ I, int w, int h, int pitch,
+                                                     size_t i_frame_stride, float* __restrict__ R,
+                                                     size_t plane_stride, size_t r_frame_stride, PolyConst pc) {
+  constexpr int CW = PE_TW + 2 * N;        // halo columns; column c is image column x0 - N + c
+  constexpr int HR = PE_TH / 2;            // rows per half tile: row r pairs with row r + HR
+  constexpr int SEG = 8, NSEG = HR / SEG;
+  static_assert(PE_TH == 32 && CW * NSEG <= 256 && (CW % 2) == 0, "tile geometry");
+  __shared__ __align__(16) float2 s_r[3][HR][CW];
+  const int x0 = blockIdx.x * PE_TW, y0 = blockIdx.y * PE_TH;
+  const float* ib = I + blockIdx.z * i_frame_stride;
+  const int t = threadIdx.x;
+  if (t < CW * NSEG) {
+    const int seg = t / CW, c = t - seg * CW;
+    const float* col = ib + clampi(x0 + c - N, 0, w - 1);
+    const int yb = y0 + seg * SEG - N;
+    float2 v[SEG + 2 * N];
+    if (y0 >= N && y0 + PE_TH + N <= h) {    // no row of the halo tile is clamped (uniform over the CTA)
+      const float* plo = col + (size_t)yb * pitch;
+      const float* phi = plo + (size_t)HR * pitch;
+#pragma unroll
+      for (int j = 0; j < SEG + 2 * N; ++j) {
+        v[j].x = plo[j * pitch];
+        v[j].y = phi[j * pitch];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < SEG + 2 * N; ++j) {
+        v[j].x = col[(size_t)clampi(yb + j, 0, h - 1) * pitch];
+        v[j].y = col[(size_t)clampi(yb + j + HR, 0, h - 1) * pitch];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < SEG; ++j) {
+      float2 r0 = __fmul2_rn(v[j + N], f2_bc(pc.g[0]));
+      float2 r1 = make_float2(0.f, 0.f), r2 = r1;
+#pragma unroll
+      for (int k = 1; k <= N; ++k) {
+        const float2 a = v[j + N - k], b = v[j + N + k];
+        const float2 sum = __fadd2_rn(a, b);
+        r0 = __ffma2_rn(f2_bc(pc.g[k]), sum, r0);
+        r1 = __ffma2_rn(f2_bc(pc.xg[k]), __fadd2_rn(b, f2_neg(a)), r1);
+        r2 = __ffma2_rn(f2_bc(pc.xxg[k]), sum, r2);
+      }
+      const int r = seg * SEG + j;
+      s_r[0][r][c] = r0; s_r[1][r][c] = r1; s_r[2][r][c] = r2;
+    }
+  }
+  __syncthreads();
+  {
+    const int warp = t >> 5, lane = t & 31;
+    const int xl = 2 * lane;                 // local x of the first of two outputs
+    const int gx = x0 + xl;
+    float* rb = R + blockIdx.z * r_frame_stride;
+    float4* ra4 = (float4*)rb;
+    float* rb1 = rb + 4 * plane_stride;
+    if (gx < w) {
+#pragma unroll 1
+      for (int r = warp; r < HR; r += 8) {
+        if (y0 + r >= h) break;
+        float2 b1[2], b2[2], b3[2], b4[2], b5[2], b6[2];
+        {
+          float2 p0[2 * N + 2];
+#pragma unroll
+          for (int q = 0; q < N + 1; ++q) {
+            const float4 f = *(const float4*)&s_r[0][r][xl + 2 * q];
+            p0[2 * q] = make_float2(f.x, f.y); p0[2 * q + 1] = make_float2(f.z, f.w);
+          }
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int ctr = e + N;
+            b1[e] = __fmul2_rn(p0[ctr], f2_bc(pc.g[0]));
+            b2[e] = make_float2(0.f, 0.f); b4[e] = b2[e];
+#pragma unroll
+            for (int k = 1; k <= N; ++k) {
+              const float2 tg = __fadd2_rn(p0[ctr + k], p0[ctr - k]);
+              b1[e] = __ffma2_rn(tg, f2_bc(pc.g[k]), b1[e]);
+              b4[e] = __ffma2_rn(tg, f2_bc(pc.xxg[k]), b4[e]);
+              b2[e] = __ffma2_rn(__fadd2_rn(p0[ctr + k], f2_neg(p0[ctr - k])), f2_bc(pc.xg[k]), b2[e]);
+            }
+          }
+        }
+        {
+          float2 p1[2 * N + 2];
+#pragma unroll
+          for (int q = 0; q < N + 1; ++q) {
+            const float4 f = *(const float4*)&s_r[1][r][xl + 2 * q];
+            p1[2 * q] = make_float2(f.x, f.y); p1[2 * q + 1] = make_float2(f.z, f.w);
+          }
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int ctr = e + N;
+            b3[e] = __fmul2_rn(p1[ctr], f2_bc(pc.g[0]));
+            b6[e] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 1; k <= N; ++k) {
+              b3[e] = __ffma2_rn(__fadd2_rn(p1[ctr + k], p1[ctr - k]), f2_bc(pc.g[k]), b3[e]);
+              b6[e] = __ffma2_rn(__fadd2_rn(p1[ctr + k], f2_neg(p1[ctr - k])), f2_bc(pc.xg[k]), b6[e]);
+            }
+          }
+        }
+        {
+          float2 p2[2 * N + 2];
+#pragma unroll
+          for (int q = 0; q < N + 1; ++q) {
+            const float4 f = *(const float4*)&s_r[2][r][xl + 2 * q];
+            p2[2 * q] = make_float2(f.x, f.y); p2[2 * q + 1] = make_float2(f.z, f.w);
+          }
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int ctr = e + N;
+            b5[e] = __fmul2_rn(p2[ctr], f2_bc(pc.g[0]));
+#pragma unroll
+            for (int k = 1; k <= N; ++k)
+              b5[e] = __ffma2_rn(__fadd2_rn(p2[ctr + k], p2[ctr - k]), f2_bc(pc.g[k]), b5[e]);
+          }
+        }
+        // final scaling and stores, one row of the pair at a time (scalar: same expressions as fb_polyexp_n)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int gy = y0 + r + hh * HR;
+          if (gy >= h) break;
+          float4 oa[2];
+          float ob[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float c1 = hh ? b1[e].y : b1[e].x, c2 = hh ? b2[e].y : b2[e].x, c3 = hh ? b3[e].y : b3[e].x;
+            const float c4 = hh ? b4[e].y : b4[e].x, c5 = hh ? b5[e].y : b5[e].x, c6 = hh ? b6[e].y : b6[e].x;
+            oa[e] = make_float4(c3 * pc.ig11, c2 * pc.ig11, c1 * pc.ig03 + c5 * pc.ig33, c1 * pc.ig03 + c4 * pc.ig33);
+            ob[e] = c6 * pc.ig55;
+          }
+          const size_t o = (size_t)gy * pitch + gx;
+          if (gx + 1 < w) {
+            // both records in ONE 32-byte store (o is even: pitch % 32 == 0, gx even): two 16-byte stores per lane
+            // leave every 32-byte sector half written by each instruction and nearly double the L1 -> L2 write traffic
+            // (ncu: 151.6 M sectors for 84 M sectors of output)
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ra4 + o), "f"(oa[0].x), "f"(oa[0].y),
+                         "f"(oa[0].z), "f"(oa[0].w), "f"(oa[1].x), "f"(oa[1].y), "f"(oa[1].z), "f"(oa[1].w)
+                         : "memory");
+            *(float2*)(rb1 + o) = make_float2(ob[0], ob[1]);
+          } else {
+            ra4[o] = oa[0];
+            rb1[o] = ob[0];
+          }
+        }
       }
     }
   }
@@ -1708,7 +1892,12 @@ static int fb_frames(const FbPlan* pl, const FbWorkspace& ws, const uint8_t* fra
         ps0.frames = frames_dev; ps0.step = step; ps0.frame_stride = frame_stride;
         ps0.c[0] = L.r_c[0]; ps0.c[1] = L.r_c[1]; ps0.c[2] = L.r_c[2];
         fb_polyexp_n<5, true><<<g3, 320, 0, st>>>(Ib, L.w, L.h, L.pitch, i_stride, Rb, plane, r_stride, pl->pc, ps0);
-      } else if (n == 5) fb_polyexp_n<5, false><<<g3, 320, 0, st>>>(Ib, L.w, L.h, L.pitch, i_stride, Rb, plane, r_stride, pl->pc, ps0);
+#ifndef FB_POLY_PACKED
+#define FB_POLY_PACKED 1
+#endif
+      } else if (FB_POLY_PACKED && n == 5) fb_polyexp_p<5><<<g3, 256, 0, st>>>(Ib, L.w, L.h, L.pitch, i_stride, Rb, plane, r_stride, pl->pc);
+      else if (FB_POLY_PACKED && n == 7) fb_polyexp_p<7><<<g3, 256, 0, st>>>(Ib, L.w, L.h, L.pitch, i_stride, Rb, plane, r_stride, pl->pc);
+      else if (n == 5) fb_polyexp_n<5, false><<<g3, 320, 0, st>>>(Ib, L.w, L.h, L.pitch, i_stride, Rb, plane, r_stride, pl->pc, ps0);
       else if (n == 7) fb_polyexp_n<7, false><<<g3, 320, 0, st>>>(Ib, L.w, L.h, L.pitch, i_stride, Rb, plane, r_stride, pl->pc, ps0);
       else fb_polyexp<<<g3, 256, smem, st>>>(Ib, L.w, L.h, L.pitch, i_stride, Rb, plane, r_stride, pl->pc, n);
     }

@@ -50,7 +50,22 @@ constexpr int FBW_C_WARPS = 6;
 #define FBW_EW_N 128
 #endif
 constexpr int FBS_EW = FBW_EW_N;
-constexpr int FBW_A_WARPS = FBW_EW_N / 8;  // four row runs of EW columns
+#ifndef FBW_A_WARPS_N
+#define FBW_A_WARPS_N (FBW_EW_N / 8)       // four row runs of EW columns
+#endif
+constexpr int FBW_A_WARPS = FBW_A_WARPS_N;
+// Register budgets per role (setmaxnreg at the head of each role's branch).  With the shipped 16 + 4 + 4 warps every
+// role stays at the 80 registers the CTA is launched with: the three instructions move nothing, but they end ptxas'
+// allocation regions at the role boundaries, and that build measures 1.2 % faster (5.34 vs 5.41 ms, same bits).
+// 20 A warps need 80 / 48 / 56 (A / B / C, launched at 72): step A alone then runs 17 % faster (its throughput is
+// proportional to the number of A warps: 12 / 16 / 20 warps = 5.88 / 4.54 / 3.75 ms), the whole kernel only 1 %
+// (5.36 ms): the B and C warps take issue slots from a stage that is bound by the latency of each warp's dependent
+// chain, and with 56 registers step C is slower (profiles/README.md).
+#if !defined(FBW_REGS_A) && !FBW_WIDE && FBW_A_WARPS_N == 16 && !defined(FBW_MAXNREG)
+#define FBW_REGS_A 80
+#define FBW_REGS_B 80
+#define FBW_REGS_C 80
+#endif
 constexpr int FBW_B_WARPS = 4;
 constexpr int FBW_C_WARPS = 4;
 #endif
@@ -304,6 +319,9 @@ __global__ void FBW_BOUNDS fb_iter_ws(IterArgs a) {
 
   if (t < NA) {
     // =========================== A warps: UpdateMatrices ===========================
+#ifdef FBW_REGS_A   // experiment: registers moved between the roles (the three counts must add up to the launch allocation)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FBW_REGS_A));
+#endif
     // R of the pair's first frame: {float4 plane ch0..3, float plane ch4}; the second frame follows at r_frame_stride
     const float* base0 = a.R + (size_t)pair * a.pair_frame_step * a.r_frame_stride;
     const float2* __restrict__ fin = MODE ? a.flow_in + (size_t)pair * a.flow_in_pair_stride : nullptr;
@@ -363,6 +381,11 @@ __global__ void FBW_BOUNDS fb_iter_ws(IterArgs a) {
 #define FB_R1E(o) ((const float*)(rb + ((unsigned)(o) * 4u + c_r1b)))
 #endif
 
+#ifndef FBW_PREF_NEXT
+#define FBW_PREF_NEXT 0   // 1: fetch the flow vector of the next block's first row before handing this block over -- measured 0.8 % SLOWER
+#endif
+    float2 d_pref = make_float2(0.f, 0.f);
+    bool have_pref = false;
     int j0 = 0;                                         // ring row (mod NR) of the first new M row of the block
     for (int s = 0; s < nblk; ++s) {
       const int yb = ys + s * RB;
@@ -427,7 +450,9 @@ __global__ void FBW_BOUNDS fb_iter_ws(IterArgs a) {
 #else
         auto fetch = [&](int o, int y) -> float2 { return fetch_flow_m<MODE>(a, fi, o, y, uxa, uxb, ufx); };
 #endif
-        float2 dA = fetch(oA, yA), dB = dA;
+        // (the first row's flow vector was requested at the end of the previous block: its latency passes while
+        // the block is handed over instead of at the head of this run's dependent chain)
+        float2 dA = (FBW_PREF_NEXT && have_pref) ? d_pref : fetch(oA, yA), dB = dA;
         auto rowf = [&](const float2 d, float2& dn, const int y, int& yn, const int o, int& on, bool has_next,
                         FbCorner& top, FbCorner& bot) {
           const float4 q = ldg_f4<0>(FB_R0A(o));
@@ -494,6 +519,11 @@ __global__ void FBW_BOUNDS fb_iter_ws(IterArgs a) {
           rowf(dB, dA, yB, yA, oB, oA, k + 2 < n, cB, cA);
         }
         if (k < n) rowf(dA, dB, yA, yB, oA, oB, false, cA, cB);
+        if (FBW_PREF_NEXT && s + 1 < nblk) {            // block s + 1 >= 1: RB rows, runs of RB / FBW_RUNS
+          const int yn = min(max(ys + (s + 1) * RB + M + run * (RB / FBW_RUNS), 0), hm1);
+          d_pref = fetch(yn * pit + x, yn);
+          have_pref = true;
+        }
       }
 #if FBW_PAIR
       // thread 0's arrival also announces the neighbour's 7 columns x nrows x 20 bytes
@@ -513,6 +543,9 @@ __global__ void FBW_BOUNDS fb_iter_ws(IterArgs a) {
     // items of a block: (plane, half, row) -- 4 * nrows of float2 type (planes 0, 1), then 2 * nrows of float type
     // (plane 2); a warp takes 32 items of one type at a time (no divergence between the two element types), rows
     // fastest across lanes (the odd row stride spreads them over the banks)
+#ifdef FBW_REGS_A
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FBW_REGS_B));
+#endif
     const int bt = t - NA, bw = bt >> 5, lane = bt & 31;
     int j0 = 0;
     for (int s = 0; s < nblk; ++s) {
@@ -545,6 +578,9 @@ __global__ void FBW_BOUNDS fb_iter_ws(IterArgs a) {
     }
   } else {
     // =========================== C warps: vertical running sums + solve ===========================
+#ifdef FBW_REGS_A
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FBW_REGS_C));
+#endif
     const int ct = t - NA - NB;
     const bool act = ct < TW && x0 + ct < w;
     const int col = woff + (ct < HL ? ct : ct + 2 * M); // where step B left this column's sums

@@ -20,7 +20,10 @@ namespace b2of {
 int pyrdown_dev(const uint8_t*, int, int, size_t, size_t, uint8_t*, size_t, size_t, int, cudaStream_t);
 
 constexpr int LK_MAX_LEVELS = 12;
-constexpr int LK_WARPS = 4;          // warps per CTA
+#ifndef B2OF_LK_WARPS
+#define B2OF_LK_WARPS 4
+#endif
+constexpr int LK_WARPS = B2OF_LK_WARPS;          // warps per CTA
 #ifndef B2OF_LK_SPLIT
 #define B2OF_LK_SPLIT 1
 #endif
@@ -450,6 +453,27 @@ size_t pyrlk_workspace_bytes(int rows, int cols, const b2of_lk_params* p, int ba
   return (size_t)batch * (2 * L.pyr_bytes + L.deriv_elems * sizeof(short2)) + 1024;
 }
 
+// level 0 of a pyramid block: the caller's frames copied into the padded-step layout, the whole batch in one launch
+// (16-byte units when the source allows it; the padded destination rows always do: the tail of the last unit lands in
+// the row padding)
+__global__ void __launch_bounds__(256) lk_stage_level0(const uint8_t* __restrict__ src, size_t step, size_t frame_stride,
+                                                        uint8_t* __restrict__ dst, size_t dstep, size_t dstride, int cols,
+                                                        int vec) {
+  const int u = blockIdx.x * 256 + threadIdx.x;
+  const uint8_t* s = src + blockIdx.z * frame_stride + blockIdx.y * step;
+  uint8_t* d = dst + blockIdx.z * dstride + blockIdx.y * dstep;
+  if (vec) {
+    if (16 * u >= cols) return;
+    if (16 * u + 16 <= cols) {
+      *(uint4*)(d + 16 * u) = __ldg((const uint4*)(s + 16 * u));
+    } else {
+      for (int c = 16 * u; c < cols; ++c) d[c] = s[c];
+    }
+  } else if (u < cols) {
+    d[u] = s[u];
+  }
+}
+
 int pyrlk_dev(const uint8_t* prev, const uint8_t* next, size_t step, size_t frame_stride, int batch, int rows, int cols,
               const float* prev_pts, size_t pts_bstride, int n_pts, float* next_pts, uint8_t* status, float* err,
               const b2of_lk_params* p, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -473,9 +497,12 @@ int pyrlk_dev(const uint8_t* prev, const uint8_t* next, size_t step, size_t fram
     uint8_t* dst = which ? pj : pi;
     const uint8_t* src = which ? next : prev;
     if (batch == 1 || frame_stride != 0) {
-      for (int b = 0; b < batch; ++b)
-        B2OF_CUDA(cudaMemcpy2DAsync(dst + (size_t)b * a.L.pyr_bytes, a.L.step[0], src + (size_t)b * frame_stride, step,
-                                    cols, rows, cudaMemcpyDeviceToDevice, st));
+      // one launch for the whole batch (blockIdx.z = batch item) instead of one 2-D copy per image
+      const bool vec = (((uintptr_t)src | step | frame_stride | (uintptr_t)dst | a.L.pyr_bytes) & 15) == 0;   // (destination steps are 16-byte multiples)
+      const int units = vec ? cdiv(cols, 16) : cols;
+      lk_stage_level0<<<dim3(cdiv(units, 256), rows, batch), 256, 0, st>>>(src, step, frame_stride, dst, a.L.step[0],
+                                                                         a.L.pyr_bytes, cols, vec ? 1 : 0);
+      B2OF_LAUNCH_CHECK();
     } else {
       return fail(B2OF_E_BADARG, "frame_stride == 0 with batch > 1");
     }
