@@ -1693,32 +1693,53 @@ __global__ void __launch_bounds__(256) fb_flow_only(IterArgs a) {
 // fine pixels that interpolate inside it (x = 2i + 1, 2i + 2; y = 2j + 1, 2j + 2; fractions 0.25 / 0.75, 0 at the
 // clamped ends).  Same expression as fetch_flow_m<2>, same bits; a quarter of its loads per pixel and no tables.
 __global__ void __launch_bounds__(256) fb_upsample2x(IterArgs a) {
-  const int i = blockIdx.x * 64 + (threadIdx.x & 63) - 1, j = blockIdx.y * 4 + (threadIdx.x >> 6) - 1;
+  // thread = the fine pixel pair (2k, 2k + 1) of four fine rows 4m .. 4m + 3: its two pixels are ONE aligned 16-byte
+  // store per row (a thread per coarse cell owns pixels 2i + 1, 2i + 2 -- two 8-byte stores 16 bytes apart across the
+  // lanes, every 32-byte sector half written per instruction).  cv2's linear-resize table in closed form:
+  //   x = 0 -> (0, 1, 0);  x = 2q + 1 -> (q, min(q + 1, n - 1), q >= n - 1 ? 0 : 0.25);  x = 2q + 2 -> (q, q + 1, 0.75)
+  const int k = blockIdx.x * 64 + (threadIdx.x & 63), m = blockIdx.y * 4 + (threadIdx.x >> 6);
   const int pair = blockIdx.z;
-  if (i >= a.cw || j >= a.ch) return;
+  if (2 * k >= a.w || 4 * m >= a.h) return;
   const float2* fin = a.flow_in + (size_t)pair * a.flow_in_pair_stride;
-  // cv2's linear-resize table in closed form: x = 0 -> (0, 1, 0); x = 2k + 1 -> (k, k + 1, 0.25), clamped to
-  // (n - 1, n - 1, 0) at the end; x = 2k + 2 -> (k, k + 1, 0.75).  Cell -1 is the pair (0, 1) that pixel 0 reads.
-  const int ia = max(i, 0), ib = i < 0 ? min(1, a.cw - 1) : min(i + 1, a.cw - 1);
-  const int ja = max(j, 0), jb = j < 0 ? min(1, a.ch - 1) : min(j + 1, a.ch - 1);
-  const float2 p00 = fin[ja * a.in_pitch + ia], p01 = fin[ja * a.in_pitch + ib];
-  const float2 p10 = fin[jb * a.in_pitch + ia], p11 = fin[jb * a.in_pitch + ib];
-  float2* out = a.flow_out + (size_t)pair * a.flow_out_pair_stride;
+  const int cA = max(k - 1, 0), cB = k, cC = min(k + 1, a.cw - 1);
+  // coarse rows 2m - 1 .. 2m + 2 (clamped), three columns each
+  float2 p[4][3];
 #pragma unroll
-  for (int dy = 1; dy <= 2; ++dy) {
-    const int y = 2 * j + dy;
-    if (y < 0 || y >= a.h) continue;
-    const float fy = y == 0 ? 0.f : (y & 1) ? ((y >> 1) >= a.ch - 1 ? 0.f : 0.25f) : 0.75f;
+  for (int r = 0; r < 4; ++r) {
+    const float2* row = fin + (size_t)min(max(2 * m - 1 + r, 0), a.ch - 1) * a.in_pitch;
+    p[r][0] = row[cA]; p[r][1] = row[cB]; p[r][2] = row[cC];
+  }
+  const float fx0 = k == 0 ? 0.f : 0.75f, fx1 = k >= a.cw - 1 ? 0.f : 0.25f;
+  const bool first = k == 0;                            // pixel 0 reads columns (0, min(1, n - 1)) = (cA, cC)
+  float2* out = a.flow_out + (size_t)pair * a.flow_out_pair_stride + 2 * k;
 #pragma unroll
-    for (int dx = 1; dx <= 2; ++dx) {
-      const int x = 2 * i + dx;
-      if (x < 0 || x >= a.w) continue;
-      const float fx = x == 0 ? 0.f : (x & 1) ? ((x >> 1) >= a.cw - 1 ? 0.f : 0.25f) : 0.75f;
+  for (int dy = 0; dy < 4; ++dy) {
+    const int y = 4 * m + dy;
+    if (y >= a.h) break;
+    // rows (ra, rb) as indices into p[] (coarse row 2m - 1 + index) and the weight of rb
+    int ra, rb;
+    float fy;
+    if (dy == 0) { ra = y == 0 ? 1 : 0; rb = y == 0 ? 2 : 1; fy = y == 0 ? 0.f : 0.75f; }   // y = 2 (2m - 1) + 2
+    else if (dy == 1) { ra = 1; rb = 2; fy = 2 * m >= a.ch - 1 ? 0.f : 0.25f; }             // y = 2 (2m) + 1
+    else if (dy == 2) { ra = 1; rb = 2; fy = 0.75f; }                                       // y = 2 (2m) + 2
+    else { ra = 2; rb = 3; fy = 2 * m + 1 >= a.ch - 1 ? 0.f : 0.25f; }                      // y = 2 (2m + 1) + 1
+    float2 qa[3], qb[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {                       // (dy == 0 picks between two register rows: selects, no indexing)
+      qa[c] = dy == 0 ? (y == 0 ? p[1][c] : p[0][c]) : p[ra][c];
+      qb[c] = dy == 0 ? (y == 0 ? p[2][c] : p[1][c]) : p[rb][c];
+    }
+    float2 o[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float fx = e ? fx1 : fx0;
+      const float2 p00 = e ? qa[1] : qa[0], p01 = e ? qa[2] : (first ? qa[2] : qa[1]);
+      const float2 p10 = e ? qb[1] : qb[0], p11 = e ? qb[2] : (first ? qb[2] : qb[1]);
       const float tx0 = p00.x * (1.f - fx) + p01.x * fx, ty0 = p00.y * (1.f - fx) + p01.y * fx;
       const float tx1 = p10.x * (1.f - fx) + p11.x * fx, ty1 = p10.y * (1.f - fx) + p11.y * fx;
-      out[(size_t)y * a.out_pitch + x] =
-          make_float2((tx0 * (1.f - fy) + tx1 * fy) * a.up_mult, (ty0 * (1.f - fy) + ty1 * fy) * a.up_mult);
+      o[e] = make_float2((tx0 * (1.f - fy) + tx1 * fy) * a.up_mult, (ty0 * (1.f - fy) + ty1 * fy) * a.up_mult);
     }
+    *(float4*)(out + (size_t)y * a.out_pitch) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
   }
 }
 
@@ -2036,7 +2057,7 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
         dim3 gf(cdiv(L.w, 256), L.h, pairs);
         {
           ProfScope ps(PT_FB_UPSAMPLE, st, pairs * (8.0 * cw * ch + 8.0 * L.w * L.h));
-          if (u.up_exact2) fb_upsample2x<<<dim3(cdiv(cw + 1, 64), cdiv(ch + 1, 4), pairs), 256, 0, st>>>(u);
+          if (u.up_exact2) fb_upsample2x<<<dim3(cdiv(cw, 64), cdiv(L.h, 16), pairs), 256, 0, st>>>(u);
           else fb_flow_only<2><<<gf, 256, 0, st>>>(u);
         }
         B2OF_LAUNCH_CHECK();

@@ -137,6 +137,9 @@ __device__ __forceinline__ void mbar_init(unsigned addr, int count) {
 __device__ __forceinline__ void mbar_arrive(unsigned addr) {
   asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(addr) : "memory");
 }
+#ifndef FBW_SLEEP_NS
+#define FBW_SLEEP_NS 200
+#endif
 __device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
   // poll with back-off (a bare try_wait loop, a try_wait with a suspend-time hint and longer sleeps all time the same)
   asm volatile(
@@ -146,7 +149,7 @@ __device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
       "W_%=: nanosleep.u32 %2;\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@!p bra W_%=;\n"
-      "D_%=: }" ::"r"(addr), "r"(parity), "n"(200) : "memory");
+      "D_%=: }" ::"r"(addr), "r"(parity), "n"(FBW_SLEEP_NS) : "memory");
 }
 
 #if FBW_PAIR
@@ -381,6 +384,9 @@ __global__ void FBW_BOUNDS fb_iter_ws(IterArgs a) {
 #define FB_R1E(o) ((const float*)(rb + ((unsigned)(o) * 4u + c_r1b)))
 #endif
 
+#ifndef FBW_GSHFL
+#define FBW_GSHFL 0
+#endif
 #ifndef FBW_PREF_NEXT
 #define FBW_PREF_NEXT 0   // 1: fetch the flow vector of the next block's first row before handing this block over -- measured 0.8 % SLOWER
 #endif
@@ -469,11 +475,29 @@ __global__ void FBW_BOUNDS fb_iter_ws(IterArgs a) {
             top.a0 = ldg_f4<0>(pa); top.a1 = ldg_f4<16>(pa); top.e0 = ldg_f1<0>(pe); top.e1 = ldg_f1<4>(pe);
           }
           const int ob = ot + pitb;
+#if FBW_GSHFL
+          {
+            // the right-hand corner of lane l is the left-hand corner of lane l + 1 whenever the two pixels' integer
+            // displacements agree (almost always): it comes over by shuffle, and only lane 31 and the lanes at a
+            // displacement step load it themselves -- one unaligned 16-byte load per lane and row instead of two
+            const float4* pa = FB_R1A(ob);
+            const float* pe = FB_R1E(ob);
+            bot.a0 = ldg_f4<0>(pa); bot.e0 = ldg_f1<0>(pe);
+            const int obn = __shfl_down_sync(0xffffffffu, ob, 1);
+            const bool own = obn != ob + 1 || (t & 31) == 31;
+            if (own) { bot.a1 = ldg_f4<16>(pa); bot.e1 = ldg_f1<4>(pe); }
+            const float nx = __shfl_down_sync(0xffffffffu, bot.a0.x, 1), ny = __shfl_down_sync(0xffffffffu, bot.a0.y, 1);
+            const float nz = __shfl_down_sync(0xffffffffu, bot.a0.z, 1), nw = __shfl_down_sync(0xffffffffu, bot.a0.w, 1);
+            const float ne = __shfl_down_sync(0xffffffffu, bot.e0, 1);
+            if (!own) { bot.a1 = make_float4(nx, ny, nz, nw); bot.e1 = ne; }
+          }
+#else
           {
             const float4* pa = FB_R1A(ob);
             const float* pe = FB_R1E(ob);
             bot.a0 = ldg_f4<0>(pa); bot.a1 = ldg_f4<16>(pa); bot.e0 = ldg_f1<0>(pe); bot.e1 = ldg_f1<4>(pe);
           }
+#endif
           o_carry = ob;
           const float gx = 1.f - fx, gy = 1.f - fy;
           const float a00 = gx * gy, a01 = fx * gy, a10 = gx * fy, a11 = fx * fy;
