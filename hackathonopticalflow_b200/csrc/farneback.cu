@@ -730,6 +730,26 @@ __device__ __forceinline__ void lc_vpass(const float* __restrict__ sh, const flo
   out[(size_t)(y0 + y) * pitch + x0 + x] = v;
 }
 
+template <int K, int S, int NY, int P>
+__device__ __forceinline__ void lc_vwalk(const float* __restrict__ sh, const float* __restrict__ c, int x, int yf,
+                                         float* __restrict__ out, int x0, int y0, int wk, int hk, int pitch) {
+  if (x0 + x >= wk || y0 + yf >= hk) return;
+  constexpr int NR = S * (NY - 1) + K;
+  float v[NR];
+  const float* p = sh + (S * yf) * P + x;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) v[r] = p[r * P];
+  float* o = out + (size_t)(y0 + yf) * pitch + x0 + x;
+#pragma unroll
+  for (int y = 0; y < NY; ++y) {
+    if (y0 + yf + y >= hk) break;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc = fmaf(c[j], v[S * y + j], acc);
+    o[(size_t)y * pitch] = acc;
+  }
+}
+
 __global__ void __launch_bounds__(LC_NT) fb_levels_coarse(LevelCoarseArgs a) {
   __shared__ __align__(16) float s_src[LC_REG * LC_RP];   // source region as floats
   __shared__ float s_h1[66 * 33], s_h2[70 * 17], s_h3[76 * 9];
@@ -792,18 +812,22 @@ __global__ void __launch_bounds__(LC_NT) fb_levels_coarse(LevelCoarseArgs a) {
     }
   }
   __syncthreads();
-  constexpr int V1 = 32 * 32, V2 = 16 * 16, V3 = 8 * 8;
-  for (int i = t; i < V1 + V2 + V3; i += LC_NT) {
-    if (i < V1)
-      lc_vpass<4, 2, 32, 33>(s_h1, a.c2, i, a.I[0] + blockIdx.z * a.i_frame_stride[0], 32 * blockIdx.x,
-                             32 * blockIdx.y, a.wk[0], a.hk[0], a.pitch[0]);
-    else if (i < V1 + V2)
-      lc_vpass<10, 4, 16, 17>(s_h2, a.c4, i - V1, a.I[1] + blockIdx.z * a.i_frame_stride[1], 16 * blockIdx.x,
-                              16 * blockIdx.y, a.wk[1], a.hk[1], a.pitch[1]);
-    else
-      lc_vpass<20, 8, 8, 9>(s_h3, a.c8, i - V1 - V2, a.I[2] + blockIdx.z * a.i_frame_stride[2], 8 * blockIdx.x,
-                            8 * blockIdx.y, a.wk[2], a.hk[2], a.pitch[2]);
-  }
+  // vertical passes: a thread owns one output column of one level and a run of NY consecutive rows; the filtered
+  // rows the run needs are read once into registers (consecutive outputs share K - S of their K rows) and the output
+  // index is the thread's own -- the first version looped over a flat output index with a level switch, a division
+  // and K shared-memory reads per output, a third of the kernel's instructions.  Warps 0-3: the 32 x 32 tile of the
+  // S = 2 level (8 rows each), warps 4-5: the 16 x 16 tile of S = 4 (4 rows per half warp), warp 6: the 8 x 8 tile
+  // of S = 8 (2 rows per quarter warp).
+  if (warp < 4)
+    lc_vwalk<4, 2, 8, 33>(s_h1, a.c2, lane, 8 * warp, a.I[0] + blockIdx.z * a.i_frame_stride[0], 32 * blockIdx.x,
+                          32 * blockIdx.y, a.wk[0], a.hk[0], a.pitch[0]);
+  else if (warp < 6)
+    lc_vwalk<10, 4, 4, 17>(s_h2, a.c4, lane & 15, 4 * (2 * (warp - 4) + (lane >> 4)),
+                           a.I[1] + blockIdx.z * a.i_frame_stride[1], 16 * blockIdx.x, 16 * blockIdx.y, a.wk[1], a.hk[1],
+                           a.pitch[1]);
+  else if (warp == 6)
+    lc_vwalk<20, 8, 2, 9>(s_h3, a.c8, lane & 7, 2 * (lane >> 3), a.I[2] + blockIdx.z * a.i_frame_stride[2],
+                          8 * blockIdx.x, 8 * blockIdx.y, a.wk[2], a.hk[2], a.pitch[2]);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1312,6 +1336,11 @@ __device__ __forceinline__ void sts_f1(unsigned addr, float x) {
 }
 
 // flow vector of pixel (x, y) of this level: o = y * pitch + x (MODE 1: the flow buffers share the level's pitch)
+// a * wa + b * wb with both products rounded (no FMA contraction): the arithmetic of cv2's linear resize
+__device__ __forceinline__ float lerp_nc(float a, float wa, float b, float wb) {
+  return __fadd_rn(__fmul_rn(a, wa), __fmul_rn(b, wb));
+}
+
 template <int MODE>
 __device__ __forceinline__ float2 fetch_flow_m(const IterArgs& a, const float2* fin, int o, int y, int xa, int xb,
                                                float ufx) {
@@ -1331,9 +1360,11 @@ __device__ __forceinline__ float2 fetch_flow_m(const IterArgs& a, const float2* 
   }
   float2 p00 = fin[ya * a.in_pitch + xa], p01 = fin[ya * a.in_pitch + xb];
   float2 p10 = fin[yb * a.in_pitch + xa], p11 = fin[yb * a.in_pitch + xb];
-  float tx0 = p00.x * (1.f - ufx) + p01.x * ufx, ty0 = p00.y * (1.f - ufx) + p01.y * ufx;
-  float tx1 = p10.x * (1.f - ufx) + p11.x * ufx, ty1 = p10.y * (1.f - ufx) + p11.y * ufx;
-  return make_float2((tx0 * (1.f - fy) + tx1 * fy) * a.up_mult, (ty0 * (1.f - fy) + ty1 * fy) * a.up_mult);
+  // lerp_nc: cv2's resize rounds both products before the add; a contracted FMA (either way round) is other bits
+  const float gx = 1.f - ufx, gy = 1.f - fy;
+  float tx0 = lerp_nc(p00.x, gx, p01.x, ufx), ty0 = lerp_nc(p00.y, gx, p01.y, ufx);
+  float tx1 = lerp_nc(p10.x, gx, p11.x, ufx), ty1 = lerp_nc(p10.y, gx, p11.y, ufx);
+  return make_float2(__fmul_rn(lerp_nc(tx0, gy, tx1, fy), a.up_mult), __fmul_rn(lerp_nc(ty0, gy, ty1, fy), a.up_mult));
 }
 
 template <int NT, int CT, int CM, bool GAUSS, int MODE>
@@ -1735,9 +1766,10 @@ __global__ void __launch_bounds__(256) fb_upsample2x(IterArgs a) {
       const float fx = e ? fx1 : fx0;
       const float2 p00 = e ? qa[1] : qa[0], p01 = e ? qa[2] : (first ? qa[2] : qa[1]);
       const float2 p10 = e ? qb[1] : qb[0], p11 = e ? qb[2] : (first ? qb[2] : qb[1]);
-      const float tx0 = p00.x * (1.f - fx) + p01.x * fx, ty0 = p00.y * (1.f - fx) + p01.y * fx;
-      const float tx1 = p10.x * (1.f - fx) + p11.x * fx, ty1 = p10.y * (1.f - fx) + p11.y * fx;
-      o[e] = make_float2((tx0 * (1.f - fy) + tx1 * fy) * a.up_mult, (ty0 * (1.f - fy) + ty1 * fy) * a.up_mult);
+      const float gx = 1.f - fx, gy = 1.f - fy;
+      const float tx0 = lerp_nc(p00.x, gx, p01.x, fx), ty0 = lerp_nc(p00.y, gx, p01.y, fx);
+      const float tx1 = lerp_nc(p10.x, gx, p11.x, fx), ty1 = lerp_nc(p10.y, gx, p11.y, fx);
+      o[e] = make_float2(__fmul_rn(lerp_nc(tx0, gy, tx1, fy), a.up_mult), __fmul_rn(lerp_nc(ty0, gy, ty1, fy), a.up_mult));
     }
     *(float4*)(out + (size_t)y * a.out_pitch) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
   }

@@ -436,7 +436,8 @@ __global__ void FBW_BOUNDS fb_iter_ws(IterArgs a) {
         float2 u_ha = make_float2(0.f, 0.f), u_hb = u_ha;
         auto coarse_row = [&](int r) {
           const float2 p0 = fi[r * a.in_pitch + uxa], p1 = fi[r * a.in_pitch + uxb];
-          return make_float2(p0.x * (1.f - ufx) + p1.x * ufx, p0.y * (1.f - ufx) + p1.y * ufx);
+          const float gx = 1.f - ufx;
+          return make_float2(lerp_nc(p0.x, gx, p1.x, ufx), lerp_nc(p0.y, gx, p1.y, ufx));
         };
         auto fetch = [&](int o, int y) -> float2 {
           if (MODE != 2) return fetch_flow_m<MODE>(a, fi, o, y, uxa, uxb, ufx);
@@ -450,8 +451,9 @@ __global__ void FBW_BOUNDS fb_iter_ws(IterArgs a) {
             u_hb = yb == ya ? u_ha : coarse_row(yb);
             u_yb = yb;
           }
-          return make_float2((u_ha.x * (1.f - fy) + u_hb.x * fy) * a.up_mult,
-                             (u_ha.y * (1.f - fy) + u_hb.y * fy) * a.up_mult);
+          const float gy = 1.f - fy;
+          return make_float2(__fmul_rn(lerp_nc(u_ha.x, gy, u_hb.x, fy), a.up_mult),
+                             __fmul_rn(lerp_nc(u_ha.y, gy, u_hb.y, fy), a.up_mult));
         };
 #else
         auto fetch = [&](int o, int y) -> float2 { return fetch_flow_m<MODE>(a, fi, o, y, uxa, uxb, ufx); };
