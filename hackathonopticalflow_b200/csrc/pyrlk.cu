@@ -30,12 +30,22 @@ constexpr int LK_WARPS = B2OF_LK_WARPS;          // warps per CTA
 constexpr int LK_SPLIT = B2OF_LK_SPLIT;   // warps per feature
 constexpr int LK_FEATS = LK_WARPS / LK_SPLIT;   // features per CTA
 
+
+// One image's pyramid block: every level is stored with a border of pad_x columns and pad_y rows on each side, filled
+// with BORDER_REFLECT_101 pixels (derivatives: zeros -- cv2 pads them with BORDER_CONSTANT) by lk_pad_borders.  A
+// window may stick out of the frame by its own size (cv2 tracks such points), and with the border in memory the walk
+// over a window at the frame edge is the same straight-line code as anywhere else: the reflecting walk (an index
+// reflection per row and five byte loads per strip row) took a third of lk_track's time for a tenth of the windows.
 struct LkLevels {
   int n;  // number of levels (effective maxLevel + 1)
   int w[LK_MAX_LEVELS], h[LK_MAX_LEVELS];
-  size_t step[LK_MAX_LEVELS];
-  size_t off[LK_MAX_LEVELS];         // byte offset of level l inside one image's pyramid block
-  size_t doff[LK_MAX_LEVELS];        // short2 offset of level l inside one image's derivative block
+  int pad_x, pad_y;
+  size_t step[LK_MAX_LEVELS];        // row pitch in bytes (w + 2 pad_x rounded up to 16)
+  size_t dstep[LK_MAX_LEVELS];       // derivative row pitch in elements (= step)
+  size_t off[LK_MAX_LEVELS];         // byte offset of pixel (0, 0) of level l inside one image's pyramid block
+  size_t base[LK_MAX_LEVELS];        // byte offset of the level's padded block (row -pad_y, column -pad_x)
+  size_t doff[LK_MAX_LEVELS];        // short2 offset of derivative (0, 0) of level l inside one image's block
+  size_t dbase[LK_MAX_LEVELS];
   size_t pyr_bytes, deriv_elems;     // per image
 };
 
@@ -43,12 +53,19 @@ static int lk_plan(int rows, int cols, const b2of_lk_params* p, LkLevels* L) {
   memset(L, 0, sizeof *L);
   int w = cols, h = rows, n = 0;
   size_t off = 0, doff = 0;
+  // columns read: window column -win_w .. w - 1 + win_w, plus the over-read of the last four-column strip and of its
+  // aligned word pair (<= 10 columns); rows: -win_h .. h - 1 + win_h
+  L->pad_x = (int)align_up(p->win_w + 10, 16);
+  L->pad_y = p->win_h + 1;
   for (int level = 0; level <= p->max_level && level < LK_MAX_LEVELS; ++level) {
     L->w[n] = w; L->h[n] = h;
-    L->step[n] = align_up(w, 16);
-    L->off[n] = off; L->doff[n] = doff;
-    off += align_up(L->step[n] * h, 256);
-    doff += align_up((size_t)w * h, 64);
+    L->step[n] = align_up(w + 2 * L->pad_x, 16);
+    L->dstep[n] = L->step[n];
+    L->base[n] = off; L->dbase[n] = doff;
+    L->off[n] = off + (size_t)L->pad_y * L->step[n] + L->pad_x;
+    L->doff[n] = doff + (size_t)L->pad_y * L->dstep[n] + L->pad_x;
+    off += align_up(L->step[n] * (h + 2 * L->pad_y), 256);
+    doff += align_up(L->dstep[n] * (h + 2 * L->pad_y), 64);
     ++n;
     w = (w + 1) / 2; h = (h + 1) / 2;
     if (w <= p->win_w || h <= p->win_h) break;
@@ -68,7 +85,8 @@ __device__ __forceinline__ int reflect101_pm1(int i, int n) {   // BORDER_REFLEC
 // four pixels per thread: the 3 x 6 neighbourhood comes in as bytes from L1, the four (Ix, Iy) pairs go out as one
 // 16-byte store when the row start is aligned
 __global__ void __launch_bounds__(256) lk_scharr(const uint8_t* __restrict__ img, size_t step, size_t img_bstride,
-                                                  int w, int h, short2* __restrict__ d, size_t d_bstride) {
+                                                  int w, int h, short2* __restrict__ d, size_t d_bstride,
+                                                  size_t d_pitch) {
   const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
   if (x0 >= w) return;
   const uint8_t* b = img + blockIdx.z * img_bstride;
@@ -87,7 +105,7 @@ __global__ void __launch_bounds__(256) lk_scharr(const uint8_t* __restrict__ img
 #pragma unroll
   for (int k = 0; k < 4; ++k)
     o[k] = make_short2((short)(t0[k + 2] - t0[k]), (short)((t1[k] + t1[k + 2]) * 3 + t1[k + 1] * 10));
-  short2* out = d + blockIdx.z * d_bstride + (size_t)y * w + x0;
+  short2* out = d + blockIdx.z * d_bstride + (size_t)y * d_pitch + x0;
   if (x0 + 3 < w && (((size_t)out) & 15) == 0) {
     *(int4*)out = make_int4(*(int*)&o[0], *(int*)&o[1], *(int*)&o[2], *(int*)&o[3]);
   } else {
@@ -128,149 +146,197 @@ __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01,
   w11 = 16384 - w00 - w01 - w10;
 }
 
-// Patch layout in shared memory: rows of wwp = ww rounded up to even elements, so that two horizontally adjacent
-// elements are one aligned 4-byte (Iw pair) / 8-byte (derivative pair) access.
-__host__ __device__ inline int lk_wwp(int ww) { return (ww + 1) & ~1; }
+// Patch layout in shared memory, per warp: Iw as int16 [wh][wwp] with wwp = ww rounded up to a multiple of four, then
+// one 16-byte record per (row, group of four columns): (Ix0 | Ix1 << 16, Ix2 | Ix3 << 16, Iy0 | Iy1 << 16,
+// Iy2 | Iy3 << 16).  Padding columns hold zeros, so whatever the window walk computes for them multiplies to nothing.
+__host__ __device__ inline int lk_wwp(int ww) { return (ww + 3) & ~3; }
+__host__ __device__ inline size_t lk_iw_bytes(int ww, int wh) { return (((size_t)lk_wwp(ww) * wh * 2) + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t lk_patch_bytes(int ww, int wh) {
-  size_t n = (size_t)lk_wwp(ww) * wh;
-  return ((((n + 3) & ~(size_t)3) * 2 + n * 4) + 15) & ~(size_t)15;
+  return lk_iw_bytes(ww, wh) + (size_t)lk_wwp(ww) * wh * 4;
 }
 
-// Work split of a window inside the image: the warp's lanes own strips two columns wide (S = wwp / 2 strips) and,
-// when the window is narrow, G = 32 / S groups of rows.  A lane walks down its strip: the three bytes of the next
-// image row are loaded once and serve as bottom neighbours of this row and top neighbours of the next one
-// (1.5 loads per element instead of 4), addresses advance by one row step, and the template patch comes in as
-// aligned pairs.  Window sums are exact 64-bit integers, so the result does not depend on the split.
+// Work split of a window: the warp's lanes own strips NC columns wide (S strips) and, when the window is narrow,
+// G = 32 / S groups of rows.  A lane walks down its strip: the image row below is loaded once and serves as the
+// bottom neighbours of this row and the top neighbours of the next one, addresses advance by one row step, and the
+// template patch comes in as aligned records.  Window sums are exact integers, so the result does not depend on the
+// split.  The window walk uses NC = 4 (12 strips x 2 row groups for the 45-wide grid window), the patch pass NC = 2.
+template <int NC>
 struct LkStrips {
   int S, G, RG;
   __device__ __forceinline__ LkStrips(int ww, int nrows) {   // nrows = rows of this warp's share of the window
-    S = lk_wwp(ww) >> 1;
+    S = lk_wwp(ww) / NC;
     G = S <= 16 ? 32 / S : 1;
     RG = (nrows + G - 1) / G;
   }
 };
 
-// sum over the window of (bilinear(J) >> 9 - Iw) * {Ixw, Iyw}  (or |diff| when ABS).
-// Windows that stick out of the image read BORDER_REFLECT_101 pixels: the three reflected column indices of a
-// strip are computed once, the reflected row index once per row.
-template <bool ABS, bool INSIDE>
-__device__ __forceinline__ void lk_window_strips(const uint8_t* __restrict__ J, size_t step, int w, int h, int ix,
-                                                 int iy, int w00, int w01, int w10, int w11, const short* sI,
-                                                 const short2* sD, int ww, int ya, int yb, int lane, long long& s1,
-                                                 long long& s2) {
+// d = c + a.h0 * b.b0 + a.h1 * b.b1 (LO: bytes 0, 1 of b; HI: bytes 2, 3), a signed 16-bit halves, b unsigned bytes
+__device__ __forceinline__ int dp2a_lo_su(int a, unsigned b, int c) {
+  int d;
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(int a, unsigned b, int c) {
+  int d;
+  asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// sum over the window of (bilinear(J) >> 9 - Iw) * {Ixw, Iyw}  (or |diff| when ABS).  J points at pixel (0, 0) of a
+// level stored with its reflected border (LkLevels), so a window anywhere is walked with the same code.
+//
+// A lane's strip is four columns wide.  Its five source bytes of an image row (columns c .. c + 4) are two aligned
+// words and two funnel shifts: R = bytes c .. c + 3, R2 = bytes c + 1 .. c + 4.  The 14-bit bilinear weights fit 16
+// bits, so one IDP.2A does two of the four taps of an element:
+//   v0 = 256 + (w00, w01) . R.lo + (w10, w11) . Rbelow.lo,   v1: R2.lo,   v2: R.hi,   v3: R2.hi        (8 IDP.2A)
+// against sixteen IMADs and four adds.  The four differences stay packed: (v >> 9) + 0x2000 - Iw is positive and below
+// 2^15, so two of them are subtracted from the packed Iw pair with ONE 32-bit add; a byte permute sorts the low and
+// the high bytes of such a pair together and four more IDP.2A per pair multiply them by the packed (Ix0, Ix1) and
+// (Iy0, Iy1) of the patch -- sum(e * Ix) = sum(el * Ix) + 256 sum(eh * Ix) with e = diff + 0x2000, and the offset
+// 0x2000 * sum(Ix) is a constant of the patch, taken off by the caller.  All partial sums fit 32 bits for a strip
+// (|Ix| <= 4080, el <= 255: 2^20 per product, at most a few hundred products); they are widened per strip.
+template <bool ABS>
+__device__ __forceinline__ void lk_window_strips(const uint8_t* __restrict__ J, size_t step, int ix, int iy,
+                                                 unsigned wt, unsigned wb, const short* sI, const int4* sD, int ww,
+                                                 int ya, int yb, int lane, long long& s1, long long& s2) {
   const int wwp = lk_wwp(ww);
-  const LkStrips st(ww, yb - ya);
+  const LkStrips<4> st(ww, yb - ya);
+  const ptrdiff_t stepw = (ptrdiff_t)(step >> 2);          // (pyramid steps are multiples of 16 bytes)
   for (int u = lane; u < st.S * st.G; u += 32) {
     const int g = u / st.S, sx = u - g * st.S;
-    const int x0 = 2 * sx;
-    const bool two = x0 + 1 < ww;
+    const int x0 = 4 * sx;
     const int y0 = ya + g * st.RG, y1 = min(yb, y0 + st.RG);
-    int c0 = ix + x0, c1 = c0 + 1, c2 = c0 + 2;
-    if (!INSIDE) { c0 = reflect101(c0, w); c1 = reflect101(c1, w); c2 = reflect101(c2, w); }
-    auto rowp = [&](int y) { return J + (size_t)(INSIDE ? iy + y : reflect101(iy + y, h)) * step; };
-    const uint8_t* r = rowp(y0);
-    int t0 = r[c0], t1 = r[c1], t2 = two ? r[c2] : 0;
+    const uint8_t* p0 = J + (ptrdiff_t)(iy + y0) * (ptrdiff_t)step + (ix + x0);
+    const unsigned sh = ((unsigned)(uintptr_t)p0 & 3u) * 8u;
+    const uint32_t* q = (const uint32_t*)(p0 - ((uintptr_t)p0 & 3));   // the aligned word holding column ix + x0
+    auto shifted = [&](unsigned lo, unsigned hi, unsigned& R, unsigned& R2) {
+      R = __funnelshift_r(lo, hi, sh);
+      R2 = __funnelshift_rc(lo, hi, sh + 8u);
+    };
+    unsigned Rt, Rt2;
+    shifted(q[0], q[1], Rt, Rt2);
     const short* pI = sI + y0 * wwp + x0;
-    const short2* pD = sD + y0 * wwp + x0;
-    auto one_row = [&](int b0, int b1, int b2, int ipair, int2 dp) {
-      const int v0 = t0 * w00 + t1 * w01 + b0 * w10 + b1 * w11;
-      const int v1 = t1 * w00 + t2 * w01 + b1 * w10 + b2 * w11;
-      const int diff0 = ((v0 + 256) >> 9) - (int)(short)(ipair & 0xffff);
-      const int diff1 = ((v1 + 256) >> 9) - (ipair >> 16);
+    const int4* pD = sD + y0 * st.S + sx;
+    int aL1 = 0, aH1 = 0, aL2 = 0, aH2 = 0;
+    unsigned sabs = 0;
+    auto one_row = [&](unsigned blo, unsigned bhi, int2 iq, int4 dq) {
+      unsigned Rb, Rb2;
+      shifted(blo, bhi, Rb, Rb2);
+      const unsigned v0 = __dp2a_lo(wb, Rb, __dp2a_lo(wt, Rt, 256u));
+      const unsigned v1 = __dp2a_lo(wb, Rb2, __dp2a_lo(wt, Rt2, 256u));
+      const unsigned v2 = __dp2a_hi(wb, Rb, __dp2a_hi(wt, Rt, 256u));
+      const unsigned v3 = __dp2a_hi(wb, Rb2, __dp2a_hi(wt, Rt2, 256u));
+      // e = (v >> 9) + 0x2000 - Iw, two to a register
+      const unsigned e01 = __byte_perm(v0 >> 9, v1 >> 9, 0x5410) + 0x20002000u - (unsigned)iq.x;
+      const unsigned e23 = __byte_perm(v2 >> 9, v3 >> 9, 0x5410) + 0x20002000u - (unsigned)iq.y;
       if (ABS) {
-        s1 += abs(diff0);
-        if (two) s1 += abs(diff1);
+        // padding columns hold Iw = 0 and must not count: the caller's window is ww wide
+        const int d0 = (int)(e01 & 0xffffu) - 0x2000, d1 = (int)(e01 >> 16) - 0x2000;
+        const int d2 = (int)(e23 & 0xffffu) - 0x2000, d3 = (int)(e23 >> 16) - 0x2000;
+        sabs += abs(d0);
+        if (x0 + 1 < ww) sabs += abs(d1);
+        if (x0 + 2 < ww) sabs += abs(d2);
+        if (x0 + 3 < ww) sabs += abs(d3);
       } else {
-        s1 += (long long)diff0 * (int)(short)(dp.x & 0xffff);
-        s2 += (long long)diff0 * (dp.x >> 16);
-        if (two) {
-          s1 += (long long)diff1 * (int)(short)(dp.y & 0xffff);
-          s2 += (long long)diff1 * (dp.y >> 16);
-        }
+        const unsigned q01 = __byte_perm(e01, 0, 0x3120), q23 = __byte_perm(e23, 0, 0x3120);   // (el0, el1, eh0, eh1)
+        aL1 = dp2a_lo_su(dq.x, q01, aL1); aH1 = dp2a_hi_su(dq.x, q01, aH1);
+        aL2 = dp2a_lo_su(dq.z, q01, aL2); aH2 = dp2a_hi_su(dq.z, q01, aH2);
+        aL1 = dp2a_lo_su(dq.y, q23, aL1); aH1 = dp2a_hi_su(dq.y, q23, aH1);
+        aL2 = dp2a_lo_su(dq.w, q23, aL2); aH2 = dp2a_hi_su(dq.w, q23, aH2);
       }
-      t0 = b0; t1 = b1; t2 = b2;
+      Rt = Rb; Rt2 = Rb2;
     };
     int y = y0;
     // four rows per step, every load of the step issued before the first use
     for (; y + 4 <= y1; y += 4) {
-      int b[4][3], ip[4];
-      int2 dp[4];
+      unsigned bl[4], bh[4];
+      int2 ip[4];
+      int4 dp[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const uint8_t* rk = INSIDE ? r + (size_t)(k + 1) * step : rowp(y + k + 1);
-        b[k][0] = rk[c0]; b[k][1] = rk[c1]; b[k][2] = two ? rk[c2] : 0;
-        ip[k] = *(const int*)(pI + k * wwp);
-        dp[k] = ABS ? make_int2(0, 0) : *(const int2*)(pD + k * wwp);
+        bl[k] = q[(k + 1) * stepw]; bh[k] = q[(k + 1) * stepw + 1];
+        ip[k] = *(const int2*)(pI + k * wwp);
+        dp[k] = ABS ? make_int4(0, 0, 0, 0) : pD[k * st.S];
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) one_row(b[k][0], b[k][1], b[k][2], ip[k], dp[k]);
-      if (INSIDE) r += 4 * step;
-      pI += 4 * wwp; pD += 4 * wwp;
+      for (int k = 0; k < 4; ++k) one_row(bl[k], bh[k], ip[k], dp[k]);
+      q += 4 * stepw;
+      pI += 4 * wwp; pD += 4 * st.S;
     }
     for (; y < y1; ++y) {
-      const uint8_t* rk = INSIDE ? r + step : rowp(y + 1);
-      if (INSIDE) r = rk;
-      one_row(rk[c0], rk[c1], two ? rk[c2] : 0, *(const int*)pI, ABS ? make_int2(0, 0) : *(const int2*)pD);
-      pI += wwp; pD += wwp;
+      q += stepw;
+      one_row(q[0], q[1], *(const int2*)pI, ABS ? make_int4(0, 0, 0, 0) : *pD);
+      pI += wwp; pD += st.S;
+    }
+    if (ABS) {
+      s1 += sabs;
+    } else {
+      s1 += (long long)aL1 + 256ll * aH1;
+      s2 += (long long)aL2 + 256ll * aH2;
     }
   }
 }
 
+// sIx, sIy: sums of the patch's Ixw / Iyw over this warp's rows (the 0x2000 offset of the packed differences)
 template <bool ABS>
-__device__ __forceinline__ void lk_window_pass(const uint8_t* __restrict__ J, size_t step, int w, int h, int ix,
-                                               int iy, int w00, int w01, int w10, int w11, const short* sI,
-                                               const short2* sD, int ww, int wh, int ya, int yb, int lane,
-                                               long long& o1, long long& o2) {
-  const bool inside = ix >= 0 && iy >= 0 && ix + ww < w && iy + wh < h;
+__device__ __forceinline__ void lk_window_pass(const uint8_t* __restrict__ J, size_t step, int ix, int iy, int w00,
+                                               int w01, int w10, int w11, const short* sI, const int4* sD, int ww,
+                                               int ya, int yb, int lane, long long sIx, long long sIy, long long& o1,
+                                               long long& o2) {
+  const unsigned wt = (unsigned)w00 | ((unsigned)w01 << 16), wb = (unsigned)w10 | ((unsigned)w11 << 16);
   long long s1 = 0, s2 = 0;
-  if (inside) lk_window_strips<ABS, true>(J, step, w, h, ix, iy, w00, w01, w10, w11, sI, sD, ww, ya, yb, lane, s1, s2);
-  else lk_window_strips<ABS, false>(J, step, w, h, ix, iy, w00, w01, w10, w11, sI, sD, ww, ya, yb, lane, s1, s2);
+  lk_window_strips<ABS>(J, step, ix, iy, wt, wb, sI, sD, ww, ya, yb, lane, s1, s2);
   o1 = warp_sum_ll(s1);
-  o2 = ABS ? 0 : warp_sum_ll(s2);
+  o2 = 0;
+  if (!ABS) {
+    o1 -= 0x2000ll * sIx;
+    o2 = warp_sum_ll(s2) - 0x2000ll * sIy;
+  }
 }
 
-// template patch (Iw, Ixw, Iyw) of the window at (ipx, ipy) + the three sums of the normal matrix.  Image pixels
-// outside the frame are BORDER_REFLECT_101, derivatives outside the frame are zero.
-template <bool INSIDE>
+// template patch (Iw, Ixw, Iyw) of the window at (ipx, ipy) + the three sums of the normal matrix and the plain sums
+// of Ixw, Iyw.  I and D point at element (0, 0) of levels stored with their borders (reflected pixels, zero
+// derivatives).
 __device__ __forceinline__ void lk_patch_strips(const uint8_t* __restrict__ I, const short2* __restrict__ D, size_t step,
-                                                int W, int H, int ipx, int ipy, int w00, int w01, int w10, int w11,
-                                                short* sI, short2* sD, int ww, int ya, int yb, int lane,
-                                                long long& sA11, long long& sA12, long long& sA22) {
+                                                size_t dstep, int ipx, int ipy, int w00, int w01, int w10, int w11,
+                                                short* sI, int4* sD, int ww, int ya, int yb, int lane,
+                                                long long& sA11, long long& sA12, long long& sA22, long long& sIx,
+                                                long long& sIy) {
   const int wwp = lk_wwp(ww);
-  const LkStrips st(ww, yb - ya);
+  const LkStrips<2> st(ww, yb - ya);
+  const int S4 = wwp >> 2;
+  int accx = 0, accy = 0;                          // |Ixw| <= 4080: 32 bits hold any window that fits shared memory
   for (int u = lane; u < st.S * st.G; u += 32) {
     const int g = u / st.S, sx = u - g * st.S;
     const int x0 = 2 * sx;
     const bool two = x0 + 1 < ww;
     const int y0 = ya + g * st.RG, y1 = min(yb, y0 + st.RG);
-    const int a0 = ipx + x0;                     // unreflected columns a0, a0 + 1, a0 + 2
-    int c0 = a0, c1 = a0 + 1, c2 = a0 + 2;
-    bool v0 = true, v1 = true, v2 = two;         // derivative columns inside the frame
-    if (!INSIDE) {
-      v0 = (unsigned)c0 < (unsigned)W; v1 = (unsigned)c1 < (unsigned)W; v2 = two && (unsigned)c2 < (unsigned)W;
-      c0 = reflect101(c0, W); c1 = reflect101(c1, W); c2 = reflect101(c2, W);
+    short* pI = sI + y0 * wwp + x0;
+    int* pD = (int*)(sD + y0 * S4 + (sx >> 1)) + (sx & 1);      // .x/.y: the Ix pair; + 2: the Iy pair
+    if (x0 >= ww) {                                // a strip of padding columns only
+      for (int y = y0; y < y1; ++y) {
+        *(int*)pI = 0; pD[0] = 0; pD[2] = 0;
+        pI += wwp; pD += 4 * S4;
+      }
+      continue;
     }
-    const short2 z = make_short2(0, 0);
-    auto load_row = [&](int y, int& i0, int& i1, int& i2, short2& d0, short2& d1, short2& d2) {
-      const int ya = ipy + y;
-      const uint8_t* r = I + (size_t)(INSIDE ? ya : reflect101(ya, H)) * step;
-      i0 = r[c0]; i1 = r[c1]; i2 = two ? r[c2] : 0;
-      const bool vy = INSIDE || (unsigned)ya < (unsigned)H;
-      const short2* dr = D + (size_t)(vy ? ya : 0) * W;
-      d0 = (vy && v0) ? dr[a0] : z;
-      d1 = (vy && v1) ? dr[a0 + 1] : z;
-      d2 = (vy && v2) ? dr[a0 + 2] : z;
+    const uint8_t* r = I + (ptrdiff_t)(ipy + y0) * (ptrdiff_t)step + (ipx + x0);
+    const short2* dr = D + (ptrdiff_t)(ipy + y0) * (ptrdiff_t)dstep + (ipx + x0);
+    auto load_row = [&](int& i0, int& i1, int& i2, short2& d0, short2& d1, short2& d2) {
+      i0 = r[0]; i1 = r[1]; i2 = r[2];
+      d0 = dr[0]; d1 = dr[1]; d2 = dr[2];
+      r += step; dr += dstep;
     };
     int t0, t1, t2;
     short2 e0, e1, e2;
-    load_row(y0, t0, t1, t2, e0, e1, e2);
-    short* pI = sI + y0 * wwp + x0;
-    short2* pD = sD + y0 * wwp + x0;
+    load_row(t0, t1, t2, e0, e1, e2);
+    int q11 = 0, q12 = 0, q22 = 0;                 // widened every four rows
+    auto flush = [&]() { sA11 += q11; sA12 += q12; sA22 += q22; q11 = q12 = q22 = 0; };
 #pragma unroll 2
     for (int y = y0; y < y1; ++y) {
       int b0, b1, b2;
       short2 f0, f1, f2;
-      load_row(y + 1, b0, b1, b2, f0, f1, f2);
+      load_row(b0, b1, b2, f0, f1, f2);
       const int iv0 = t0 * w00 + t1 * w01 + b0 * w10 + b1 * w11;
       const int iv1 = t1 * w00 + t2 * w01 + b1 * w10 + b2 * w11;
       const int dx0 = e0.x * w00 + e1.x * w01 + f0.x * w10 + f1.x * w11;
@@ -281,17 +347,22 @@ __device__ __forceinline__ void lk_patch_strips(const uint8_t* __restrict__ I, c
       int ival1 = (iv1 + 256) >> 9, ixv1 = (dx1 + 8192) >> 14, iyv1 = (dy1 + 8192) >> 14;
       if (!two) ival1 = ixv1 = iyv1 = 0;             // padding column of an odd-width window
       *(int*)pI = (ival0 & 0xffff) | (ival1 << 16);
-      *(int2*)pD = make_int2((ixv0 & 0xffff) | (iyv0 << 16), (ixv1 & 0xffff) | (iyv1 << 16));
-      sA11 += (long long)ixv0 * ixv0 + (long long)ixv1 * ixv1;
-      sA12 += (long long)ixv0 * iyv0 + (long long)ixv1 * iyv1;
-      sA22 += (long long)iyv0 * iyv0 + (long long)iyv1 * iyv1;
+      pD[0] = (ixv0 & 0xffff) | (ixv1 << 16);
+      pD[2] = (iyv0 & 0xffff) | (iyv1 << 16);
+      q11 += ixv0 * ixv0 + ixv1 * ixv1;            // |Ixw| <= 4080: eight products fit 32 bits with room to spare
+      q12 += ixv0 * iyv0 + ixv1 * iyv1;
+      q22 += iyv0 * iyv0 + iyv1 * iyv1;
+      accx += ixv0 + ixv1; accy += iyv0 + iyv1;
       t0 = b0; t1 = b1; t2 = b2; e0 = f0; e1 = f1; e2 = f2;
-      pI += wwp; pD += wwp;
+      pI += wwp; pD += 4 * S4;
+      if (((y - y0) & 3) == 3) flush();
     }
+    flush();
   }
+  sIx += accx; sIy += accy;
 }
 
-__global__ void __launch_bounds__(LK_WARPS * 32) lk_track(LkArgs a) {
+__global__ void __launch_bounds__(LK_WARPS * 32, 512 / (LK_WARPS * 32)) lk_track(LkArgs a) {
   extern __shared__ __align__(16) unsigned char lk_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int feat = warp / LK_SPLIT, half = warp - feat * LK_SPLIT;
@@ -325,7 +396,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_track(LkArgs a) {
     xpar ^= 1;        // the next exchange uses the other slot: this one is re-written only after another barrier
   };
   short* sI = (short*)(lk_smem + feat * per_warp);                 // [wh][wwp] int16
-  short2* sD = (short2*)(sI + (((size_t)wwp * wh + 3) & ~(size_t)3));   // [wh][wwp] (Ixw, Iyw), 8-byte aligned
+  int4* sD = (int4*)(lk_smem + feat * per_warp + lk_iw_bytes(ww, wh));   // [wh][wwp / 4] packed (Ixw, Iyw) records
   const uint8_t* PI = a.pyr_i + (size_t)b * a.L.pyr_bytes;
   const uint8_t* PJ = a.pyr_j + (size_t)b * a.L.pyr_bytes;
   const short2* DV = a.deriv + (size_t)b * a.L.deriv_elems;
@@ -342,7 +413,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_track(LkArgs a) {
   const int max_level = a.L.n - 1;
   for (int level = max_level; level >= 0; --level) {
     const int W = a.L.w[level], H = a.L.h[level];
-    const size_t step = a.L.step[level];
+    const size_t step = a.L.step[level], dstep = a.L.dstep[level];
     const uint8_t* I = PI + a.L.off[level];
     const uint8_t* J = PJ + a.L.off[level];
     const short2* D = DV + a.L.doff[level];
@@ -365,13 +436,13 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_track(LkArgs a) {
     int w00, w01, w10, w11;
     lk_weights(px - ipx, py - ipy, w00, w01, w10, w11);
     // ---- template patch + normal matrix ----
-    long long sA11 = 0, sA12 = 0, sA22 = 0;
+    long long sA11 = 0, sA12 = 0, sA22 = 0, sIx = 0, sIy = 0;
     {
-      const bool inside = ipx >= 0 && ipy >= 0 && ipx + ww < W && ipy + wh < H;
       __syncwarp();
-      if (inside) lk_patch_strips<true>(I, D, step, W, H, ipx, ipy, w00, w01, w10, w11, sI, sD, ww, ya, yb, lane, sA11, sA12, sA22);
-      else lk_patch_strips<false>(I, D, step, W, H, ipx, ipy, w00, w01, w10, w11, sI, sD, ww, ya, yb, lane, sA11, sA12, sA22);
+      lk_patch_strips(I, D, step, dstep, ipx, ipy, w00, w01, w10, w11, sI, sD, ww, ya, yb, lane, sA11, sA12, sA22, sIx,
+                      sIy);
       sA11 = warp_sum_ll(sA11); sA12 = warp_sum_ll(sA12); sA22 = warp_sum_ll(sA22);
+      sIx = warp_sum_ll(sIx); sIy = warp_sum_ll(sIy);
       __syncwarp();
       feature_sum(sA11, sA12, sA22, 3);
     }
@@ -398,7 +469,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_track(LkArgs a) {
       }
       lk_weights(qx - ix, qy - iy, w00, w01, w10, w11);
       long long s1, s2, s3 = 0;
-      lk_window_pass<false>(J, step, W, H, ix, iy, w00, w01, w10, w11, sI, sD, ww, wh, ya, yb, lane, s1, s2);
+      lk_window_pass<false>(J, step, ix, iy, w00, w01, w10, w11, sI, sD, ww, ya, yb, lane, sIx, sIy, s1, s2);
       feature_sum(s1, s2, s3, 2);
       float b1 = __fmul_rn((float)s1, FLT_SCALE), b2 = __fmul_rn((float)s2, FLT_SCALE);
       float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), Dt);
@@ -420,7 +491,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_track(LkArgs a) {
       } else {
         lk_weights(ex - ix, ey - iy, w00, w01, w10, w11);
         long long s1, s2, s3 = 0;
-        lk_window_pass<true>(J, step, W, H, ix, iy, w00, w01, w10, w11, sI, sD, ww, wh, ya, yb, lane, s1, s2);
+        lk_window_pass<true>(J, step, ix, iy, w00, w01, w10, w11, sI, sD, ww, ya, yb, lane, sIx, sIy, s1, s2);
         feature_sum(s1, s2, s3, 1);
         err = __fmul_rn((float)s1, 1.f / (float)(32 * ww * wh));
       }
@@ -474,6 +545,44 @@ __global__ void __launch_bounds__(256) lk_stage_level0(const uint8_t* __restrict
   }
 }
 
+// Border of one level of every pyramid block (LkLevels): word (4 columns) per thread over the top band, the bottom
+// band and the two side bands of the padded block.  Image words are assembled from BORDER_REFLECT_101 pixels (a side
+// word that straddles the frame edge rewrites its interior bytes with themselves); derivative borders are zeros.
+__global__ void __launch_bounds__(256) lk_pad_borders(uint8_t* __restrict__ img, size_t img_bstride, short2* __restrict__ der,
+                                                       size_t der_bstride, int n_der, size_t base, size_t dbase,
+                                                       size_t step, int w, int h, int pad_x, int pad_y) {
+  const int wpr = (int)(step >> 2);                       // words per padded row
+  const int lw = pad_x >> 2, rw0 = (pad_x + w) >> 2;      // side bands: words [0, lw) and [rw0, wpr)
+  const int side = lw + (wpr - rw0);
+  const int band = 2 * pad_y * wpr;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= band + h * side) return;
+  int Y, Xw;                                              // padded coordinates (row, word)
+  if (t < band) {
+    Y = t / wpr; Xw = t - Y * wpr;
+    if (Y >= pad_y) Y += h;
+  } else {
+    const int u = t - band;
+    const int r = u / side, c = u - r * side;
+    Y = pad_y + r; Xw = c < lw ? c : rw0 + (c - lw);
+  }
+  uint8_t* ib = img + blockIdx.y * img_bstride + base;
+  const uint8_t* src = ib + (size_t)pad_y * step + pad_x + (size_t)reflect101(Y - pad_y, h) * step;
+  unsigned v = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v |= (unsigned)src[reflect101(4 * Xw + k - pad_x, w)] << (8 * k);
+  *(unsigned*)(ib + (size_t)Y * step + 4 * Xw) = v;
+  if ((int)blockIdx.y < n_der) {
+    short2* db = der + blockIdx.y * der_bstride + dbase + (size_t)Y * step + 4 * Xw;
+    const bool row_in = Y >= pad_y && Y < pad_y + h;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = 4 * Xw + k - pad_x;
+      if (!(row_in && x >= 0 && x < w)) db[k] = make_short2(0, 0);
+    }
+  }
+}
+
 int pyrlk_dev(const uint8_t* prev, const uint8_t* next, size_t step, size_t frame_stride, int batch, int rows, int cols,
               const float* prev_pts, size_t pts_bstride, int n_pts, float* next_pts, uint8_t* status, float* err,
               const b2of_lk_params* p, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -500,7 +609,7 @@ int pyrlk_dev(const uint8_t* prev, const uint8_t* next, size_t step, size_t fram
       // one launch for the whole batch (blockIdx.z = batch item) instead of one 2-D copy per image
       const bool vec = (((uintptr_t)src | step | frame_stride | (uintptr_t)dst | a.L.pyr_bytes) & 15) == 0;   // (destination steps are 16-byte multiples)
       const int units = vec ? cdiv(cols, 16) : cols;
-      lk_stage_level0<<<dim3(cdiv(units, 256), rows, batch), 256, 0, st>>>(src, step, frame_stride, dst, a.L.step[0],
+      lk_stage_level0<<<dim3(cdiv(units, 256), rows, batch), 256, 0, st>>>(src, step, frame_stride, dst + a.L.off[0], a.L.step[0],
                                                                          a.L.pyr_bytes, cols, vec ? 1 : 0);
       B2OF_LAUNCH_CHECK();
     } else {
@@ -520,8 +629,19 @@ int pyrlk_dev(const uint8_t* prev, const uint8_t* next, size_t step, size_t fram
     {
       ProfScope ps(PT_LK_SCHARR, st, batch * 5.0 * a.L.w[l] * a.L.h[l]);
       lk_scharr<<<grid, 256, 0, st>>>(pi + a.L.off[l], a.L.step[l], a.L.pyr_bytes, a.L.w[l], a.L.h[l], dv + a.L.doff[l],
-                                      a.L.deriv_elems);
+                                      a.L.deriv_elems, a.L.dstep[l]);
     }
+    B2OF_LAUNCH_CHECK();
+  }
+  // borders of every level: both pyramids (pi and pj are adjacent: 2 x batch blocks) and the derivatives of the first
+  for (int l = 0; l < a.L.n; ++l) {
+    const int wpr = (int)(a.L.step[l] >> 2);
+    const int side = (a.L.pad_x >> 2) + (wpr - ((a.L.pad_x + a.L.w[l]) >> 2));
+    const int total = 2 * a.L.pad_y * wpr + a.L.h[l] * side;
+    ProfScope ps(PT_LK_SCHARR, st, 2.0 * batch * 4.0 * total);
+    lk_pad_borders<<<dim3(cdiv(total, 256), 2 * batch), 256, 0, st>>>(pi, a.L.pyr_bytes, dv, a.L.deriv_elems, batch,
+                                                                      a.L.base[l], a.L.dbase[l], a.L.step[l], a.L.w[l],
+                                                                      a.L.h[l], a.L.pad_x, a.L.pad_y);
     B2OF_LAUNCH_CHECK();
   }
   a.pyr_i = pi; a.pyr_j = pj; a.deriv = dv;
