@@ -296,65 +296,81 @@ __device__ __forceinline__ void lk_window_pass(const uint8_t* __restrict__ J, si
 
 // template patch (Iw, Ixw, Iyw) of the window at (ipx, ipy) + the three sums of the normal matrix and the plain sums
 // of Ixw, Iyw.  I and D point at element (0, 0) of levels stored with their borders (reflected pixels, zero
-// derivatives).
+// derivatives).  Same four-column strips as the window walk: the image row comes in as two aligned words and Iw takes
+// eight IDP.2A; the five (Ix, Iy) pairs of a derivative row are unpacked once and serve four elements (the 16 x 16-bit
+// products have no packed form: 32 IMADs per strip row, which is what bounds this loop).  One 8-byte and one 16-byte
+// store per strip row.
 __device__ __forceinline__ void lk_patch_strips(const uint8_t* __restrict__ I, const short2* __restrict__ D, size_t step,
                                                 size_t dstep, int ipx, int ipy, int w00, int w01, int w10, int w11,
                                                 short* sI, int4* sD, int ww, int ya, int yb, int lane,
                                                 long long& sA11, long long& sA12, long long& sA22, long long& sIx,
                                                 long long& sIy) {
   const int wwp = lk_wwp(ww);
-  const LkStrips<2> st(ww, yb - ya);
-  const int S4 = wwp >> 2;
+  const LkStrips<4> st(ww, yb - ya);
+  const unsigned wt = (unsigned)w00 | ((unsigned)w01 << 16), wb = (unsigned)w10 | ((unsigned)w11 << 16);
+  const ptrdiff_t stepw = (ptrdiff_t)(step >> 2);
   int accx = 0, accy = 0;                          // |Ixw| <= 4080: 32 bits hold any window that fits shared memory
   for (int u = lane; u < st.S * st.G; u += 32) {
     const int g = u / st.S, sx = u - g * st.S;
-    const int x0 = 2 * sx;
-    const bool two = x0 + 1 < ww;
+    const int x0 = 4 * sx;
+    const int nv = ww - x0;                        // elements x0 + k with k >= nv are padding and are stored as zeros
     const int y0 = ya + g * st.RG, y1 = min(yb, y0 + st.RG);
-    short* pI = sI + y0 * wwp + x0;
-    int* pD = (int*)(sD + y0 * S4 + (sx >> 1)) + (sx & 1);      // .x/.y: the Ix pair; + 2: the Iy pair
-    if (x0 >= ww) {                                // a strip of padding columns only
-      for (int y = y0; y < y1; ++y) {
-        *(int*)pI = 0; pD[0] = 0; pD[2] = 0;
-        pI += wwp; pD += 4 * S4;
-      }
-      continue;
+    const uint8_t* p0 = I + (ptrdiff_t)(ipy + y0) * (ptrdiff_t)step + (ipx + x0);
+    const unsigned sh = ((unsigned)(uintptr_t)p0 & 3u) * 8u;
+    const uint32_t* q = (const uint32_t*)(p0 - ((uintptr_t)p0 & 3));
+    const int* dr = (const int*)(D + (ptrdiff_t)(ipy + y0) * (ptrdiff_t)dstep + (ipx + x0));
+    unsigned Rt, Rt2;
+    int ex[5], ey[5];                              // the row above: unpacked derivatives of columns x0 .. x0 + 4
+    auto unpack = [](int v, int& x, int& y) { x = (int)(short)(v & 0xffff); y = v >> 16; };
+    {
+      const unsigned lo = q[0], hi = q[1];
+      Rt = __funnelshift_r(lo, hi, sh); Rt2 = __funnelshift_rc(lo, hi, sh + 8u);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) unpack(dr[k], ex[k], ey[k]);
     }
-    const uint8_t* r = I + (ptrdiff_t)(ipy + y0) * (ptrdiff_t)step + (ipx + x0);
-    const short2* dr = D + (ptrdiff_t)(ipy + y0) * (ptrdiff_t)dstep + (ipx + x0);
-    auto load_row = [&](int& i0, int& i1, int& i2, short2& d0, short2& d1, short2& d2) {
-      i0 = r[0]; i1 = r[1]; i2 = r[2];
-      d0 = dr[0]; d1 = dr[1]; d2 = dr[2];
-      r += step; dr += dstep;
-    };
-    int t0, t1, t2;
-    short2 e0, e1, e2;
-    load_row(t0, t1, t2, e0, e1, e2);
+    int2* pI = (int2*)(sI + y0 * wwp + x0);
+    int4* pD = sD + y0 * st.S + sx;
     int q11 = 0, q12 = 0, q22 = 0;                 // widened every four rows
     auto flush = [&]() { sA11 += q11; sA12 += q12; sA22 += q22; q11 = q12 = q22 = 0; };
 #pragma unroll 2
     for (int y = y0; y < y1; ++y) {
-      int b0, b1, b2;
-      short2 f0, f1, f2;
-      load_row(b0, b1, b2, f0, f1, f2);
-      const int iv0 = t0 * w00 + t1 * w01 + b0 * w10 + b1 * w11;
-      const int iv1 = t1 * w00 + t2 * w01 + b1 * w10 + b2 * w11;
-      const int dx0 = e0.x * w00 + e1.x * w01 + f0.x * w10 + f1.x * w11;
-      const int dy0 = e0.y * w00 + e1.y * w01 + f0.y * w10 + f1.y * w11;
-      const int dx1 = e1.x * w00 + e2.x * w01 + f1.x * w10 + f2.x * w11;
-      const int dy1 = e1.y * w00 + e2.y * w01 + f1.y * w10 + f2.y * w11;
-      const int ival0 = (iv0 + 256) >> 9, ixv0 = (dx0 + 8192) >> 14, iyv0 = (dy0 + 8192) >> 14;
-      int ival1 = (iv1 + 256) >> 9, ixv1 = (dx1 + 8192) >> 14, iyv1 = (dy1 + 8192) >> 14;
-      if (!two) ival1 = ixv1 = iyv1 = 0;             // padding column of an odd-width window
-      *(int*)pI = (ival0 & 0xffff) | (ival1 << 16);
-      pD[0] = (ixv0 & 0xffff) | (ixv1 << 16);
-      pD[2] = (iyv0 & 0xffff) | (iyv1 << 16);
-      q11 += ixv0 * ixv0 + ixv1 * ixv1;            // |Ixw| <= 4080: eight products fit 32 bits with room to spare
-      q12 += ixv0 * iyv0 + ixv1 * iyv1;
-      q22 += iyv0 * iyv0 + iyv1 * iyv1;
-      accx += ixv0 + ixv1; accy += iyv0 + iyv1;
-      t0 = b0; t1 = b1; t2 = b2; e0 = f0; e1 = f1; e2 = f2;
-      pI += wwp; pD += 4 * S4;
+      q += stepw; dr += dstep;
+      const unsigned lo = q[0], hi = q[1];
+      int dv[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) dv[k] = dr[k];
+      const unsigned Rb = __funnelshift_r(lo, hi, sh), Rb2 = __funnelshift_rc(lo, hi, sh + 8u);
+      const unsigned v0 = __dp2a_lo(wb, Rb, __dp2a_lo(wt, Rt, 256u));
+      const unsigned v1 = __dp2a_lo(wb, Rb2, __dp2a_lo(wt, Rt2, 256u));
+      const unsigned v2 = __dp2a_hi(wb, Rb, __dp2a_hi(wt, Rt, 256u));
+      const unsigned v3 = __dp2a_hi(wb, Rb2, __dp2a_hi(wt, Rt2, 256u));
+      unsigned iw01 = __byte_perm(v0 >> 9, v1 >> 9, 0x5410), iw23 = __byte_perm(v2 >> 9, v3 >> 9, 0x5410);
+      int fx[5], fy[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) unpack(dv[k], fx[k], fy[k]);
+      int ix[4], iy[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        ix[k] = (ex[k] * w00 + ex[k + 1] * w01 + fx[k] * w10 + fx[k + 1] * w11 + 8192) >> 14;
+        iy[k] = (ey[k] * w00 + ey[k + 1] * w01 + fy[k] * w10 + fy[k + 1] * w11 + 8192) >> 14;
+      }
+      if (nv < 4) {                                // the window's last strip
+        if (nv < 2) { ix[1] = iy[1] = 0; iw01 &= 0xffffu; }
+        if (nv < 3) { ix[2] = iy[2] = 0; iw23 = 0; }
+        ix[3] = iy[3] = 0; iw23 &= 0xffffu;
+      }
+      *pI = make_int2((int)iw01, (int)iw23);
+      *pD = make_int4((int)__byte_perm(ix[0], ix[1], 0x5410), (int)__byte_perm(ix[2], ix[3], 0x5410),
+                      (int)__byte_perm(iy[0], iy[1], 0x5410), (int)__byte_perm(iy[2], iy[3], 0x5410));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {                // |Ixw| <= 4080: sixteen products fit 32 bits with room to spare
+        q11 += ix[k] * ix[k]; q12 += ix[k] * iy[k]; q22 += iy[k] * iy[k];
+      }
+      accx += (ix[0] + ix[1]) + (ix[2] + ix[3]); accy += (iy[0] + iy[1]) + (iy[2] + iy[3]);
+      Rt = Rb; Rt2 = Rb2;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) { ex[k] = fx[k]; ey[k] = fy[k]; }
+      pI += wwp >> 2; pD += st.S;
       if (((y - y0) & 3) == 3) flush();
     }
     flush();

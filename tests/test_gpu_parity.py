@@ -360,6 +360,28 @@ def test_lk_edge_points_and_oracle(b2, crops):
         assert np.abs(got[0] - want[0]).max() <= LK_POS_TOL
 
 
+def test_lk_border_band_random_points_vs_oracle(b2, crops):
+    """Windows that stick out of the frame on every side (the levels are stored with reflected borders and zero
+    derivative borders; the oracle reflects per access): 480 random points in the band of one window size around
+    the frame edge, positions, statuses and errors."""
+    from oracle import pyrlk as olk
+    g0, g1 = crops["gray0_2"], crops["gray1_2"]
+    H, W = g0.shape
+    rng = np.random.default_rng(5)
+    for win, lvl in [((45, 45), 2), ((15, 15), 2), ((13, 27), 1)]:
+        bx, by = win[0] + 1, win[1] + 1
+        pts = np.concatenate([rng.uniform([-bx, -by], [W + bx, by], (120, 2)), rng.uniform([-bx, H - by], [W + bx, H + by], (120, 2)),
+                              rng.uniform([-bx, -by], [bx, H + by], (120, 2)), rng.uniform([W - bx, -by], [W + bx, H + by], (120, 2))
+                              ]).astype(np.float32)
+        want = olk.pyrlk(g1, g0, pts, None, win, lvl, (3, 10, 0.03))
+        got = b2.calcOpticalFlowPyrLK(g1, g0, pts, None, winSize=win, maxLevel=lvl, criteria=(3, 10, 0.03))
+        assert np.array_equal(got[1], want[1]), (win, np.flatnonzero(got[1].ravel() != want[1].ravel()))
+        ok = want[1].ravel() == 1
+        assert ok.sum() >= 40
+        assert np.abs(got[0] - want[0])[ok].max() <= LK_POS_TOL
+        assert np.allclose(got[2].ravel()[ok], want[2].ravel()[ok], rtol=1e-3, atol=1e-4)
+
+
 def test_lk_initial_flow_and_min_eig_flags(b2, crops):
     from oracle import pyrlk as olk
     from hackathonopticalflow_b200 import pathfinder
