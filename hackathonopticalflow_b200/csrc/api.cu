@@ -56,6 +56,7 @@ size_t farneback_workspace_bytes(int, int, const b2of_farneback_params*, int, in
 int farneback_dev(const uint8_t*, const uint8_t*, size_t, size_t, int, int, int, int, const b2of_farneback_params*,
                   float*, float*, void*, size_t, cudaStream_t);
 void farneback_release();
+void farneback_release_streams();
 size_t pyrlk_workspace_bytes(int, int, const b2of_lk_params*, int);
 int pyrlk_dev(const uint8_t*, const uint8_t*, size_t, size_t, int, int, int, const float*, size_t, int, float*,
               uint8_t*, float*, const b2of_lk_params*, void*, size_t, cudaStream_t);
@@ -165,6 +166,7 @@ int b2of_release(void) {
   }
   cudaSetDevice(cur);
   farneback_release();
+  farneback_release_streams();
   b2of_profile_reset();
   return B2OF_OK;
 }

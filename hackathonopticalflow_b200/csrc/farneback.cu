@@ -1984,10 +1984,15 @@ static void set_func_attrs() {
 int flow_stats_dev(const float*, int, int, int, float*, cudaStream_t);          // pathfinder.cu
 int flow_stats_finalize_dev(float*, size_t, int, cudaStream_t);
 
-static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fstep, int total_slots, float* flow_out,
-                    float* stats, const b2of_farneback_params& p, cudaStream_t st) {
+// Pairs [pair0, pair0 + pairs) of a chunk of pairs_total pairs whose per-frame work (fb_frames) is in the workspace.
+// `concurrent`: another range of the same chunk runs on a second stream at the same time (fb_pairs).
+static int fb_pairs_range(const FbPlan* pl, const FbWorkspace& ws, int pairs_total, int pair0, int pairs, int fstep,
+                          int total_slots, float* flow_out, float* stats, const b2of_farneback_params& p,
+                          bool concurrent, cudaStream_t st) {
   // `p` is THIS call's parameter block: the cached plan only fixes what its key holds (sizes, windows, taps)
   const int call_flags = p.flags;
+  flow_out += (size_t)pair0 * pl->rows * pl->cols * 2;
+  if (stats) stats += (size_t)pair0 * B2OF_STATS_WIDTH;
   const int m = p.winsize / 2;
   const bool gauss = (p.flags & B2OF_OPTFLOW_FARNEBACK_GAUSSIAN) != 0;
   // the reference's window runs on the strip kernel; anything else on the general kernel with the largest tile whose
@@ -2014,10 +2019,10 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
     const FbLevel& L = pl->lv[li];
     const bool last_level = li + 1 == pl->lv.size();
     size_t plane = (size_t)L.h * L.pitch;
-    float2* A = ws.FA + (size_t)pairs * lvl_off;
-    float2* B = ws.FB + (size_t)pairs * lvl_off;
+    float2* A = ws.FA + (size_t)pairs_total * lvl_off + (size_t)pair0 * plane;
+    float2* B = ws.FB + (size_t)pairs_total * lvl_off + (size_t)pair0 * plane;
     IterArgs a{};
-    a.R = ws.R + (size_t)total_slots * 5 * lvl_off;
+    a.R = ws.R + (size_t)total_slots * 5 * lvl_off + (size_t)pair0 * fstep * 5 * plane;
     a.r_frame_stride = 5 * plane;
     a.plane_stride = plane;
     a.pitch = L.pitch; a.w = L.w; a.h = L.h;
@@ -2138,7 +2143,10 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
           long long best_cost = -1;
           for (int nbc = FBW_REFRESH; nbc <= cdiv(blocks, FBW_REFRESH) * FBW_REFRESH; nbc += FBW_REFRESH) {
             const long long ctas = (long long)pairs * nstrips * cdiv(blocks, nbc);
-            const long long cost = ((ctas + n_sm - 1) / n_sm) * (nbc * FBW_RB + 30);
+            const long long rows = (nbc < blocks ? nbc : blocks) * FBW_RB + 30;
+            // with a second range of the chunk on another stream the SMs a partial last wave leaves idle run that
+            // range's CTAs: what counts is the total work, as long as this launch alone can fill the machine
+            const long long cost = (concurrent && ctas >= n_sm) ? ctas * rows : ((ctas + n_sm - 1) / n_sm) * rows * n_sm;
             if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best_nb = nbc; }
           }
           b.nb = best_nb;
@@ -2169,6 +2177,78 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
     return flow_stats_dev(flow_out, pairs, pl->rows, pl->cols, stats, st);
   }
   return B2OF_OK;
+}
+
+// Side streams of a device (fb_pairs), created on first use, destroyed by b2of_release().
+constexpr int FB_MAX_RANGES = 8;
+struct FbFork { cudaStream_t s[FB_MAX_RANGES - 1] = {}; cudaEvent_t fork = nullptr, join[FB_MAX_RANGES - 1] = {}; bool ok = false; };
+static FbFork g_fork[B2OF_MAX_DEVICES];
+static std::mutex g_fork_mu;
+
+static FbFork* get_fork() {
+  std::lock_guard<std::mutex> lock(g_fork_mu);
+  FbFork& f = g_fork[current_device()];
+  if (!f.ok) {
+    bool good = cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < FB_MAX_RANGES - 1 && good; ++i)
+      good = cudaStreamCreateWithFlags(&f.s[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&f.join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!good) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    f.ok = true;
+  }
+  return &f;
+}
+
+void farneback_release_streams() {
+  std::lock_guard<std::mutex> lock(g_fork_mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < B2OF_MAX_DEVICES; ++d) {
+    FbFork& f = g_fork[d];
+    if (!f.ok) continue;
+    cudaSetDevice(d);
+    cudaEventDestroy(f.fork);
+    for (int i = 0; i < FB_MAX_RANGES - 1; ++i) { cudaStreamDestroy(f.s[i]); cudaEventDestroy(f.join[i]); }
+    f = FbFork();
+  }
+  cudaSetDevice(cur);
+}
+
+#ifndef FB_RANGES
+#define FB_RANGES 4
+#endif
+// The pairs of a chunk are independent once the per-frame work is done.  A chunk of sixteen pairs or more is walked as
+// two, and one of 32 or more as FB_RANGES = 4, contiguous ranges on as many streams (measured at 64 pairs, 1080p: one
+// stream 7207 pairs/s, two 7500, three 7470, four 7630, six 7450, eight 7680): every launch of the level / iteration sequence then has launches of
+// the other ranges queued next to it, and the SMs that a partial last wave of CTAs would leave idle (one 160 KB CTA
+// per SM: 7.8 waves at the finest level of 64 pairs, 2.2 and 1.3 at the two coarsest) pick up their CTAs.  Same
+// kernels, same arguments per pair, same bits.  With per-kernel profiling on (b2of_profile_enable) the chunk runs as
+// one range on the caller's stream, so that a launch's events time that launch alone.
+static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fstep, int total_slots, float* flow_out,
+                    float* stats, const b2of_farneback_params& p, cudaStream_t st) {
+  static const int n_env = getenv("B2OF_STREAMS") ? atoi(getenv("B2OF_STREAMS")) : FB_RANGES;   // developer A/B knob
+  int nr = 1;                                    // a power of two, at least eight pairs per range
+  while (2 * nr <= n_env && 2 * nr <= FB_MAX_RANGES && pairs >= 16 * nr) nr *= 2;
+  const bool fast = !(p.flags & B2OF_OPTFLOW_FARNEBACK_GAUSSIAN) && p.winsize / 2 == FBS_M;
+  FbFork* f = nullptr;
+  if (nr > 1 && fast && p.iterations > 0 && g_prof_on.load(std::memory_order_relaxed) == 0)
+    f = get_fork();
+  if (!f) return fb_pairs_range(pl, ws, pairs, 0, pairs, fstep, total_slots, flow_out, stats, p, false, st);
+  B2OF_CUDA(cudaEventRecord(f->fork, st));
+  int rc = 0;
+  for (int r = 0; r < nr; ++r) {
+    const int p0 = (int)((long long)pairs * r / nr), p1 = (int)((long long)pairs * (r + 1) / nr);
+    cudaStream_t sr = r == 0 ? st : f->s[r - 1];
+    if (r > 0) cudaStreamWaitEvent(sr, f->fork, 0);
+    const int rcr = fb_pairs_range(pl, ws, pairs, p0, p1 - p0, fstep, total_slots, flow_out, stats, p, true, sr);
+    if (rcr && !rc) rc = rcr;
+    // always join: the caller's stream must not run ahead of a side stream, error or not
+    if (r > 0) { cudaEventRecord(f->join[r - 1], sr); cudaStreamWaitEvent(st, f->join[r - 1], 0); }
+  }
+  return rc;
 }
 
 int farneback_dev(const uint8_t* prev, const uint8_t* next, size_t step, size_t frame_stride, int n_pairs, int shared,

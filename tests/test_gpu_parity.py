@@ -257,6 +257,26 @@ def test_farneback_result_independent_of_batch_split(batch):
         assert torch.equal(ref, got), chunk
 
 
+def test_farneback_chunk_ranges_on_side_streams_equal_single_pairs(batch):
+    """A chunk of 32 pairs or more is walked as four contiguous ranges on four streams (fb_pairs): flow fields and
+    per-pair statistics must equal what pair-at-a-time calls give, bit for bit; uneven range sizes included."""
+    import torch
+    from hackathonopticalflow_b200 import synth
+    fr = synth.sequence(135, 241, 8, seed=1004)
+    frames = torch.from_numpy(np.ascontiguousarray(fr[[i % 8 for i in range(39)]])).cuda()      # 38 pairs
+    stats = torch.empty((38, 8), dtype=torch.float32, device="cuda")
+    got = batch.FarnebackEngine(135, 241, chunk_pairs=38).flow_sequence(frames, stats=stats)
+    torch.cuda.synchronize()
+    one = batch.FarnebackEngine(135, 241, chunk_pairs=1)
+    st1 = torch.empty((38, 8), dtype=torch.float32, device="cuda")
+    want = one.flow_sequence(frames, stats=st1)
+    assert torch.equal(got, want)
+    assert torch.equal(stats, st1)
+    # and again into the same buffers right away: the side streams are joined before the call returns its stream
+    got2 = batch.FarnebackEngine(135, 241, chunk_pairs=38).flow_sequence(frames, got, stats=stats)
+    assert torch.equal(got2, want) and torch.equal(stats, st1)
+
+
 def test_farneback_live_cv2_1080p_and_720p(b2, seq1080):
     import cv2
     from hackathonopticalflow_b200 import synth
