@@ -343,9 +343,9 @@ def main():
     launches = lib.b2of_launch_count() - launches0
     clocks = sampler.stop(t0, t1) if sampler else None
     # Per-kernel pass: the same K steps again with the library's per-launch CUDA events on.  In the timed region
-    # above the library walks the two halves of a 64-pair chunk on two streams (a partial last wave of one launch is
-    # filled by the other half's CTAs), where a launch's events would time both halves' kernels interleaved; with the
-    # events on, the chunk runs as one range on one stream and every launch is timed alone.
+    # above the library walks a 64-pair chunk as four ranges of pairs on four streams (a partial last wave of one
+    # launch is filled by the other ranges' CTAs), where a launch's events would time several ranges' kernels
+    # interleaved; with the events on, the chunk runs as one range on one stream and every launch is timed alone.
     _lib.profile(True, reset=True)
     barrier()
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -451,8 +451,8 @@ def main():
                           "frac": path_gbs / peak, "note": "whole dense-flow path per GPU, SURVEY 8(d) B_stream"},
         "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
         "kernel_timing_pass": {"ms_per_step": serial_ms, "sum_of_kernels_ms": total_ms / args.steps,
-                               "note": "one stream, per-launch events on; the timed region (ms_per_step) runs the "
-                                       "chunk's two halves on two streams with the events off"},
+                               "note": "one stream, per-launch events on; the timed region (ms_per_step) walks the "
+                                       "chunk as four ranges of pairs on four streams with the events off"},
     }
     if world == 1 and not args.no_cpu:
         from oracle import cv2_reference as ref
