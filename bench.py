@@ -250,7 +250,6 @@ def pipeline_4k_record(rank, world, dev, pairs=8, steps=3):
     if world > 1:
         tdist.barrier()
     torch.cuda.synchronize()
-    _lib.profile(True, reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -260,6 +259,10 @@ def pipeline_4k_record(rank, world, dev, pairs=8, steps=3):
         tdist.barrier()
     torch.cuda.synchronize()
     ms = b2dist.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+    _lib.profile(True, reset=True)               # per-kernel pass (one stream, per-launch events), as in main()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
     prof = _lib.profile()
     _lib.profile(False, reset=True)
     rec = {"pairs_per_s": world * pairs / (ms * 1e-3), "ms_per_step": ms, "pairs_per_gpu_per_step": pairs,

@@ -2218,7 +2218,7 @@ void farneback_release_streams() {
 }
 
 #ifndef FB_RANGES
-#define FB_RANGES 4
+#define FB_RANGES 8
 #endif
 // The pairs of a chunk are independent once the per-frame work is done.  A chunk of sixteen pairs or more is walked as
 // two, and one of 32 or more as FB_RANGES = 4, contiguous ranges on as many streams (measured at 64 pairs, 1080p: one
@@ -2230,8 +2230,13 @@ void farneback_release_streams() {
 static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fstep, int total_slots, float* flow_out,
                     float* stats, const b2of_farneback_params& p, cudaStream_t st) {
   static const int n_env = getenv("B2OF_STREAMS") ? atoi(getenv("B2OF_STREAMS")) : FB_RANGES;   // developer A/B knob
-  int nr = 1;                                    // a power of two, at least eight pairs per range
-  while (2 * nr <= n_env && 2 * nr <= FB_MAX_RANGES && pairs >= 16 * nr) nr *= 2;
+  // a power of two; a range keeps at least two pairs and enough CTAs at the finest level to fill min_fill of the SMs
+  static const int fill_env = getenv("B2OF_RANGE_FILL") ? atoi(getenv("B2OF_RANGE_FILL")) : 90;   // percent of the SMs
+  const long long strips = cdiv(pl->cols, FBS_TW);
+  int nr = 1;
+  while (2 * nr <= n_env && 2 * nr <= FB_MAX_RANGES && pairs / (2 * nr) >= 2 &&
+         (pairs / (2 * nr)) * strips * 100 >= (long long)fill_env * 148)
+    nr *= 2;
   const bool fast = !(p.flags & B2OF_OPTFLOW_FARNEBACK_GAUSSIAN) && p.winsize / 2 == FBS_M;
   FbFork* f = nullptr;
   if (nr > 1 && fast && p.iterations > 0 && g_prof_on.load(std::memory_order_relaxed) == 0)

@@ -77,22 +77,44 @@ class PathfinderPipeline:
     """Full per-frame pipeline on device-resident BGR frames (config 5): gray -> grid LK (current -> previous)
     -> vector filter + danger points [+ dense Farneback flow and its statistics]."""
 
-    def __init__(self, height, width, step=30, dense=False, chunk_pairs=4, device=None):
+    def __init__(self, height, width, step=30, dense=False, chunk_pairs=4, device=None, side_stream=False):
         self.h, self.w = int(height), int(width)
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.points = torch.from_numpy(grid_points(self.w, self.h, step)).to(self.device)
         self.dense = batch.FarnebackEngine(self.h, self.w, chunk_pairs=chunk_pairs, device=self.device) if dense else None
+        # The sparse branch (grid LK + filter) and the dense branch only share the gray frames; side_stream=True runs
+        # the sparse branch on a side stream next to the dense one.  Off by default: at 4K x 8 pairs it measured 1008
+        # pairs/s in one run and 746 in the next against 981 on one stream -- lk_track's thousands of small CTAs keep
+        # landing on SMs that a 160 KB fb_iter_ws CTA needs empty, and which kernel starves is a matter of timing.
+        self._side = torch.cuda.Stream(device=self.device) if dense and side_stream else None
+
+    def _sparse(self, gray):
+        prev, cur = gray[:-1], gray[1:]
+        nxt, status, err = batch.pyrlk(cur, prev, self.points, **batch.LK_GRID_DEFAULTS)
+        out = batch.pathfinder_filter(self.points, nxt, self.w, self.h)
+        out.update(next_pts=nxt, status=status, err=err)
+        return out
 
     def run(self, bgr_frames):
         """uint8 (F,H,W,3) -> dict with per-pair outputs for the F-1 consecutive pairs."""
         gray = batch.bgr2gray(bgr_frames)
-        prev, cur = gray[:-1], gray[1:]
-        nxt, status, err = batch.pyrlk(cur, prev, self.points, **batch.LK_GRID_DEFAULTS)
-        out = batch.pathfinder_filter(self.points, nxt, self.w, self.h)
-        out.update(gray=gray, next_pts=nxt, status=status, err=err)
+        main = torch.cuda.current_stream(self.device)
+        if self._side is not None:
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                out = self._sparse(gray)
+        else:
+            out = self._sparse(gray)
+        out["gray"] = gray
         if self.dense is not None:
-            out["flow"] = self.dense.flow_sequence(gray)
-            out["flow_stats"] = batch.flow_stats(out["flow"])
+            stats = torch.empty((gray.shape[0] - 1, 8), dtype=torch.float32, device=self.device)
+            out["flow"] = self.dense.flow_sequence(gray, stats=stats)      # statistics reduced inside the last kernel
+            out["flow_stats"] = stats
+            if self._side is not None:
+                main.wait_stream(self._side)
+                for v in out.values():                                      # allocated on the side stream, used here
+                    if torch.is_tensor(v):
+                        v.record_stream(main)
             # the same vector filter / danger points driven by the dense field sampled on the grid (SURVEY 8f.1).
             # The viewer tracks current -> previous; the dense field is previous -> current, hence the sign.
             back = self.points[None] - (batch.flow_sample(out["flow"], self.points) - self.points[None])

@@ -29,7 +29,8 @@ def main():
     base = synth.sequence(h, w, 5, seed=2000 + rank, gray=False)
     idx = [0, 1, 2, 3, 4, 3, 2, 1] * (P // 8 + 2)
     bgr = torch.from_numpy(np.ascontiguousarray(base[idx[:P + 1]])).to(dev)
-    pipe = pathfinder.PathfinderPipeline(h, w, dense=not args.no_dense, chunk_pairs=min(P, 16), device=dev)
+    pipe = pathfinder.PathfinderPipeline(h, w, dense=not args.no_dense, chunk_pairs=min(P, 16), device=dev,
+                                          side_stream=bool(os.environ.get("B2OF_SIDE")))
     n_frames_global = world * P + 1
 
     def step():
@@ -42,7 +43,6 @@ def main():
     if world > 1:
         tdist.barrier()
     torch.cuda.synchronize()
-    _lib.profile(True, reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -52,6 +52,10 @@ def main():
         tdist.barrier()
     torch.cuda.synchronize()
     ms = b2dist.max_over_ranks(e0.elapsed_time(e1), dev)
+    _lib.profile(True, reset=True)               # per-kernel pass: per-launch events on, dense chunks on one stream
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
     prof = _lib.profile()
     _lib.profile(False, reset=True)
     if rank == 0:
