@@ -2181,7 +2181,12 @@ static int fb_pairs_range(const FbPlan* pl, const FbWorkspace& ws, int pairs_tot
 
 // Side streams of a device (fb_pairs), created on first use, destroyed by b2of_release().
 constexpr int FB_MAX_RANGES = 8;
-struct FbFork { cudaStream_t s[FB_MAX_RANGES - 1] = {}; cudaEvent_t fork = nullptr, join[FB_MAX_RANGES - 1] = {}; bool ok = false; };
+struct FbFork {
+  cudaStream_t s[FB_MAX_RANGES - 1] = {};
+  cudaEvent_t fork = nullptr, join[FB_MAX_RANGES - 1] = {};
+  bool ok = false;
+  std::mutex mu;
+};
 static FbFork g_fork[B2OF_MAX_DEVICES];
 static std::mutex g_fork_mu;
 
@@ -2211,8 +2216,11 @@ void farneback_release_streams() {
     if (!f.ok) continue;
     cudaSetDevice(d);
     cudaEventDestroy(f.fork);
-    for (int i = 0; i < FB_MAX_RANGES - 1; ++i) { cudaStreamDestroy(f.s[i]); cudaEventDestroy(f.join[i]); }
-    f = FbFork();
+    for (int i = 0; i < FB_MAX_RANGES - 1; ++i) {
+      cudaStreamDestroy(f.s[i]); cudaEventDestroy(f.join[i]);
+      f.s[i] = nullptr; f.join[i] = nullptr;
+    }
+    f.fork = nullptr; f.ok = false;
   }
   cudaSetDevice(cur);
 }
@@ -2242,6 +2250,9 @@ static int fb_pairs(const FbPlan* pl, const FbWorkspace& ws, int pairs, int fste
   if (nr > 1 && fast && p.iterations > 0 && g_prof_on.load(std::memory_order_relaxed) == 0)
     f = get_fork();
   if (!f) return fb_pairs_range(pl, ws, pairs, 0, pairs, fstep, total_slots, flow_out, stats, p, false, st);
+  // one host thread at a time enqueues on a device's side streams: a wait captures the event's record at the time of
+  // the call, so the events can be re-recorded by the next caller as soon as this one has enqueued its joins
+  std::lock_guard<std::mutex> lock(f->mu);
   B2OF_CUDA(cudaEventRecord(f->fork, st));
   int rc = 0;
   for (int r = 0; r < nr; ++r) {
