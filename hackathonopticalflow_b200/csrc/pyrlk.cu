@@ -54,9 +54,9 @@ static int lk_plan(int rows, int cols, const b2of_lk_params* p, LkLevels* L) {
   int w = cols, h = rows, n = 0;
   size_t off = 0, doff = 0;
   // columns read: window column -win_w .. w - 1 + win_w, plus the over-read of the last four-column strip and of its
-  // aligned word pair (<= 10 columns); rows: -win_h .. h - 1 + win_h
+  // aligned word pair (<= 10 columns); rows: -win_h .. h - 1 + win_h, plus the rows requested ahead
   L->pad_x = (int)align_up(p->win_w + 10, 16);
-  L->pad_y = p->win_h + 1;
+  L->pad_y = p->win_h + 5;            // (+4: lk_track requests the image words of a strip one four-row step ahead)
   for (int level = 0; level <= p->max_level && level < LK_MAX_LEVELS; ++level) {
     L->w[n] = w; L->h[n] = h;
     L->step[n] = align_up(w + 2 * L->pad_x, 16);
@@ -247,26 +247,34 @@ __device__ __forceinline__ void lk_window_strips(const uint8_t* __restrict__ J, 
       Rt = Rb; Rt2 = Rb2;
     };
     int y = y0;
-    // four rows per step, every load of the step issued before the first use
+    // four rows per step.  The image words of the NEXT step's rows are requested before this step's arithmetic (a
+    // whole step of work hides their latency; the rows past the strip's last that this reads lie in the level's
+    // border); the patch records come from shared memory at the head of the step that uses them.
+    unsigned nl[4], nh[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { nl[k] = q[(k + 1) * stepw]; nh[k] = q[(k + 1) * stepw + 1]; }
     for (; y + 4 <= y1; y += 4) {
       unsigned bl[4], bh[4];
       int2 ip[4];
       int4 dp[4];
+      q += 4 * stepw;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        bl[k] = q[(k + 1) * stepw]; bh[k] = q[(k + 1) * stepw + 1];
+        bl[k] = nl[k]; bh[k] = nh[k];
+        nl[k] = q[(k + 1) * stepw]; nh[k] = q[(k + 1) * stepw + 1];
         ip[k] = *(const int2*)(pI + k * wwp);
         dp[k] = ABS ? make_int4(0, 0, 0, 0) : pD[k * st.S];
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) one_row(bl[k], bh[k], ip[k], dp[k]);
-      q += 4 * stepw;
       pI += 4 * wwp; pD += 4 * st.S;
     }
-    for (; y < y1; ++y) {
-      q += stepw;
-      one_row(q[0], q[1], *(const int2*)pI, ABS ? make_int4(0, 0, 0, 0) : *pD);
-      pI += wwp; pD += st.S;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {                  // the up to three rows left: their words are already here
+      if (y + k < y1) {
+        one_row(nl[k], nh[k], *(const int2*)pI, ABS ? make_int4(0, 0, 0, 0) : *pD);
+        pI += wwp; pD += st.S;
+      }
     }
     if (ABS) {
       s1 += sabs;
@@ -332,13 +340,24 @@ __device__ __forceinline__ void lk_patch_strips(const uint8_t* __restrict__ I, c
     int4* pD = sD + y0 * st.S + sx;
     int q11 = 0, q12 = 0, q22 = 0;                 // widened every four rows
     auto flush = [&]() { sA11 += q11; sA12 += q12; sA22 += q22; q11 = q12 = q22 = 0; };
+    // the loads of the row after next are issued before this row's arithmetic: a whole row of work hides them (the
+    // borders make the one row read past the strip's last harmless)
+    unsigned nlo, nhi;
+    int ndv[5];
+    q += stepw; dr += dstep;
+    nlo = q[0]; nhi = q[1];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) ndv[k] = dr[k];
 #pragma unroll 2
     for (int y = y0; y < y1; ++y) {
-      q += stepw; dr += dstep;
-      const unsigned lo = q[0], hi = q[1];
+      const unsigned lo = nlo, hi = nhi;
       int dv[5];
 #pragma unroll
-      for (int k = 0; k < 5; ++k) dv[k] = dr[k];
+      for (int k = 0; k < 5; ++k) dv[k] = ndv[k];
+      q += stepw; dr += dstep;
+      nlo = q[0]; nhi = q[1];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) ndv[k] = dr[k];
       const unsigned Rb = __funnelshift_r(lo, hi, sh), Rb2 = __funnelshift_rc(lo, hi, sh + 8u);
       const unsigned v0 = __dp2a_lo(wb, Rb, __dp2a_lo(wt, Rt, 256u));
       const unsigned v1 = __dp2a_lo(wb, Rb2, __dp2a_lo(wt, Rt2, 256u));
