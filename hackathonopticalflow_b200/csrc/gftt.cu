@@ -162,6 +162,143 @@ __global__ void __launch_bounds__(256) gftt_mineig(const uint8_t* __restrict__ i
   if ((t & 31) == 0 && local_max) atomicMax(max_key + blockIdx.z, local_max);
 }
 
+// K7, shipped form for the 3 x 3 Sobel (the reference's gradientSize) and blockSize 3 / 5 / 7: the same arithmetic as
+// gftt_mineig<3> with every loop bound a compile-time constant and the work laid out so that each value is converted
+// and loaded once (gftt_mineig<3> spends 80 % of its instructions on index divisions, float -> double conversions
+// inside run-time loops and 7 + 7 shared-memory reads per output and channel: 795 us per 16 frames at 1080p).
+//   A  products fx fx, fx fy, fy fy of the (32 + BS - 1)^2 halo pixels.  Tiles whose halo and its +-1 neighbours lie
+//      inside the frame (all but the outer ring): thread = (halo row, run of five pixels), 3 x 7 bytes loaded and
+//      converted once for five pixels.  Border tiles: per pixel with reflected coordinates, as in gftt_mineig.
+//      (Staging the source tile in shared memory first -- reflected coordinates resolved once per byte, one path for
+//      every tile -- was built and measured 25 % slower: byte-wide shared-memory reads of four rows per warp conflict.)
+//   B  horizontal BS-sums in double: thread = (channel, halo row, group of four outputs): three 16-byte reads, the
+//      first sum direct, the next three by sliding (cv2's own box filter slides in double), two 16-byte writes.
+//   C  vertical BS-sums in double + eigenvalue / Harris response: thread = (column, run of four rows), first sum
+//      direct, three slides; coalesced stores, masked maximum as an ordered key.
+template <int BS>
+__global__ void __launch_bounds__(256) gftt_mineig3_fast(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask,
+                                                          size_t step, size_t frame_stride, int w, int h, float scale,
+                                                          int harris, float hk, float* __restrict__ eig,
+                                                          unsigned int* __restrict__ max_key) {
+  constexpr int R = BS / 2, E = GF_T + BS - 1, EP = (E + 3) & ~3;      // halo edge; product row pitch (16-byte rows)
+  __shared__ __align__(16) float sP[3][E][EP];
+  __shared__ __align__(16) double sH[3][E][GF_T];
+  const int x0 = blockIdx.x * GF_T, y0 = blockIdx.y * GF_T;
+  const uint8_t* ib = img + blockIdx.z * frame_stride;
+  const int t = threadIdx.x;
+  const float s2 = 2.f * scale;
+  // cv2.Sobel(CV_32F, scale) as opencv's separable filter rounds it in its SIMD body (probed bit for bit against
+  // cv2 4.13, oracle/gftt.py::sobel3_f32): the scaled smoothing taps [s, 2s, s] go through fused multiply-adds
+  auto products = [&](float a0, float a1, float a2, float b0, float b2, float c0, float c1, float c2, int iy, int ix) {
+    // rows a (above), b (this), c (below); columns 0 (left), 1, 2 (right)
+    const float t0 = a2 - a0, t1 = b2 - b0, t2 = c2 - c0;              // small integers: exact
+    const float fx = __fmaf_rn(t0 + t2, scale, __fmul_rn(t1, s2));
+    const float ra = __fmaf_rn(a2, scale, __fmaf_rn(a1, s2, __fmul_rn(a0, scale)));
+    const float rb = __fmaf_rn(c2, scale, __fmaf_rn(c1, s2, __fmul_rn(c0, scale)));
+    const float fy = __fsub_rn(rb, ra);
+    sP[0][iy][ix] = __fmul_rn(fx, fx);
+    sP[1][iy][ix] = __fmul_rn(fx, fy);
+    sP[2][iy][ix] = __fmul_rn(fy, fy);
+  };
+  const bool interior = x0 - R - 1 >= 0 && y0 - R - 1 >= 0 && x0 - R + E < w && y0 - R + E < h;
+  if (interior) {
+    constexpr int RUN = 5, NRUN = (E + RUN - 1) / RUN;
+    for (int i = t; i < E * NRUN; i += 256) {
+      const int iy = i / NRUN, q = i - iy * NRUN;
+      const int ix0 = q * RUN;
+      const uint8_t* p = ib + (size_t)(y0 - R + iy - 1) * step + (x0 - R + ix0 - 1);
+      float a[RUN + 2], b[RUN + 2], c[RUN + 2];
+#pragma unroll
+      for (int k = 0; k < RUN + 2; ++k) {
+        const bool in = ix0 + k - 1 <= E;                              // (the last run of a row is shorter)
+        a[k] = in ? (float)p[k] : 0.f;
+        b[k] = in ? (float)p[step + k] : 0.f;
+        c[k] = in ? (float)p[2 * step + k] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < RUN; ++k)
+        if (ix0 + k < E) products(a[k], a[k + 1], a[k + 2], b[k], b[k + 2], c[k], c[k + 1], c[k + 2], iy, ix0 + k);
+    }
+  } else {
+    for (int i = t; i < E * E; i += 256) {
+      const int iy = i / E, ix = i - iy * E;
+      const int x = reflect101(x0 - R + ix, w), y = reflect101(y0 - R + iy, h);
+      const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+      const uint8_t* r0 = ib + (size_t)reflect101(y - 1, h) * step;
+      const uint8_t* r1 = ib + (size_t)y * step;
+      const uint8_t* r2 = ib + (size_t)reflect101(y + 1, h) * step;
+      products((float)r0[xm], (float)r0[x], (float)r0[xp], (float)r1[xm], (float)r1[xp], (float)r2[xm], (float)r2[x],
+               (float)r2[xp], iy, ix);
+    }
+  }
+  __syncthreads();
+  for (int i = t; i < 3 * E * (GF_T / 4); i += 256) {
+    const int c = i / (E * (GF_T / 4)), rem = i - c * (E * (GF_T / 4));
+    const int iy = rem / (GF_T / 4), g = rem - iy * (GF_T / 4);
+    const float* row = &sP[c][iy][4 * g];
+    constexpr int NV = (BS + 3 + 3) / 4;                               // float4 reads covering BS + 3 values
+    double d[4 * NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const float4 v = *(const float4*)(row + 4 * k);
+      d[4 * k] = (double)v.x; d[4 * k + 1] = (double)v.y; d[4 * k + 2] = (double)v.z; d[4 * k + 3] = (double)v.w;
+    }
+    double o0 = d[0];
+#pragma unroll
+    for (int k = 1; k < BS; ++k) o0 += d[k];
+    const double o1 = o0 - d[0] + d[BS], o2 = o1 - d[1] + d[BS + 1], o3 = o2 - d[2] + d[BS + 2];
+    *(double2*)&sH[c][iy][4 * g] = make_double2(o0, o1);
+    *(double2*)&sH[c][iy][4 * g + 2] = make_double2(o2, o3);
+  }
+  __syncthreads();
+  unsigned int local_max = 0;  // ordered key; 0 is below every real float
+  const uint8_t* mb = mask ? mask + blockIdx.z * frame_stride : nullptr;
+  {
+    const int x = t & 31, yq = (t >> 5) * 4;
+    double sum[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double hv[BS + 3];
+#pragma unroll
+      for (int k = 0; k < BS + 3; ++k) hv[k] = sH[c][yq + k][x];
+      double o = hv[0];
+#pragma unroll
+      for (int k = 1; k < BS; ++k) o += hv[k];
+      sum[c][0] = o;
+#pragma unroll
+      for (int j = 1; j < 4; ++j) { o = o - hv[j - 1] + hv[j + BS - 1]; sum[c][j] = o; }
+    }
+    const int gx = x0 + x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gy = y0 + yq + j;
+      if (gx >= w || gy >= h) continue;
+      const float c0 = (float)sum[0][j], c1 = (float)sum[1][j], c2 = (float)sum[2][j];
+      float v;
+      if (harris) {
+        // cv2's calcHarris as its SIMD body rounds it (probed bit for bit): (a c - b b) - k ((a + c)(a + c)), float32
+        const float tr = __fadd_rn(c0, c2);
+        v = __fsub_rn(__fsub_rn(__fmul_rn(c0, c2), __fmul_rn(c1, c1)), __fmul_rn(hk, __fmul_rn(tr, tr)));
+      } else {
+        const float a = c0 * 0.5f, b = c1, c = c2 * 0.5f;
+        const float d = __fsub_rn(a, c);
+        v = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b))));
+      }
+      eig[blockIdx.z * (size_t)w * h + (size_t)gy * w + gx] = v;
+      if (!mb || mb[(size_t)gy * step + gx]) {
+        const unsigned int k = f2ord(v);
+        local_max = k > local_max ? k : local_max;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned int other = __shfl_xor_sync(0xffffffffu, local_max, o);
+    local_max = other > local_max ? other : local_max;
+  }
+  if ((t & 31) == 0 && local_max) atomicMax(max_key + blockIdx.z, local_max);
+}
+
 __global__ void __launch_bounds__(256) gftt_nms_compact(const float* __restrict__ eig,
                                                          const uint8_t* __restrict__ mask, size_t step,
                                                          size_t frame_stride, int w, int h, double quality,
@@ -354,7 +491,17 @@ int gftt_dev(const uint8_t* img, const uint8_t* mask, size_t step, size_t frame_
   }
   float scale = (float)(1.0 / ((double)(1 << (p->gradient_size - 1)) * bs * 255.0));
   dim3 g1(cdiv(cols, GF_T), cdiv(rows, GF_T), batch);
-  if (ks == 3)
+  const bool fast_ok = ks == 3 && cols >= 16 && rows >= 16;
+  if (fast_ok && bs == 3)
+    gftt_mineig3_fast<3><<<g1, 256, 0, st>>>(img, mask, step, frame_stride, cols, rows, scale, p->use_harris,
+                                             (float)p->k, L.eig, L.max_key);
+  else if (fast_ok && bs == 5)
+    gftt_mineig3_fast<5><<<g1, 256, 0, st>>>(img, mask, step, frame_stride, cols, rows, scale, p->use_harris,
+                                             (float)p->k, L.eig, L.max_key);
+  else if (fast_ok && bs == 7)
+    gftt_mineig3_fast<7><<<g1, 256, 0, st>>>(img, mask, step, frame_stride, cols, rows, scale, p->use_harris,
+                                             (float)p->k, L.eig, L.max_key);
+  else if (ks == 3)
     gftt_mineig<3><<<g1, 256, smem, st>>>(img, mask, step, frame_stride, cols, rows, bs, scale, p->use_harris,
                                           (float)p->k, L.eig, L.max_key);
   else if (ks == 5)
