@@ -342,21 +342,11 @@ __global__ void __launch_bounds__(256) gftt_nms_compact(const float* __restrict_
 // One CTA per image: bitonic sort (descending 64-bit keys = value desc, then address desc) of the candidate
 // list padded to a power of two, then the greedy min-distance pass with warp 0 (lane k scans bucket k of the
 // 3x3 neighbourhood; candidates are visited strictly in sorted order, as featureselect.cpp does).
-__global__ void __launch_bounds__(1024) gftt_select(unsigned long long* __restrict__ cand, int cand_cap,
-                                                     const int* __restrict__ cand_count, int w, int h,
-                                                     int max_corners, int cell, double md2,
-                                                     int* __restrict__ cell_head,
-                                                     int* __restrict__ next_in_cell, float* __restrict__ corners,
-                                                     int corners_cap, int* __restrict__ n_corners) {
-  const int b = blockIdx.x;
-  unsigned long long* keys = cand + (size_t)b * cand_cap;
-  int n = cand_count[b];
-  if (n > cand_cap) n = cand_cap;
-  int np2 = 1;
-  while (np2 < n) np2 <<= 1;
-  if (np2 > cand_cap) np2 = cand_cap;  // cand_cap is a power of two
-  for (int i = n + threadIdx.x; i < np2; i += blockDim.x) keys[i] = 0ull;
-  __syncthreads();
+// sort (value desc, address desc) + greedy min-distance pass of one frame's candidates.  `keys`, `head`, `nxt` all
+// live in the same memory (shared or global): the two instantiations are inlined with their address space known.
+__device__ __forceinline__ void gftt_select_body(unsigned long long* keys, int* head, int* nxt, int n, int np2, int w,
+                                                 int h, int max_corners, int cell, double md2, float* out,
+                                                 int corners_cap, int* n_out) {
   for (int k = 2; k <= np2; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int i = threadIdx.x; i < np2; i += blockDim.x) {
@@ -370,7 +360,6 @@ __global__ void __launch_bounds__(1024) gftt_select(unsigned long long* __restri
       __syncthreads();
     }
   }
-  float* out = corners + (size_t)b * corners_cap * 2;
   // cell == 0: cv2's minDistance < 1 branch (no distance test).  The host decides with cv2's own double
   // arithmetic (minDistance >= 1, cvRound) and passes the cell size and the squared distance down.
   if (cell == 0) {
@@ -380,12 +369,10 @@ __global__ void __launch_bounds__(1024) gftt_select(unsigned long long* __restri
       out[2 * i] = (float)(idx % w);
       out[2 * i + 1] = (float)(idx / w);
     }
-    if (threadIdx.x == 0) n_corners[b] = total;
+    if (threadIdx.x == 0) *n_out = total;
     return;
   }
   const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
-  int* head = cell_head + (size_t)b * gw * gh;
-  int* nxt = next_in_cell + (size_t)b * cand_cap;
   for (int i = threadIdx.x; i < gw * gh; i += blockDim.x) head[i] = -1;
   __syncthreads();
   if (threadIdx.x >= 32) return;
@@ -416,7 +403,43 @@ __global__ void __launch_bounds__(1024) gftt_select(unsigned long long* __restri
     ++accepted;
     if (max_corners > 0 && accepted == max_corners) break;
   }
-  if (lane == 0) n_corners[b] = accepted;
+  if (lane == 0) *n_out = accepted;
+}
+
+// One CTA per frame.  The sort passes and the sequential greedy pass are chains of dependent accesses: when the
+// frame's candidates (and the cell grid) fit the kernel's shared memory -- smem_keys keys + links, smem_cells heads --
+// they are sorted and linked there; a frame with more candidates works in the global workspace.
+__global__ void __launch_bounds__(1024) gftt_select(unsigned long long* __restrict__ cand, int cand_cap,
+                                                     const int* __restrict__ cand_count, int w, int h,
+                                                     int max_corners, int cell, double md2,
+                                                     int* __restrict__ cell_head,
+                                                     int* __restrict__ next_in_cell, float* __restrict__ corners,
+                                                     int corners_cap, int* __restrict__ n_corners, int smem_keys,
+                                                     int smem_cells) {
+  extern __shared__ __align__(16) unsigned char sel_smem[];
+  const int b = blockIdx.x;
+  unsigned long long* keys = cand + (size_t)b * cand_cap;
+  int n = cand_count[b];
+  if (n > cand_cap) n = cand_cap;
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  if (np2 > cand_cap) np2 = cand_cap;  // cand_cap is a power of two
+  float* out = corners + (size_t)b * corners_cap * 2;
+  const int cells = cell > 0 ? ((w + cell - 1) / cell) * ((h + cell - 1) / cell) : 0;
+  if (np2 <= smem_keys && cells <= smem_cells) {          // (uniform over the CTA)
+    unsigned long long* skeys = (unsigned long long*)sel_smem;
+    int* snxt = (int*)(skeys + smem_keys);
+    int* shead = snxt + smem_keys;
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) skeys[i] = i < n ? keys[i] : 0ull;
+    __syncthreads();
+    gftt_select_body(skeys, shead, snxt, n, np2, w, h, max_corners, cell, md2, out, corners_cap, n_corners + b);
+  } else {
+    for (int i = n + threadIdx.x; i < np2; i += blockDim.x) keys[i] = 0ull;
+    __syncthreads();
+    const int gw = cell > 0 ? (w + cell - 1) / cell : 0, gh = cell > 0 ? (h + cell - 1) / cell : 0;
+    gftt_select_body(keys, cell_head + (size_t)b * gw * gh, next_in_cell + (size_t)b * cand_cap, n, np2, w, h,
+                     max_corners, cell, md2, out, corners_cap, n_corners + b);
+  }
 }
 
 static int gftt_check(int rows, int cols, const b2of_gftt_params* p) {
@@ -515,9 +538,21 @@ int gftt_dev(const uint8_t* img, const uint8_t* mask, size_t step, size_t frame_
   gftt_nms_compact<<<g2, 256, 0, st>>>(L.eig, mask, step, frame_stride, cols, rows, p->quality_level, L.max_key, L.cand,
                                        L.cand_cap, L.cand_count);
   B2OF_LAUNCH_CHECK();
-  gftt_select<<<batch, 1024, 0, st>>>(L.cand, L.cand_cap, L.cand_count, cols, rows, p->max_corners, L.cell,
-                                      p->min_distance * p->min_distance, L.cell_head, L.next_in_cell, corners,
-                                      cap, n_corners);
+  // shared memory of the selection kernel: up to 4096 keys + links (48 KB) and the cell grid when it fits beside them
+#ifdef B2OF_SEL_NOSMEM                                     // developer A/B: everything in the global workspace
+  const int sel_keys = 0;
+#else
+  const int sel_keys = L.cand_cap < 4096 ? L.cand_cap : 4096;
+#endif
+  const long long cells = L.cell > 0 ? (long long)cdiv(cols, L.cell) * cdiv(rows, L.cell) : 0;
+  const int sel_cells = (size_t)sel_keys * 12 + (size_t)cells * 4 <= 200 * 1024 ? (int)cells : 0;
+  const size_t sel_smem = (size_t)sel_keys * 12 + (size_t)sel_cells * 4;
+  static PerDeviceMax sel_max;
+  if (sel_smem > 48 * 1024 && sel_max.raise(sel_smem))
+    B2OF_CUDA(cudaFuncSetAttribute(gftt_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+  gftt_select<<<batch, 1024, sel_smem, st>>>(L.cand, L.cand_cap, L.cand_count, cols, rows, p->max_corners, L.cell,
+                                             p->min_distance * p->min_distance, L.cell_head, L.next_in_cell, corners,
+                                             cap, n_corners, sel_keys, sel_cells);
   B2OF_LAUNCH_CHECK();
   return B2OF_OK;
 }
