@@ -167,8 +167,9 @@ __global__ void __launch_bounds__(256) gftt_mineig(const uint8_t* __restrict__ i
 // and loaded once (gftt_mineig<3> spends 80 % of its instructions on index divisions, float -> double conversions
 // inside run-time loops and 7 + 7 shared-memory reads per output and channel: 795 us per 16 frames at 1080p).
 //   A  products fx fx, fx fy, fy fy of the (32 + BS - 1)^2 halo pixels.  Tiles whose halo and its +-1 neighbours lie
-//      inside the frame (all but the outer ring): thread = (halo row, run of five pixels), 3 x 7 bytes loaded and
-//      converted once for five pixels.  Border tiles: per pixel with reflected coordinates, as in gftt_mineig.
+//      inside the frame (all but the outer ring): thread = (halo column, run of five rows), 7 x 3 bytes loaded and
+//      converted once for five pixels, a warp's loads on one image row each.  Border tiles: per pixel with reflected
+//      coordinates, as in gftt_mineig.
 //      (Staging the source tile in shared memory first -- reflected coordinates resolved once per byte, one path for
 //      every tile -- was built and measured 25 % slower: byte-wide shared-memory reads of four rows per warp conflict.)
 //   B  horizontal BS-sums in double: thread = (channel, halo row, group of four outputs): three 16-byte reads, the
@@ -202,22 +203,32 @@ __global__ void __launch_bounds__(256) gftt_mineig3_fast(const uint8_t* __restri
   };
   const bool interior = x0 - R - 1 >= 0 && y0 - R - 1 >= 0 && x0 - R + E < w && y0 - R + E < h;
   if (interior) {
+    // thread = (halo column, run of five rows): the lanes of a warp read consecutive bytes of ONE image row per load
+    // (five-pixel row runs touched four rows per load: four L1 wavefronts each); the row's horizontal difference and
+    // smoothed value are computed once and serve the three pixel rows that use them
     constexpr int RUN = 5, NRUN = (E + RUN - 1) / RUN;
     for (int i = t; i < E * NRUN; i += 256) {
-      const int iy = i / NRUN, q = i - iy * NRUN;
-      const int ix0 = q * RUN;
-      const uint8_t* p = ib + (size_t)(y0 - R + iy - 1) * step + (x0 - R + ix0 - 1);
-      float a[RUN + 2], b[RUN + 2], c[RUN + 2];
+      const int q = i / E, ix = i - q * E;
+      const int iy0 = q * RUN;
+      const uint8_t* p = ib + (size_t)(y0 - R + iy0 - 1) * step + (x0 - R + ix - 1);
+      float td[RUN + 2], hs[RUN + 2];
 #pragma unroll
       for (int k = 0; k < RUN + 2; ++k) {
-        const bool in = ix0 + k - 1 <= E;                              // (the last run of a row is shorter)
-        a[k] = in ? (float)p[k] : 0.f;
-        b[k] = in ? (float)p[step + k] : 0.f;
-        c[k] = in ? (float)p[2 * step + k] : 0.f;
+        const bool in = iy0 + k - 1 <= E;                              // (the last run of a column is shorter)
+        const float l = in ? (float)p[k * step] : 0.f, c = in ? (float)p[k * step + 1] : 0.f,
+                    r = in ? (float)p[k * step + 2] : 0.f;
+        td[k] = r - l;                                                 // small integers: exact
+        hs[k] = __fmaf_rn(r, scale, __fmaf_rn(c, s2, __fmul_rn(l, scale)));
       }
 #pragma unroll
-      for (int k = 0; k < RUN; ++k)
-        if (ix0 + k < E) products(a[k], a[k + 1], a[k + 2], b[k], b[k + 2], c[k], c[k + 1], c[k + 2], iy, ix0 + k);
+      for (int k = 0; k < RUN; ++k) {
+        if (iy0 + k >= E) break;
+        const float fx = __fmaf_rn(td[k] + td[k + 2], scale, __fmul_rn(td[k + 1], s2));
+        const float fy = __fsub_rn(hs[k + 2], hs[k]);
+        sP[0][iy0 + k][ix] = __fmul_rn(fx, fx);
+        sP[1][iy0 + k][ix] = __fmul_rn(fx, fy);
+        sP[2][iy0 + k][ix] = __fmul_rn(fy, fy);
+      }
     }
   } else {
     for (int i = t; i < E * E; i += 256) {
@@ -247,20 +258,24 @@ __global__ void __launch_bounds__(256) gftt_mineig3_fast(const uint8_t* __restri
 #pragma unroll
     for (int k = 1; k < BS; ++k) o0 += d[k];
     const double o1 = o0 - d[0] + d[BS], o2 = o1 - d[1] + d[BS + 1], o3 = o2 - d[2] + d[BS + 2];
-    *(double2*)&sH[c][iy][4 * g] = make_double2(o0, o1);
-    *(double2*)&sH[c][iy][4 * g + 2] = make_double2(o2, o3);
+    // row layout of sH: outputs 4g, 4g + 1 at [2g, 2g + 1]; outputs 4g + 2, 4g + 3 at 16 + ((2g + 8) mod 16): a thread's
+    // two 16-byte stores are contiguous across a quarter warp, and the sixteen doubles a half warp of step C reads
+    // fall on sixteen different bank pairs (the plain layout [4g .. 4g + 3] costs the stores a two-way conflict)
+    *(double2*)&sH[c][iy][2 * g] = make_double2(o0, o1);
+    *(double2*)&sH[c][iy][GF_T / 2 + ((2 * g + 8) & 15)] = make_double2(o2, o3);
   }
   __syncthreads();
   unsigned int local_max = 0;  // ordered key; 0 is below every real float
   const uint8_t* mb = mask ? mask + blockIdx.z * frame_stride : nullptr;
   {
     const int x = t & 31, yq = (t >> 5) * 4;
+    const int xs = (x & 2) ? GF_T / 2 + ((2 * (x >> 2) + 8) & 15) + (x & 1) : 2 * (x >> 2) + (x & 1);   // step B's layout
     double sum[3][4];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       double hv[BS + 3];
 #pragma unroll
-      for (int k = 0; k < BS + 3; ++k) hv[k] = sH[c][yq + k][x];
+      for (int k = 0; k < BS + 3; ++k) hv[k] = sH[c][yq + k][xs];
       double o = hv[0];
 #pragma unroll
       for (int k = 1; k < BS; ++k) o += hv[k];
