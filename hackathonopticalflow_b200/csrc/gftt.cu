@@ -314,24 +314,44 @@ __global__ void __launch_bounds__(256) gftt_mineig3_fast(const uint8_t* __restri
   if ((t & 31) == 0 && local_max) atomicMax(max_key + blockIdx.z, local_max);
 }
 
+// thread = four adjacent pixels of a row (one 16-byte load of the score map when rows are 16-byte aligned): almost
+// every pixel fails the quality threshold, so the kernel is a stream over the map -- one pixel per thread left a
+// 4-byte load per thread in flight and ran at 1.1 TB/s
 __global__ void __launch_bounds__(256) gftt_nms_compact(const float* __restrict__ eig,
                                                          const uint8_t* __restrict__ mask, size_t step,
                                                          size_t frame_stride, int w, int h, double quality,
                                                          const unsigned int* __restrict__ max_key,
                                                          unsigned long long* __restrict__ cand, int cand_cap,
                                                          int* __restrict__ cand_count) {
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane = threadIdx.x & 31;
+  const int x4 = (blockIdx.x * 32 + lane) * 4;
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int b = blockIdx.z;
   const float* e = eig + (size_t)b * w * h;
-  bool is_cand = false;
-  float v = 0.f;
-  if (x >= 1 && x < w - 1 && y >= 1 && y < h - 1) {
-    unsigned int mk = max_key[b];
-    float max_val = mk ? ord2f(mk) : 0.f;
-    float thr = (float)((double)max_val * quality);
-    v = e[(size_t)y * w + x];
-    if (v > thr && v != 0.f && (!mask || mask[b * frame_stride + (size_t)y * step + x])) {
+  float v4[4] = {0.f, 0.f, 0.f, 0.f};
+  float thr = 0.f;
+  const bool row_ok = y >= 1 && y < h - 1 && x4 < w;
+  if (row_ok) {
+    const unsigned int mk = max_key[b];
+    const float max_val = mk ? ord2f(mk) : 0.f;
+    thr = (float)((double)max_val * quality);
+    const float* r = e + (size_t)y * w + x4;
+    if ((w & 3) == 0) {
+      const float4 f = __ldg((const float4*)r);
+      v4[0] = f.x; v4[1] = f.y; v4[2] = f.z; v4[3] = f.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (x4 + k < w) v4[k] = r[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = x4 + k;
+    const float v = v4[k];
+    bool is_cand = false;
+    if (row_ok && x >= 1 && x < w - 1 && v > thr && v != 0.f &&
+        (!mask || mask[b * frame_stride + (size_t)y * step + x])) {
       is_cand = true;
 #pragma unroll
       for (int dy = -1; dy <= 1; ++dy)
@@ -339,24 +359,20 @@ __global__ void __launch_bounds__(256) gftt_nms_compact(const float* __restrict_
         for (int dx = -1; dx <= 1; ++dx)
           if (e[(size_t)(y + dy) * w + x + dx] > v) is_cand = false;
     }
-  }
-  unsigned int ballot = __ballot_sync(0xffffffffu, is_cand);
-  if (ballot) {
-    int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(cand_count + b, __popc(ballot));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (is_cand) {
-      int slot = base + __popc(ballot & ((1u << lane) - 1));
-      if (slot < cand_cap)
-        cand[(size_t)b * cand_cap + slot] = ((unsigned long long)f2ord(v) << 32) | (unsigned int)(y * w + x);
+    const unsigned int ballot = __ballot_sync(0xffffffffu, is_cand);
+    if (ballot) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(cand_count + b, __popc(ballot));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (is_cand) {
+        const int slot = base + __popc(ballot & ((1u << lane) - 1));
+        if (slot < cand_cap)
+          cand[(size_t)b * cand_cap + slot] = ((unsigned long long)f2ord(v) << 32) | (unsigned int)(y * w + x);
+      }
     }
   }
 }
 
-// One CTA per image: bitonic sort (descending 64-bit keys = value desc, then address desc) of the candidate
-// list padded to a power of two, then the greedy min-distance pass with warp 0 (lane k scans bucket k of the
-// 3x3 neighbourhood; candidates are visited strictly in sorted order, as featureselect.cpp does).
 // sort (value desc, address desc) + greedy min-distance pass of one frame's candidates.  `keys`, `head`, `nxt` all
 // live in the same memory (shared or global): the two instantiations are inlined with their address space known.
 __device__ __forceinline__ void gftt_select_body(unsigned long long* keys, int* head, int* nxt, int n, int np2, int w,
@@ -549,7 +565,7 @@ int gftt_dev(const uint8_t* img, const uint8_t* mask, size_t step, size_t frame_
     gftt_mineig<7><<<g1, 256, smem, st>>>(img, mask, step, frame_stride, cols, rows, bs, scale, p->use_harris,
                                           (float)p->k, L.eig, L.max_key);
   B2OF_LAUNCH_CHECK();
-  dim3 g2(cdiv(cols, 32), cdiv(rows, 8), batch);
+  dim3 g2(cdiv(cols, 128), cdiv(rows, 8), batch);
   gftt_nms_compact<<<g2, 256, 0, st>>>(L.eig, mask, step, frame_stride, cols, rows, p->quality_level, L.max_key, L.cand,
                                        L.cand_cap, L.cand_count);
   B2OF_LAUNCH_CHECK();
