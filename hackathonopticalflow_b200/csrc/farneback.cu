@@ -1327,6 +1327,55 @@ __device__ __forceinline__ float2 ldg_f2(const float2* p) {
   asm("ld.global.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
   return v;
 }
+// streamed operands of fb_iter_ws (R0 record, flow vector: each byte used once by the CTA) and its gathered ones (R1
+// corners: re-used by the next row / the next run), with cache hints behind FBW_STREAM_HINT / FBW_GATHER_HINT
+#ifndef FBW_STREAM_HINT
+#define FBW_STREAM_HINT 0
+#endif
+#ifndef FBW_GATHER_HINT
+#define FBW_GATHER_HINT 0
+#endif
+#if FBW_STREAM_HINT == 1
+#define FBW_LDS_Q ".L1::no_allocate"
+#elif FBW_STREAM_HINT == 2
+#define FBW_LDS_Q ".L1::evict_first"
+#else
+#define FBW_LDS_Q ""
+#endif
+#if FBW_GATHER_HINT == 1
+#define FBW_LDG_Q ".L1::evict_last"
+#else
+#define FBW_LDG_Q ""
+#endif
+template <int OFF>
+__device__ __forceinline__ float4 lds_f4(const float4* p) {
+  float4 v;
+  asm("ld.global" FBW_LDS_Q ".v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "n"(OFF));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ float lds_f1(const float* p) {
+  float v;
+  asm("ld.global" FBW_LDS_Q ".f32 %0, [%1+%2];" : "=f"(v) : "l"(p), "n"(OFF));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f2(const float2* p) {
+  float2 v;
+  asm("ld.global" FBW_LDS_Q ".v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ float4 ldgat_f4(const float4* p) {
+  float4 v;
+  asm("ld.global" FBW_LDG_Q ".v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "n"(OFF));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ float ldgat_f1(const float* p) {
+  float v;
+  asm("ld.global" FBW_LDG_Q ".f32 %0, [%1+%2];" : "=f"(v) : "l"(p), "n"(OFF));
+  return v;
+}
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sts_f4(unsigned addr, float x, float y, float z, float w) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
@@ -1345,7 +1394,7 @@ template <int MODE>
 __device__ __forceinline__ float2 fetch_flow_m(const IterArgs& a, const float2* fin, int o, int y, int xa, int xb,
                                                float ufx) {
   if (MODE == 0) return make_float2(0.f, 0.f);
-  if (MODE == 1) return ldg_f2(fin + o);
+  if (MODE == 1) return lds_f2(fin + o);
   int ya, yb;
   float fy;
   if (a.up_exact2) {

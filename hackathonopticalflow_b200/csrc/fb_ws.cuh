@@ -463,8 +463,8 @@ __global__ void FBW_BOUNDS fb_iter_ws(IterArgs a) {
         float2 dA = (FBW_PREF_NEXT && have_pref) ? d_pref : fetch(oA, yA), dB = dA;
         auto rowf = [&](const float2 d, float2& dn, const int y, int& yn, const int o, int& on, bool has_next,
                         FbCorner& top, FbCorner& bot) {
-          const float4 q = ldg_f4<0>(FB_R0A(o));
-          const float q4 = ldg_f1<0>(FB_R0E(o));
+          const float4 q = lds_f4<0>(FB_R0A(o));
+          const float q4 = lds_f1<0>(FB_R0E(o));
           if (has_next) { next_row(yn, on); dn = fetch(on, yn); }
           float fx = xf + d.x, fy = (float)y + d.y;
           const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
@@ -474,7 +474,7 @@ __global__ void FBW_BOUNDS fb_iter_ws(IterArgs a) {
           if (ot != o_carry) {
             const float4* pa = FB_R1A(ot);
             const float* pe = FB_R1E(ot);
-            top.a0 = ldg_f4<0>(pa); top.a1 = ldg_f4<16>(pa); top.e0 = ldg_f1<0>(pe); top.e1 = ldg_f1<4>(pe);
+            top.a0 = ldgat_f4<0>(pa); top.a1 = ldgat_f4<16>(pa); top.e0 = ldgat_f1<0>(pe); top.e1 = ldgat_f1<4>(pe);
           }
           const int ob = ot + pitb;
 #if FBW_GSHFL
@@ -497,7 +497,7 @@ __global__ void FBW_BOUNDS fb_iter_ws(IterArgs a) {
           {
             const float4* pa = FB_R1A(ob);
             const float* pe = FB_R1E(ob);
-            bot.a0 = ldg_f4<0>(pa); bot.a1 = ldg_f4<16>(pa); bot.e0 = ldg_f1<0>(pe); bot.e1 = ldg_f1<4>(pe);
+            bot.a0 = ldgat_f4<0>(pa); bot.a1 = ldgat_f4<16>(pa); bot.e0 = ldgat_f1<0>(pe); bot.e1 = ldgat_f1<4>(pe);
           }
 #endif
           o_carry = ob;
