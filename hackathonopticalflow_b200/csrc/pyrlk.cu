@@ -82,8 +82,11 @@ __device__ __forceinline__ int reflect101_pm1(int i, int n) {   // BORDER_REFLEC
   return i < 0 ? 1 : (i >= n ? n - 2 : i);
 }
 
-// four pixels per thread: the 3 x 6 neighbourhood comes in as bytes from L1, the four (Ix, Iy) pairs go out as one
-// 16-byte store when the row start is aligned
+// four pixels per thread.  Rows of a pyramid level start 16-byte aligned (LkLevels), so the 3 x 6 neighbourhood of
+// the pixels x0 .. x0 + 3 (x0 a multiple of four) is three aligned words per row -- the one before (its last byte), the
+// thread's own, the one after (its first byte) -- instead of eighteen byte loads; at the frame's left / right edge the
+// missing neighbour is the REFLECT_101 pixel, one of the thread's own bytes.  The four (Ix, Iy) pairs go out as one
+// 16-byte store when the row start is aligned.
 __global__ void __launch_bounds__(256) lk_scharr(const uint8_t* __restrict__ img, size_t step, size_t img_bstride,
                                                   int w, int h, short2* __restrict__ d, size_t d_bstride,
                                                   size_t d_pitch) {
@@ -94,12 +97,30 @@ __global__ void __launch_bounds__(256) lk_scharr(const uint8_t* __restrict__ img
   const uint8_t* r1 = b + (size_t)y * step;
   const uint8_t* r2 = b + (size_t)reflect101_pm1(y + 1, h) * step;
   int t0[6], t1[6];                      // vertical smooth (3, 10, 3) and difference at columns x0 - 1 .. x0 + 4
+  if (((step | (size_t)b) & 3) == 0 && x0 + 4 <= w && w >= 2) {
+    auto row6 = [&](const uint8_t* r, int* v) {
+      const uint32_t own = __ldg((const uint32_t*)(r + x0));
+      v[1] = own & 255u; v[2] = (own >> 8) & 255u; v[3] = (own >> 16) & 255u; v[4] = own >> 24;
+      v[0] = x0 > 0 ? (int)(__ldg((const uint32_t*)(r + x0 - 4)) >> 24) : v[2];              // column -1 is column 1
+      // column x0 + 4: the next word's first byte (the word may hang over w inside the 16-byte-padded row), or, at
+      // the right edge, column w -> w - 2
+      v[5] = x0 + 4 < w ? (int)(__ldg((const uint32_t*)(r + x0 + 4)) & 255u) : v[3];
+    };
+    int a[6], c[6], e[6];
+    row6(r0, a); row6(r1, c); row6(r2, e);
 #pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const int xx = reflect101_pm1(min(x0 - 1 + k, w), w);
-    const int a = r0[xx], c = r1[xx], e = r2[xx];
-    t0[k] = (a + e) * 3 + c * 10;
-    t1[k] = e - a;
+    for (int k = 0; k < 6; ++k) {
+      t0[k] = (a[k] + e[k]) * 3 + c[k] * 10;
+      t1[k] = e[k] - a[k];
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int xx = reflect101_pm1(min(x0 - 1 + k, w), w);
+      const int a = r0[xx], c = r1[xx], e = r2[xx];
+      t0[k] = (a + e) * 3 + c * 10;
+      t1[k] = e - a;
+    }
   }
   short2 o[4];
 #pragma unroll
