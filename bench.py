@@ -12,7 +12,10 @@ plus the per-pair flow statistics and (N>1) their gather to rank 0.  Weak scalin
 value  = pairs all ranks processed / max-over-ranks device time (CUDA events), inputs resident in HBM.
 e2e    = the same metric through the cv2-compatible host call (pinned host frames in, host flow out; the H2D and
          D2H copies are inside the timed region).
-roofline = the dominant kernel (finest-level fused iteration) timed live with CUDA events on its own stream.
+roofline = the dominant kernel (finest-level fused iteration) timed with CUDA events around every launch on its
+         stream, over a second pass of the same K steps inside this run (`kernel_timing_pass`): the timed region walks
+         a chunk as several ranges of pairs on several streams, where a launch's events would time interleaved
+         kernels; with the events on the library keeps the chunk on one stream.
 cpu_baseline = the reference's own CPU path (cv2.calcOpticalFlowFarneback, one cv2 thread per pair over all
          host cores) on a bounded sample of the same workload.  Reported beside, not the target.
 """
@@ -346,7 +349,7 @@ def main():
     launches = lib.b2of_launch_count() - launches0
     clocks = sampler.stop(t0, t1) if sampler else None
     # Per-kernel pass: the same K steps again with the library's per-launch CUDA events on.  In the timed region
-    # above the library walks a 64-pair chunk as four ranges of pairs on four streams (a partial last wave of one
+    # above the library walks a 64-pair chunk as eight ranges of pairs on eight streams (a partial last wave of one
     # launch is filled by the other ranges' CTAs), where a launch's events would time several ranges' kernels
     # interleaved; with the events on, the chunk runs as one range on one stream and every launch is timed alone.
     _lib.profile(True, reset=True)
@@ -455,7 +458,7 @@ def main():
         "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
         "kernel_timing_pass": {"ms_per_step": serial_ms, "sum_of_kernels_ms": total_ms / args.steps,
                                "note": "one stream, per-launch events on; the timed region (ms_per_step) walks the "
-                                       "chunk as four ranges of pairs on four streams with the events off"},
+                                       "chunk as up to eight ranges of pairs on as many streams with the events off"},
     }
     if world == 1 and not args.no_cpu:
         from oracle import cv2_reference as ref
