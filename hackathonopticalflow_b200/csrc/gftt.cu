@@ -457,14 +457,54 @@ __global__ void __launch_bounds__(1024) gftt_select(unsigned long long* __restri
   if (np2 > cand_cap) np2 = cand_cap;  // cand_cap is a power of two
   float* out = corners + (size_t)b * corners_cap * 2;
   const int cells = cell > 0 ? ((w + cell - 1) / cell) * ((h + cell - 1) / cell) : 0;
+  unsigned long long* skeys = (unsigned long long*)sel_smem;
+  int* snxt = (int*)(skeys + smem_keys);
+  int* shead = snxt + smem_keys;
   if (np2 <= smem_keys && cells <= smem_cells) {          // (uniform over the CTA)
-    unsigned long long* skeys = (unsigned long long*)sel_smem;
-    int* snxt = (int*)(skeys + smem_keys);
-    int* shead = snxt + smem_keys;
     for (int i = threadIdx.x; i < np2; i += blockDim.x) skeys[i] = i < n ? keys[i] : 0ull;
     __syncthreads();
     gftt_select_body(skeys, shead, snxt, n, np2, w, h, max_corners, cell, md2, out, corners_cap, n_corners + b);
-  } else {
+    return;
+  }
+  if (smem_keys > 0 && cells <= smem_cells && max_corners > 0 && cell > 0) {
+    // More candidates than shared memory holds, and a bounded number of corners wanted: the greedy pass walks the
+    // candidates in descending order and stops at max_corners, so it almost always needs only the strongest few.
+    // Take the candidates of the top bins of a 4096-bin histogram of the score's leading bits -- as many whole bins
+    // as fit -- sort those in shared memory and run the pass on them: they are exactly a prefix of the full order.
+    // If the pass runs out of them before max_corners are accepted, the general path below redoes the frame.
+    int* hist = shead + smem_cells;                        // 4096 bins + the compaction counter
+    __shared__ int s_thr_bin, s_m;
+    for (int i = threadIdx.x; i <= 4096; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[(int)(keys[i] >> 52)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int cum = 0, tb = 4096;
+      for (int bin = 4095; bin >= 0; --bin) {
+        if (cum + hist[bin] > smem_keys) break;
+        cum += hist[bin]; tb = bin;
+      }
+      s_thr_bin = tb; s_m = cum;
+    }
+    __syncthreads();
+    const int tb = s_thr_bin, m = s_m;
+    if (m >= max_corners && m < n) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long k = keys[i];
+        if ((int)(k >> 52) >= tb) skeys[atomicAdd(&hist[4096], 1)] = k;
+      }
+      int mp2 = 1;
+      while (mp2 < m) mp2 <<= 1;
+      __syncthreads();
+      for (int i = m + threadIdx.x; i < mp2; i += blockDim.x) skeys[i] = 0ull;
+      __syncthreads();
+      gftt_select_body(skeys, shead, snxt, m, mp2, w, h, max_corners, cell, md2, out, corners_cap, n_corners + b);
+      __syncthreads();                                     // (threads >= 32 left the body early; all meet here)
+      if (n_corners[b] == max_corners) return;             // written by lane 0 before the barrier above
+    }
+    __syncthreads();
+  }
+  {
     for (int i = n + threadIdx.x; i < np2; i += blockDim.x) keys[i] = 0ull;
     __syncthreads();
     const int gw = cell > 0 ? (w + cell - 1) / cell : 0, gh = cell > 0 ? (h + cell - 1) / cell : 0;
@@ -576,8 +616,9 @@ int gftt_dev(const uint8_t* img, const uint8_t* mask, size_t step, size_t frame_
   const int sel_keys = L.cand_cap < 4096 ? L.cand_cap : 4096;
 #endif
   const long long cells = L.cell > 0 ? (long long)cdiv(cols, L.cell) * cdiv(rows, L.cell) : 0;
-  const int sel_cells = (size_t)sel_keys * 12 + (size_t)cells * 4 <= 200 * 1024 ? (int)cells : 0;
-  const size_t sel_smem = (size_t)sel_keys * 12 + (size_t)sel_cells * 4;
+  const size_t sel_hist = sel_keys > 0 ? (size_t)4097 * 4 : 0;          // histogram of the prefix selection
+  const int sel_cells = (size_t)sel_keys * 12 + (size_t)cells * 4 + sel_hist <= 200 * 1024 ? (int)cells : 0;
+  const size_t sel_smem = (size_t)sel_keys * 12 + (size_t)sel_cells * 4 + sel_hist;
   static PerDeviceMax sel_max;
   if (sel_smem > 48 * 1024 && sel_max.raise(sel_smem))
     B2OF_CUDA(cudaFuncSetAttribute(gftt_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
