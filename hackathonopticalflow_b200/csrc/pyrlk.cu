@@ -184,10 +184,16 @@ __host__ __device__ inline size_t lk_patch_bytes(int ww, int wh) {
 template <int NC>
 struct LkStrips {
   int S, G, RG;
-  __device__ __forceinline__ LkStrips(int ww, int nrows) {   // nrows = rows of this warp's share of the window
+  int g0, sx0;               // (row group, strip) of unit u = lane: computed once per kernel, not once per window pass
+  __device__ __forceinline__ LkStrips(int ww, int nrows, int lane) {   // nrows = rows of this warp's share of the window
     S = lk_wwp(ww) / NC;
     G = S <= 16 ? 32 / S : 1;
     RG = (nrows + G - 1) / G;
+    g0 = lane / S; sx0 = lane - g0 * S;
+  }
+  __device__ __forceinline__ void unit(int u, int lane, int& g, int& sx) const {
+    if (u == lane) { g = g0; sx = sx0; }
+    else { g = u / S; sx = u - g * S; }
   }
 };
 
@@ -219,12 +225,13 @@ __device__ __forceinline__ int dp2a_hi_su(int a, unsigned b, int c) {
 template <bool ABS>
 __device__ __forceinline__ void lk_window_strips(const uint8_t* __restrict__ J, size_t step, int ix, int iy,
                                                  unsigned wt, unsigned wb, const short* sI, const int4* sD, int ww,
-                                                 int ya, int yb, int lane, long long& s1, long long& s2) {
+                                                 int ya, int yb, int lane, const LkStrips<4>& st, long long& s1,
+                                                 long long& s2) {
   const int wwp = lk_wwp(ww);
-  const LkStrips<4> st(ww, yb - ya);
   const ptrdiff_t stepw = (ptrdiff_t)(step >> 2);          // (pyramid steps are multiples of 16 bytes)
   for (int u = lane; u < st.S * st.G; u += 32) {
-    const int g = u / st.S, sx = u - g * st.S;
+    int g, sx;
+    st.unit(u, lane, g, sx);
     const int x0 = 4 * sx;
     const int y0 = ya + g * st.RG, y1 = min(yb, y0 + st.RG);
     const uint8_t* p0 = J + (ptrdiff_t)(iy + y0) * (ptrdiff_t)step + (ix + x0);
@@ -310,11 +317,11 @@ __device__ __forceinline__ void lk_window_strips(const uint8_t* __restrict__ J, 
 template <bool ABS>
 __device__ __forceinline__ void lk_window_pass(const uint8_t* __restrict__ J, size_t step, int ix, int iy, int w00,
                                                int w01, int w10, int w11, const short* sI, const int4* sD, int ww,
-                                               int ya, int yb, int lane, long long sIx, long long sIy, long long& o1,
-                                               long long& o2) {
+                                               int ya, int yb, int lane, const LkStrips<4>& st, long long sIx,
+                                               long long sIy, long long& o1, long long& o2) {
   const unsigned wt = (unsigned)w00 | ((unsigned)w01 << 16), wb = (unsigned)w10 | ((unsigned)w11 << 16);
   long long s1 = 0, s2 = 0;
-  lk_window_strips<ABS>(J, step, ix, iy, wt, wb, sI, sD, ww, ya, yb, lane, s1, s2);
+  lk_window_strips<ABS>(J, step, ix, iy, wt, wb, sI, sD, ww, ya, yb, lane, st, s1, s2);
   o1 = warp_sum_ll(s1);
   o2 = 0;
   if (!ABS) {
@@ -332,15 +339,15 @@ __device__ __forceinline__ void lk_window_pass(const uint8_t* __restrict__ J, si
 __device__ __forceinline__ void lk_patch_strips(const uint8_t* __restrict__ I, const short2* __restrict__ D, size_t step,
                                                 size_t dstep, int ipx, int ipy, int w00, int w01, int w10, int w11,
                                                 short* sI, int4* sD, int ww, int ya, int yb, int lane,
-                                                long long& sA11, long long& sA12, long long& sA22, long long& sIx,
-                                                long long& sIy) {
+                                                const LkStrips<4>& st, long long& sA11, long long& sA12,
+                                                long long& sA22, long long& sIx, long long& sIy) {
   const int wwp = lk_wwp(ww);
-  const LkStrips<4> st(ww, yb - ya);
   const unsigned wt = (unsigned)w00 | ((unsigned)w01 << 16), wb = (unsigned)w10 | ((unsigned)w11 << 16);
   const ptrdiff_t stepw = (ptrdiff_t)(step >> 2);
   int accx = 0, accy = 0;                          // |Ixw| <= 4080: 32 bits hold any window that fits shared memory
   for (int u = lane; u < st.S * st.G; u += 32) {
-    const int g = u / st.S, sx = u - g * st.S;
+    int g, sx;
+    st.unit(u, lane, g, sx);
     const int x0 = 4 * sx;
     const int nv = ww - x0;                        // elements x0 + k with k >= nv are padding and are stored as zeros
     const int y0 = ya + g * st.RG, y1 = min(yb, y0 + st.RG);
@@ -430,6 +437,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 512 / (LK_WARPS * 32)) lk_track
   const size_t per_warp = lk_patch_bytes(ww, wh);
   // this warp's rows of the window (and of the patch: a warp only ever reads the patch rows it wrote itself)
   const int ya = (wh * half) / LK_SPLIT, yb = (wh * (half + 1)) / LK_SPLIT;
+  const LkStrips<4> st(ww, yb - ya, lane);
   // exchange of the partial window sums between the feature's warps: [parity][warp of the feature][3]
   long long* xch = (long long*)(lk_smem + LK_FEATS * per_warp) + feat * (2 * LK_SPLIT * 3);
   int xpar = 0;
@@ -495,8 +503,8 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 512 / (LK_WARPS * 32)) lk_track
     long long sA11 = 0, sA12 = 0, sA22 = 0, sIx = 0, sIy = 0;
     {
       __syncwarp();
-      lk_patch_strips(I, D, step, dstep, ipx, ipy, w00, w01, w10, w11, sI, sD, ww, ya, yb, lane, sA11, sA12, sA22, sIx,
-                      sIy);
+      lk_patch_strips(I, D, step, dstep, ipx, ipy, w00, w01, w10, w11, sI, sD, ww, ya, yb, lane, st, sA11, sA12, sA22,
+                      sIx, sIy);
       sA11 = warp_sum_ll(sA11); sA12 = warp_sum_ll(sA12); sA22 = warp_sum_ll(sA22);
       sIx = warp_sum_ll(sIx); sIy = warp_sum_ll(sIy);
       __syncwarp();
@@ -525,7 +533,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 512 / (LK_WARPS * 32)) lk_track
       }
       lk_weights(qx - ix, qy - iy, w00, w01, w10, w11);
       long long s1, s2, s3 = 0;
-      lk_window_pass<false>(J, step, ix, iy, w00, w01, w10, w11, sI, sD, ww, ya, yb, lane, sIx, sIy, s1, s2);
+      lk_window_pass<false>(J, step, ix, iy, w00, w01, w10, w11, sI, sD, ww, ya, yb, lane, st, sIx, sIy, s1, s2);
       feature_sum(s1, s2, s3, 2);
       float b1 = __fmul_rn((float)s1, FLT_SCALE), b2 = __fmul_rn((float)s2, FLT_SCALE);
       float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), Dt);
@@ -547,7 +555,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 512 / (LK_WARPS * 32)) lk_track
       } else {
         lk_weights(ex - ix, ey - iy, w00, w01, w10, w11);
         long long s1, s2, s3 = 0;
-        lk_window_pass<true>(J, step, ix, iy, w00, w01, w10, w11, sI, sD, ww, ya, yb, lane, sIx, sIy, s1, s2);
+        lk_window_pass<true>(J, step, ix, iy, w00, w01, w10, w11, sI, sD, ww, ya, yb, lane, st, sIx, sIy, s1, s2);
         feature_sum(s1, s2, s3, 1);
         err = __fmul_rn((float)s1, 1.f / (float)(32 * ww * wh));
       }
