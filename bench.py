@@ -194,18 +194,30 @@ def pcie_ceiling(dev, h2d_bytes, d2h_bytes, world, reps=3):
 
 
 def real_1080p_record(batch, dev, pairs):
-    """The committed real 1080p pair (tests/golden/real_1080p.npz, footage from the reference's own clips) replicated to
-    `pairs` pairs (frames a b a b ...: flows a->b and b->a alternate): throughput on real content (large motions,
-    discontinuities) and the error of pair 0 against the committed cv2 result."""
+    """Real footage at the clips' native 1080p (BASELINE configs[0]): the four committed full-resolution pairs, one per
+    reference clip (tests/golden/real_1080p.npz + real_sweep.npz), each played a b a b ... for a quarter of the step's
+    pairs (flows a->b and b->a alternate; the pair where one clip hands over to the next is a scene cut and is
+    computed like any other): throughput on real content (large motions, discontinuities, dark footage) and the error
+    of each clip's first pair against the committed cv2 result."""
     import numpy as np
     import torch
-    from hackathonopticalflow_b200 import _lib
-    path = os.path.join(ROOT, "tests", "golden", "real_1080p.npz")
-    if not os.path.exists(path):
+    gold = os.path.join(ROOT, "tests", "golden")
+    if not os.path.exists(os.path.join(gold, "real_1080p.npz")):
         return {"unavailable": "tests/golden/real_1080p.npz missing"}
-    z = np.load(path)
-    a, b = decode_png(z["png0"]), decode_png(z["png1"])
-    frames = torch.from_numpy(np.ascontiguousarray(np.stack([a, b] * (pairs // 2 + 1))[:pairs + 1])).to(dev)
+    z = np.load(os.path.join(gold, "real_1080p.npz"))
+    clips = [(decode_png(z["png0"]), decode_png(z["png1"]), z["flow_s8"], "real_1080p.npz", None)]
+    if os.path.exists(os.path.join(gold, "real_sweep.npz")):
+        zs = np.load(os.path.join(gold, "real_sweep.npz"))
+        clips[0] = clips[0][:4] + (zs["stable_3"],)
+        clips += [(decode_png(zs[f"png0_{i}"]), decode_png(zs[f"png1_{i}"]), zs[f"flow_s8_{i}"], f"real_sweep.npz[{i}]",
+                   zs[f"stable_{i}"]) for i in range(3)]
+    per = max(2, (pairs // len(clips)) & ~1)          # frames per clip (even: every clip starts on its a frame)
+    seq, first = [], []
+    for a, b, _, _, _ in clips:
+        first.append(len(seq))
+        seq += [a, b] * (per // 2)
+    seq = (seq + [clips[-1][0], clips[-1][1]] * (pairs // 2 + 1))[:pairs + 1]
+    frames = torch.from_numpy(np.ascontiguousarray(np.stack(seq))).to(dev)
     eng = batch.FarnebackEngine(H, W, chunk_pairs=pairs, device=dev, **PARAMS)
     flow = torch.empty((pairs, H, W, 2), dtype=torch.float32, device=dev)
     for _ in range(2):
@@ -219,14 +231,33 @@ def real_1080p_record(batch, dev, pairs):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
-    got = flow[0, ::8, ::8].cpu().numpy().astype(np.float64)
-    d = np.sqrt(((got - z["flow_s8"].astype(np.float64)) ** 2).sum(-1))
-    mag = np.sqrt((z["flow_s8"].astype(np.float64) ** 2).sum(-1))
+    per_clip = []
+    for (a, b, want, src, bits), k in zip(clips, first):
+        if k >= pairs:
+            break
+        got = flow[k, ::8, ::8].cpu().numpy().astype(np.float64)
+        d = np.sqrt(((got - want.astype(np.float64)) ** 2).sum(-1))
+        mag = np.sqrt((want.astype(np.float64) ** 2).sum(-1))
+        rec = {"source": src, "epe_mean_vs_cv2": float(d.mean()), "epe_max_vs_cv2": float(d.max()),
+               "flow_mean_px": float(mag.mean()), "flow_max_px": float(mag.max())}
+        if bits is not None:
+            stable = np.unpackbits(bits)[:d.size].reshape(d.shape).astype(bool)
+            rec.update({"cv2_stable_fraction": float(stable.mean()), "epe_max_on_cv2_stable_px": float(d[stable].max()),
+                        "fraction_over_0.5px": float((d > 0.5).mean())})
+        per_clip.append(rec)
     del eng, flow, frames
     return {"pairs_per_s": pairs / (ms * 1e-3), "ms_per_step": ms, "pairs_per_step": pairs,
-            "epe_mean_vs_cv2": float(d.mean()), "epe_max_vs_cv2": float(d.max()),
-            "flow_mean_px": float(mag.mean()), "flow_max_px": float(mag.max()),
-            "source": "tests/golden/real_1080p.npz (reference clip, frames 120-121), cv2 flow sampled every 8th px"}
+            "epe_mean_vs_cv2": max(c["epe_mean_vs_cv2"] for c in per_clip),
+            "epe_max_vs_cv2": max(c["epe_max_vs_cv2"] for c in per_clip),
+            "flow_mean_px": max(c["flow_mean_px"] for c in per_clip),
+            "flow_max_px": max(c["flow_max_px"] for c in per_clip),
+            "epe_max_on_cv2_stable_px": max(c.get("epe_max_on_cv2_stable_px", c["epe_max_vs_cv2"]) for c in per_clip),
+            "clips": per_clip,
+            "conditioning": "cv2_stable = pixels where cv2's own flow moves < 0.05 px under one grey level of noise on "
+                            "0.1 % of the input and between its SIMD / plain builds (tests/golden/make_golden_sweep.py); "
+                            "elsewhere cv2 differs from itself by up to 2.4 px on these pairs",
+            "source": "one full-resolution pair of each of the reference's four clips (tests/golden/real_1080p.npz, "
+                      "real_sweep.npz), cv2 flow sampled every 8th px; top-level error figures are the worst clip's"}
 
 
 def pipeline_4k_record(rank, world, dev, pairs=8, steps=3):

@@ -214,7 +214,9 @@ __device__ __forceinline__ int dp2a_hi_su(int a, unsigned b, int c) {
 //
 // A lane's strip is four columns wide.  Its five source bytes of an image row (columns c .. c + 4) are two aligned
 // words and two funnel shifts: R = bytes c .. c + 3, R2 = bytes c + 1 .. c + 4.  The 14-bit bilinear weights fit 16
-// bits, so one IDP.2A does two of the four taps of an element:
+// bits, so one IDP.2A does two of the four taps of an element (the bottom pair as SIGNED halves: w11 is what the three
+// rounded weights leave of 2^14 and is -1 when all three round up and the true weight is below one half -- about one
+// window position in ten thousand; cv2 carries it as a signed short too, and 256 - 255 keeps the sum positive):
 //   v0 = 256 + (w00, w01) . R.lo + (w10, w11) . Rbelow.lo,   v1: R2.lo,   v2: R.hi,   v3: R2.hi        (8 IDP.2A)
 // against sixteen IMADs and four adds.  The four differences stay packed: (v >> 9) + 0x2000 - Iw is positive and below
 // 2^15, so two of them are subtracted from the packed Iw pair with ONE 32-bit add; a byte permute sorts the low and
@@ -250,10 +252,10 @@ __device__ __forceinline__ void lk_window_strips(const uint8_t* __restrict__ J, 
     auto one_row = [&](unsigned blo, unsigned bhi, int2 iq, int4 dq) {
       unsigned Rb, Rb2;
       shifted(blo, bhi, Rb, Rb2);
-      const unsigned v0 = __dp2a_lo(wb, Rb, __dp2a_lo(wt, Rt, 256u));
-      const unsigned v1 = __dp2a_lo(wb, Rb2, __dp2a_lo(wt, Rt2, 256u));
-      const unsigned v2 = __dp2a_hi(wb, Rb, __dp2a_hi(wt, Rt, 256u));
-      const unsigned v3 = __dp2a_hi(wb, Rb2, __dp2a_hi(wt, Rt2, 256u));
+      const unsigned v0 = (unsigned)dp2a_lo_su((int)wb, Rb, (int)__dp2a_lo(wt, Rt, 256u));
+      const unsigned v1 = (unsigned)dp2a_lo_su((int)wb, Rb2, (int)__dp2a_lo(wt, Rt2, 256u));
+      const unsigned v2 = (unsigned)dp2a_hi_su((int)wb, Rb, (int)__dp2a_hi(wt, Rt, 256u));
+      const unsigned v3 = (unsigned)dp2a_hi_su((int)wb, Rb2, (int)__dp2a_hi(wt, Rt2, 256u));
       // e = (v >> 9) + 0x2000 - Iw, two to a register
       const unsigned e01 = __byte_perm(v0 >> 9, v1 >> 9, 0x5410) + 0x20002000u - (unsigned)iq.x;
       const unsigned e23 = __byte_perm(v2 >> 9, v3 >> 9, 0x5410) + 0x20002000u - (unsigned)iq.y;
@@ -387,10 +389,10 @@ __device__ __forceinline__ void lk_patch_strips(const uint8_t* __restrict__ I, c
 #pragma unroll
       for (int k = 0; k < 5; ++k) ndv[k] = dr[k];
       const unsigned Rb = __funnelshift_r(lo, hi, sh), Rb2 = __funnelshift_rc(lo, hi, sh + 8u);
-      const unsigned v0 = __dp2a_lo(wb, Rb, __dp2a_lo(wt, Rt, 256u));
-      const unsigned v1 = __dp2a_lo(wb, Rb2, __dp2a_lo(wt, Rt2, 256u));
-      const unsigned v2 = __dp2a_hi(wb, Rb, __dp2a_hi(wt, Rt, 256u));
-      const unsigned v3 = __dp2a_hi(wb, Rb2, __dp2a_hi(wt, Rt2, 256u));
+      const unsigned v0 = (unsigned)dp2a_lo_su((int)wb, Rb, (int)__dp2a_lo(wt, Rt, 256u));
+      const unsigned v1 = (unsigned)dp2a_lo_su((int)wb, Rb2, (int)__dp2a_lo(wt, Rt2, 256u));
+      const unsigned v2 = (unsigned)dp2a_hi_su((int)wb, Rb, (int)__dp2a_hi(wt, Rt, 256u));
+      const unsigned v3 = (unsigned)dp2a_hi_su((int)wb, Rb2, (int)__dp2a_hi(wt, Rt2, 256u));
       unsigned iw01 = __byte_perm(v0 >> 9, v1 >> 9, 0x5410), iw23 = __byte_perm(v2 >> 9, v3 >> 9, 0x5410);
       int fx[5], fy[5];
 #pragma unroll

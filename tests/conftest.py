@@ -25,6 +25,12 @@ def full1080():
 
 
 @pytest.fixture(scope="session")
+def sweep():
+    """One full-resolution pair from each of the reference's other three clips (tests/golden/make_golden_sweep.py)."""
+    return np.load(os.path.join(GOLDEN, "real_sweep.npz"))
+
+
+@pytest.fixture(scope="session")
 def synth_small():
     return np.load(os.path.join(GOLDEN, "synth_small.npz"))
 
