@@ -9,7 +9,12 @@ vendored); restated from SURVEY.md App. A.4.  Python loop over points, numpy ove
 the window: use on a few hundred points at most.
 
 Window sums are taken exactly (int64) where cv2 accumulates float lanes; the
-survey measured <= 7e-4 px position difference from that.
+survey measured <= 7e-4 px position difference from that on well-conditioned
+windows.  ``accum="cv2_simd128"`` restates cv2's accumulation order instead (the
+CV_SIMD128 branch of LKTrackerInvoker: four float lanes over groups of eight
+columns, a scalar float tail, lanes folded at the end) -- used by the tests to
+show that where the exact sums and cv2 part ways on real footage (diverging
+tracks through near-singular windows) it is this float rounding that does it.
 """
 import numpy as np
 
@@ -30,6 +35,33 @@ def _weights(a, b):
     return iw00, iw01, iw10, 16384 - iw00 - iw01 - iw10
 
 
+def _seq_f32(v):
+    """Sequential float32 accumulation of v (np.add.accumulate adds left to right)."""
+    v = np.asarray(v, np.float32).ravel()
+    return np.add.accumulate(v, dtype=np.float32)[-1] if len(v) else f32(0)
+
+
+def _lane_sums_A(p):
+    """sum of the exact per-pixel products p (wh, ww) in cv2's order: lane l of a float32x4 takes columns 8g + l and
+    8g + 4 + l of every group of eight, row after row; the columns past the last full group go to a scalar float."""
+    wh, ww = p.shape
+    g8 = ww // 8 * 8
+    lanes = [_seq_f32(p[:, :g8].reshape(wh, g8 // 8, 2, 4)[:, :, :, l]) for l in range(4)]
+    tail = _seq_f32(p[:, g8:])
+    return f32(tail + f32(f32(f32(lanes[0] + lanes[1]) + lanes[2]) + lanes[3]))
+
+
+def _lane_sums_b(p):
+    """same for the mismatch vector: a lane adds float(int32 p[8g + l] + p[8g + 4 + l]); lanes 0 / 2 of qb0 and qb1 are
+    folded as (qb0 + qb1)[0] + (qb0 + qb1)[2]."""
+    wh, ww = p.shape
+    g8 = ww // 8 * 8
+    q = p[:, :g8].reshape(wh, g8 // 8, 2, 4)
+    lanes = [_seq_f32((q[:, :, 0, l] + q[:, :, 1, l]).astype(np.float32)) for l in range(4)]
+    tail = _seq_f32(p[:, g8:])
+    return f32(tail + f32(f32(lanes[0] + lanes[2]) + f32(lanes[1] + lanes[3])))
+
+
 def _bilin(P, x0, y0, ww, wh, w4):
     """Integer bilinear over a ww x wh window whose top-left integer corner is (x0,y0) in P's frame."""
     a = P[y0:y0 + wh + 1, x0:x0 + ww + 1].astype(np.int64)
@@ -41,7 +73,7 @@ def _descale(v, n):
 
 
 def pyrlk(prev_img, next_img, prev_pts, next_pts=None, win=(21, 21), max_level=3,
-          criteria=(COUNT | EPS, 30, 0.01), flags=0, min_eig_threshold=1e-4):
+          criteria=(COUNT | EPS, 30, 0.01), flags=0, min_eig_threshold=1e-4, accum="exact"):
     """Returns (nextPts shaped like prev_pts, status uint8 (N,1), err float32 (N,1))."""
     ww, wh = win
     ctype, max_count, eps = criteria
@@ -89,9 +121,11 @@ def pyrlk(prev_img, next_img, prev_pts, next_pts=None, win=(21, 21), max_level=3
             Iw = _descale(_bilin(Ip, x0, y0, ww, wh, w4), 9)
             Ixw = _descale(_bilin(Dx, x0, y0, ww, wh, w4), 14)
             Iyw = _descale(_bilin(Dy, x0, y0, ww, wh, w4), 14)
-            A11 = f32(f32((Ixw * Ixw).sum()) * FLT_SCALE)
-            A12 = f32(f32((Ixw * Iyw).sum()) * FLT_SCALE)
-            A22 = f32(f32((Iyw * Iyw).sum()) * FLT_SCALE)
+            sumA = _lane_sums_A if accum == "cv2_simd128" else (lambda p: f32(p.sum()))
+            sumb = _lane_sums_b if accum == "cv2_simd128" else (lambda p: f32(p.sum()))
+            A11 = f32(sumA(Ixw * Ixw) * FLT_SCALE)
+            A12 = f32(sumA(Ixw * Iyw) * FLT_SCALE)
+            A22 = f32(sumA(Iyw * Iyw) * FLT_SCALE)
             Dt = f32(A11 * A22 - A12 * A12)
             min_eig = f32((A22 + A11 - np.sqrt(f32((A11 - A22) * (A11 - A22) + f32(4) * A12 * A12))) / f32(2 * ww * wh))
             if flags & GET_MIN_EIGENVALS:
@@ -111,8 +145,8 @@ def pyrlk(prev_img, next_img, prev_pts, next_pts=None, win=(21, 21), max_level=3
                     break
                 w4j = _weights(f32(next_pt[0] - inx[0]), f32(next_pt[1] - inx[1]))
                 diff = _descale(_bilin(Jp, int(inx[0]) + px, int(inx[1]) + py, ww, wh, w4j), 9) - Iw
-                b1 = f32(f32((diff * Ixw).sum()) * FLT_SCALE)
-                b2 = f32(f32((diff * Iyw).sum()) * FLT_SCALE)
+                b1 = f32(sumb(diff * Ixw) * FLT_SCALE)
+                b2 = f32(sumb(diff * Iyw) * FLT_SCALE)
                 delta = np.array([f32(f32(A12 * b2 - A22 * b1) * Dt), f32(f32(A12 * b1 - A11 * b2) * Dt)], np.float32)
                 next_pt = next_pt + delta
                 nxt[i] = next_pt + half

@@ -120,6 +120,25 @@ def test_real_sweep_golden_gftt_and_lk(sweep, i):
     assert np.abs(nxt - sweep[f"lk_next_{i}"][sel]).max() < 0.05
 
 
+def test_real_sweep_lk_outliers_are_cv2s_float_lane_accumulation(sweep):
+    """Where the exact-integer window sums (oracle default, and the CUDA path) and cv2 part ways on the sweep's grid
+    points (4 of 6912: tracks of 28-231 px through near-singular windows), restating cv2's float accumulation order
+    (accum="cv2_simd128") brings the oracle back onto cv2's result to the bit -- the difference is cv2's rounding of
+    window sums beyond 2^24, amplified by the ill-conditioned solve, not a different algorithm."""
+    cv2 = pytest.importorskip("cv2")
+    pts = opf.grid_points(1920, 1080, 30)
+    for i, where in [(1, [(795, 975)]), (2, [(495, 1065), (735, 315)])]:
+        g0 = cv2.imdecode(sweep[f"png0_{i}"], cv2.IMREAD_GRAYSCALE)
+        g1 = cv2.imdecode(sweep[f"png1_{i}"], cv2.IMREAD_GRAYSCALE)
+        sel = np.array([int(np.where((pts == np.float32(w)).all(-1))[0][0]) for w in where])
+        want = sweep[f"lk_next_{i}"][sel]
+        exact, _, _ = olk.pyrlk(g1, g0, pts[sel], None, **LK_GRID)
+        lanes, st, err = olk.pyrlk(g1, g0, pts[sel], None, accum="cv2_simd128", **LK_GRID)
+        assert np.abs(exact - want).max(-1).min() > 0.05
+        assert np.array_equal(lanes, want) and np.array_equal(st, sweep[f"lk_status_{i}"][sel])
+        assert np.abs(err - sweep[f"lk_err_{i}"][sel]).max() < 1e-4
+
+
 def test_real_sweep_cv2_disagrees_with_itself_only_on_unstable_pixels(sweep, full1080):
     """The committed conditioning masks: cv2's plain (SIMD off) flow against its optimised one stays within 0.005 px on
     the pixels marked stable and reaches 0.28 / 2.1 px on the others (clips 0 / 2) -- the max-EPE bar of the north_star
