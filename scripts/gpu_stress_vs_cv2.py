@@ -25,11 +25,11 @@ for ci, (g0, g1) in enumerate(pairs):
         off = np.where((d > 0.05) | (gs.ravel() != ws.ravel()))[0]
         msg = "clip %d win %s: status agree %.5f, within 0.05 px %.5f, outliers %d" % (ci, win, (gs == ws).mean(), (d <= 0.05).mean(), len(off))
         if len(off):
-            sel = off[:6]
+            sel = off[:int(os.environ.get('STRESS_ORACLE', 6))]
             on, os_, oe = olk.pyrlk(g1, g0, pts[sel], None, win, lvl, crit)
             do = np.abs(on - gn[sel]).max(-1)
-            msg += "; first %d vs oracle: max %.2e, status equal %s, flow lengths %s" % (
-                len(sel), do.max(), np.array_equal(os_.ravel(), gs[sel].ravel()), np.round(np.linalg.norm(wn[sel] - pts[sel], axis=1), 0))
+            msg += "; first %d vs oracle: max %.2e, status equal %s, median flow length %.0f" % (
+                len(sel), do.max(), np.array_equal(os_.ravel(), gs[sel].ravel()), np.median(np.linalg.norm(wn[sel] - pts[sel], axis=1)))
         print(msg, flush=True)
     for name, kw in {"sparse": dict(maxCorners=20, qualityLevel=0.3, minDistance=10, blockSize=7),
                      "dense": dict(maxCorners=500, qualityLevel=0.01, minDistance=5, blockSize=3),
