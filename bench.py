@@ -478,7 +478,11 @@ def main():
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "fb_iter_ws @ finest level (warp-specialised fused UpdateMatrices + 15x15 box + 2x2 solve)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                     "traffic": traffic, "peak_source": peak_src, "launches": dom["launches"],
+                     "traffic": traffic,
+                     "traffic_source": "profiles/roofline_traffic.json: ncu dram__bytes_read + write of the shipped kernel "
+                                       "(one --set full capture per kernel change), scaled to this launch's pairs; a "
+                                       "constant, not re-measured in this run",
+                     "peak_source": peak_src, "launches": dom["launches"],
                      "avg_launch_ms": dom["ms"] / dom["launches"] if dom["launches"] else None,
                      "algorithmic_bytes_per_launch": dom["bytes"] / dom["launches"] if dom["launches"] else None,
                      "share_of_step": dom["ms"] / total_ms if total_ms else None,
