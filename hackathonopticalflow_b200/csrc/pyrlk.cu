@@ -716,7 +716,7 @@ int pyrlk_dev(const uint8_t* prev, const uint8_t* next, size_t step, size_t fram
   a.n_pts = n_pts;
   a.ww = p->win_w; a.wh = p->win_h;
   int mc = 30;
-  double eps = 0.001;
+  double eps = 0.01;     // cv2's value when the criteria carry no EPS (probed against the wheel: COUNT-only == (COUNT|EPS, 0.01))
   if (p->crit_type & B2OF_TERM_COUNT) mc = p->crit_max_count < 0 ? 0 : (p->crit_max_count > 100 ? 100 : p->crit_max_count);
   if (p->crit_type & B2OF_TERM_EPS) eps = p->crit_eps < 0 ? 0. : (p->crit_eps > 10. ? 10. : p->crit_eps);
   double eps2 = eps * eps;

@@ -78,7 +78,7 @@ def pyrlk(prev_img, next_img, prev_pts, next_pts=None, win=(21, 21), max_level=3
     ww, wh = win
     ctype, max_count, eps = criteria
     max_count = min(max(int(max_count), 0), 100) if ctype & COUNT else 30
-    eps = min(max(float(eps), 0.0), 10.0) if ctype & EPS else 0.001
+    eps = min(max(float(eps), 0.0), 10.0) if ctype & EPS else 0.01   # probed: cv2 COUNT-only == (COUNT|EPS, .., 0.01)
     eps2 = eps * eps
     pts = np.asarray(prev_pts, np.float32).reshape(-1, 2)
     n = len(pts)

@@ -1018,3 +1018,138 @@ def test_overlay_layers_vs_oracle_restatement(batch, ref_funcs, crops, full1080)
         got = batch.overlay_lamps(filt, h, w)[0].cpu().numpy()
         want = ov.lamp_layer(filt["kept_flow"][0, :k].cpu().numpy(), filt["kept_pts"][0, :k].cpu().numpy(), w, h)
         assert np.array_equal(got, want), name
+
+
+# ------------------------------------------------------------------ randomised sweeps against live cv2 (real footage)
+def _real_pairs(sweep, full1080):
+    return [(_decode_png(sweep[f"png0_{i}"]), _decode_png(sweep[f"png1_{i}"])) for i in range(3)] + \
+           [(_decode_png(full1080["png0"]), _decode_png(full1080["png1"]))]
+
+
+@pytest.mark.skipif(not have_cv2(), reason="cv2 wheel not importable on this box")
+def test_lk_random_options_on_real_crops_vs_live_cv2(b2, sweep, full1080):
+    """Random windows (3-59), pyramid depths, criteria forms, flags (initial flow, min-eigenvalue error), thresholds and
+    strided views on random crops of the real pairs (scripts/gpu_stress_sparse_opts.py, first 16 cases): statuses and
+    positions against live cv2; every point that differs must equal the exact-integer oracle (cv2's float-lane
+    accumulation on diverging tracks)."""
+    import cv2
+    from oracle import pyrlk as olk
+    pairs = _real_pairs(sweep, full1080)
+    rng = np.random.default_rng(0)
+    for c in range(16):
+        g0, g1 = pairs[c % 4]
+        h, w = int(rng.integers(40, 1080)), int(rng.integers(40, 1920))
+        y0, x0 = int(rng.integers(0, 1080 - h + 1)), int(rng.integers(0, 1920 - w + 1))
+        a, b = g0[y0:y0 + h, x0:x0 + w], g1[y0:y0 + h, x0:x0 + w]
+        if c % 3:
+            a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        n = int(rng.integers(1, 1500))
+        pts = np.float32(np.stack([rng.uniform(-5, w + 5, n), rng.uniform(-5, h + 5, n)], 1))
+        win, lvl = (int(rng.integers(3, 60)), int(rng.integers(3, 60))), int(rng.integers(0, 6))
+        crit = (int(rng.choice([1, 2, 3])), int(rng.integers(1, 40)), float(rng.choice([0.001, 0.01, 0.03, 0.3])))
+        flags, thr = int(rng.choice([0, 0, 4, 8, 12])), float(rng.choice([1e-4, 1e-4, 1e-3, 1e-2]))
+        init = np.float32(pts + rng.normal(0, 3, pts.shape)) if flags & 4 else None
+        kw = dict(winSize=win, maxLevel=lvl, criteria=crit, flags=flags, minEigThreshold=thr)
+        wn, ws, we = cv2.calcOpticalFlowPyrLK(b, a, pts, None if init is None else init.copy(), **kw)
+        gn, gs, ge = b2.calcOpticalFlowPyrLK(b, a, pts, None if init is None else init.copy(), **kw)
+        d = np.abs(gn - wn).max(-1)
+        off = np.where((d > LK_POS_TOL) | (gs.ravel() != ws.ravel()))[0][:8]
+        if len(off):
+            on, os_, _ = olk.pyrlk(b, a, pts[off], None if init is None else init[off].copy(), win, lvl, crit, flags, thr)
+            assert np.array_equal(os_.ravel(), gs[off].ravel()) and np.abs(on - gn[off]).max() <= 1e-3, (c, kw)
+        assert (gs == ws).mean() >= LK_STATUS_TOL, (c, kw)
+        assert (d <= LK_POS_TOL).mean() >= 0.98, (c, (h, w), n, kw, (d <= LK_POS_TOL).mean())
+        ok = (gs.ravel() == 1) & (ws.ravel() == 1) & (d <= LK_POS_TOL)
+        if ok.any():
+            assert np.abs(ge.ravel()[ok] - we.ravel()[ok]).max() <= 0.05, (c, kw)
+
+
+@pytest.mark.skipif(not have_cv2(), reason="cv2 wheel not importable on this box")
+def test_gftt_random_options_on_real_crops_vs_live_cv2(b2, sweep, full1080):
+    """Random masks, block sizes, Sobel apertures 3 / 5 / 7, Harris, maxCorners 0-3000, fractional minDistance on random
+    crops (strided and contiguous) of the real frames: corner lists against live cv2."""
+    import cv2
+    pairs = _real_pairs(sweep, full1080)
+    rng = np.random.default_rng(1)
+    for c in range(24):
+        g0 = pairs[c % 4][c // 4 % 2]
+        h, w = int(rng.integers(16, 1080)), int(rng.integers(16, 1920))
+        y0, x0 = int(rng.integers(0, 1080 - h + 1)), int(rng.integers(0, 1920 - w + 1))
+        img = g0[y0:y0 + h, x0:x0 + w] if c % 2 else np.ascontiguousarray(g0[y0:y0 + h, x0:x0 + w])
+        kw = dict(maxCorners=int(rng.choice([0, 1, 20, 100, 500, 3000])), qualityLevel=float(rng.choice([0.3, 0.1, 0.03, 0.01])),
+                  minDistance=float(rng.choice([0, 1, 3.5, 10, 10.5, 40])), blockSize=int(rng.choice([3, 5, 7, 9, 15])))
+        if rng.random() < 0.3:
+            kw.update(useHarrisDetector=True, k=float(rng.choice([0.04, 0.06])))
+        g = int(rng.choice([3, 3, 5, 7]))
+        if g != 3:
+            kw["gradientSize"] = g
+        mask = (rng.random((h, w)) < rng.random()).astype(np.uint8) * 255 if rng.random() < 0.5 else None
+        want = cv2.goodFeaturesToTrack(img, mask=mask, **kw)
+        got = b2.goodFeaturesToTrack(img, mask=mask, **kw)
+        if want is None or got is None:
+            assert want is None and got is None, (c, kw)
+            continue
+        assert got.shape == want.shape, (c, kw, got.shape, want.shape)
+        if not np.array_equal(got, want):     # near-equal scores may swap places (DESIGN, known deviation)
+            A, C = set(map(tuple, got.reshape(-1, 2))), set(map(tuple, want.reshape(-1, 2)))
+            assert len(A ^ C) <= max(2, len(C) // 100), (c, kw, len(A ^ C), len(C))
+
+
+@pytest.mark.skipif(not have_cv2(), reason="cv2 wheel not importable on this box")
+def test_farneback_random_shapes_and_parameters_vs_live_cv2(b2):
+    """Random frame sizes (33x33 ... 64x2000, 1500x40) and parameter sets (pyr_scale 0.5-0.9, 1-6 levels, windows 5-45,
+    box and Gaussian, poly_n 5 / 7) on synthetic texture against live cv2 (scripts/gpu_stress_farneback.py, first 20
+    cases; measured: max <= 0.006 px except at pixels where cv2 with its SIMD paths off differs from itself by as much)."""
+    import cv2
+    from hackathonopticalflow_b200 import synth
+    rng = np.random.default_rng(0)
+    for c in range(20):
+        h, w = int(rng.integers(33, 700)), int(rng.integers(33, 900))
+        if c % 7 == 0:
+            h, w = [(1080, 1920), (720, 1280), (33, 33), (64, 2000), (1500, 40), (481, 641)][(c // 7) % 6]
+        args = dict(pyr_scale=float(rng.choice([0.5, 0.5, 0.6, 0.75, 0.8, 0.9])), levels=int(rng.integers(1, 7)),
+                    winsize=int(rng.choice([5, 9, 15, 15, 16, 21, 31, 45])), iterations=int(rng.integers(1, 5)),
+                    poly_n=int(rng.choice([5, 5, 7])), poly_sigma=float(rng.choice([1.1, 1.2, 1.5])),
+                    flags=int(rng.choice([0, 0, 256])))
+        if c % 5 == 0:
+            args.update(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)
+        fr = synth.sequence(h, w, 2, seed=500 + c)
+        want = cv2.calcOpticalFlowFarneback(fr[0], fr[1], None, **args)
+        got = b2.calcOpticalFlowFarneback(fr[0], fr[1], None, **args)
+        d = np.sqrt(((got.astype(np.float64) - want) ** 2).sum(-1))
+        assert d.mean() <= FB_MEAN_TOL and d.mean() <= 5e-3, (c, h, w, args, d.mean())
+        if d.max() > 0.02:
+            # only where the reference does not reproduce itself: cv2's plain build must be off by a comparable amount
+            cv2.setUseOptimized(False)
+            plain = cv2.calcOpticalFlowFarneback(fr[0], fr[1], None, **args)
+            cv2.setUseOptimized(True)
+            s = np.sqrt(((plain.astype(np.float64) - want) ** 2).sum(-1))
+            assert s.max() >= 0.3 * d.max(), (c, h, w, args, d.max(), s.max())
+            assert (d > 0.02).mean() <= max(1e-3, 2 * (s > 0.02).mean()), (c, h, w, args, (d > 0.02).mean(), (s > 0.02).mean())
+
+
+def test_pipeline_on_real_footage_equals_single_calls(b2, batch, sweep, full1080):
+    """PathfinderPipeline on the four real 1080p pairs played as one BGR sequence (seven pairs, three of them scene cuts),
+    chunk of three pairs: every per-pair output bit for bit what the single calls return, filter / danger output
+    identical to the restatement of the reference's functions applied to the same LK result."""
+    import torch
+    from hackathonopticalflow_b200 import pathfinder
+    from oracle import pathfinder as opf
+    seq = np.stack([g for p in _real_pairs(sweep, full1080) for g in p])
+    bgr = np.ascontiguousarray(np.repeat(seq[..., None], 3, -1))
+    pts = pathfinder.grid_points(1920, 1080, 30)
+    pipe = pathfinder.PathfinderPipeline(1080, 1920, dense=True, chunk_pairs=3)
+    out = pipe.run(torch.from_numpy(bgr).cuda())
+    torch.cuda.synchronize()
+    for k in range(7):
+        nxt, st, err = b2.calcOpticalFlowPyrLK(seq[k + 1], seq[k], pts, None, **LK_GRID)
+        flow = b2.calcOpticalFlowFarneback(seq[k], seq[k + 1], None, *REF_FB)
+        assert np.array_equal(out["gray"][k].cpu().numpy(), seq[k])
+        assert np.array_equal(out["next_pts"][k].cpu().numpy(), nxt.reshape(-1, 2))
+        assert np.array_equal(out["status"][k].cpu().numpy().ravel(), st.ravel())
+        assert np.array_equal(out["flow"][k].cpu().numpy(), flow)
+        fo, po, mo, _ = opf.vector_filter(nxt.reshape(-1, 2), pts, 1920, 1080)
+        n = int(out["n_kept"][k])
+        assert n == len(po) and np.array_equal(out["kept_pts"][k, :n].cpu().numpy(), po)
+        assert np.array_equal(out["kept_flow"][k, :n].cpu().numpy(), fo)
+        assert np.array_equal(out["danger_v"][k, :n].cpu().numpy(), opf.danger_intensity(fo, po))

@@ -120,6 +120,22 @@ def test_real_sweep_golden_gftt_and_lk(sweep, i):
     assert np.abs(nxt - sweep[f"lk_next_{i}"][sel]).max() < 0.05
 
 
+def test_lk_criteria_defaults_match_live_cv2(crops):
+    """cv2 fills in the half of the criteria the caller leaves out: COUNT-only runs with epsilon 0.01 (the survey said
+    0.001; probed on the wheel, and found by the randomised GPU sweep on real footage), EPS-only with 30 iterations."""
+    cv2 = pytest.importorskip("cv2")
+    g0, g1 = crops["gray0_1"], crops["gray1_1"]
+    rng = np.random.default_rng(3)
+    pts = np.float32(np.stack([rng.uniform(30, 610, 60), rng.uniform(30, 330, 60)], 1))
+    for crit, same_as in [((1, 25, 0.3), (3, 25, 0.01)), ((2, 5, 0.02), (3, 30, 0.02))]:
+        want, ws, _ = cv2.calcOpticalFlowPyrLK(g1, g0, pts, None, winSize=(21, 21), maxLevel=2, criteria=crit)
+        twin, _, _ = cv2.calcOpticalFlowPyrLK(g1, g0, pts, None, winSize=(21, 21), maxLevel=2, criteria=same_as)
+        assert np.array_equal(want, twin)
+        got, st, _ = olk.pyrlk(g1, g0, pts, None, (21, 21), 2, crit)
+        assert np.array_equal(st, ws)
+        assert (np.abs(got - want).max(-1) <= 0.01).mean() >= 0.95
+
+
 def test_real_sweep_lk_outliers_are_cv2s_float_lane_accumulation(sweep):
     """Where the exact-integer window sums (oracle default, and the CUDA path) and cv2 part ways on the sweep's grid
     points (4 of 6912: tracks of 28-231 px through near-singular windows), restating cv2's float accumulation order
