@@ -9,6 +9,7 @@ from hackathonopticalflow_b200 import cv2compat as b2, synth
 cv2.setNumThreads(8)
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+INIT = len(sys.argv) > 3
 res = []
 for c in range(N):
     h, w = int(rng.integers(33, 700)), int(rng.integers(33, 900))
@@ -21,12 +22,19 @@ for c in range(N):
     if c % 5 == 0:
         args.update(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)   # the reference's set
     fr = synth.sequence(h, w, 2, seed=500 + c)
+    init = None
+    if INIT and c % 3 == 1:                     # caller-supplied initial field (strided every other time)
+        args["flags"] |= 4
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+        init = np.stack([3 * np.sin(yy / 37) + rng.normal(0, 0.3, (h, w)), 2 * np.cos(xx / 51) + rng.normal(0, 0.3, (h, w))], -1).astype(np.float32)
+        if c % 2:
+            big = np.zeros((h, w, 4), np.float32); big[..., :2] = init; init = big[..., :2]
     try:
-        want = cv2.calcOpticalFlowFarneback(fr[0], fr[1], None, **args)
+        want = cv2.calcOpticalFlowFarneback(fr[0], fr[1], None if init is None else init.copy(), **args)
     except cv2.error as e:
         print("cv2 rejects", h, w, args); continue
     try:
-        got = b2.calcOpticalFlowFarneback(fr[0], fr[1], None, **args)
+        got = b2.calcOpticalFlowFarneback(fr[0], fr[1], None if init is None else init.copy(), **args)
     except Exception as e:
         print("b200 raises", h, w, args, repr(e)[:200]); continue
     d = np.sqrt(((got.astype(np.float64) - want) ** 2).sum(-1))
