@@ -321,7 +321,10 @@ __global__ void flow_stats_final(float* __restrict__ stats, size_t n_px, int n_p
 // The cvtColor call is third-party (opencv color_hsv.simd.hpp): float32 h * (6/180), v * (1/255), the table
 // {v, v(1-s), v(1-s f), v(1-s(1-f))} with s = 1, times 255, truncated (oracle/pathfinder.py::hsv2bgr_u8, pinned
 // against cv2 for every (h, v) at the saturation the reference writes).  arctan2 is evaluated in double and rounded
-// once, which reproduces numpy's correctly rounded float32 result.
+// once.  numpy 2's float32 arctan2 is a SIMD routine that is NOT correctly rounded (it differs from the rounded double
+// value on 38 % of random inputs, by an ulp), so where ang * 28.65 lands within an ulp of an integer the truncated hue
+// differs by one: 1 to 4 pixels per million on random fields (scripts/gpu_stress_overlay.py), and which pixels
+// depends on the host's numpy build.
 __global__ void __launch_bounds__(256) flow_hsv_bgr(const float2* __restrict__ flow, size_t n_px,
                                                      uint8_t* __restrict__ bgr) {
   const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
