@@ -22,6 +22,10 @@ from . import _lib
 from ._lib import error, FarnebackParams, LKParams, GFTTParams
 
 COLOR_BGR2GRAY = 6
+COLOR_RGB2GRAY = 7
+COLOR_BGRA2GRAY = 10
+COLOR_RGBA2GRAY = 11
+BORDER_DEFAULT = 4
 TERM_CRITERIA_COUNT = TERM_CRITERIA_MAX_ITER = 1
 TERM_CRITERIA_EPS = 2
 OPTFLOW_USE_INITIAL_FLOW = 4
@@ -86,10 +90,15 @@ def cvtColor(src, code, dst=None, dstCn=0, hint=0):
     """``cv2.cvtColor(src, code[, dst[, dstCn[, hint]]])``; ``hint`` (cv2.AlgorithmHint) selects between cv2's exact and
     approximate colour paths and does not change BGR2GRAY, so it is accepted and ignored."""
     fn = "cvtColor"
-    if code != COLOR_BGR2GRAY:
-        raise error(-213, f"only COLOR_BGR2GRAY ({COLOR_BGR2GRAY}) is on the reference's path; got code {code}")
-    _assert(isinstance(src, np.ndarray) and src.dtype == np.uint8 and src.ndim == 3 and src.shape[2] == 3,
-            "scn == 3 && depth == CV_8U", fn)
+    if code not in (COLOR_BGR2GRAY, COLOR_RGB2GRAY, COLOR_BGRA2GRAY, COLOR_RGBA2GRAY):
+        raise error(-213, f"only the *2GRAY codes 6 / 7 / 10 / 11 are supported (the reference uses COLOR_BGR2GRAY); got code {code}")
+    _assert(isinstance(src, np.ndarray) and src.size > 0, "!_src.empty()", fn)
+    # cv2 takes three or four channels for every one of these codes and ignores the fourth
+    _assert(src.dtype == np.uint8 and src.ndim == 3 and src.shape[2] in (3, 4), "(scn == 3 || scn == 4) && depth == CV_8U", fn)
+    if code in (COLOR_RGB2GRAY, COLOR_RGBA2GRAY):
+        src = np.ascontiguousarray(src[..., 2::-1])      # same coefficients with the colour order swapped
+    elif src.shape[2] == 4:
+        src = np.ascontiguousarray(src[..., :3])
     if src.strides[2] != 1 or src.strides[1] != 3:
         src = np.ascontiguousarray(src)
     h, w = src.shape[:2]
@@ -100,10 +109,16 @@ def cvtColor(src, code, dst=None, dstCn=0, hint=0):
     return dst
 
 
-def pyrDown(src, dst=None):
+def pyrDown(src, dst=None, dstsize=None, borderType=BORDER_DEFAULT):
+    """``cv2.pyrDown(src[, dst[, dstsize[, borderType]]])`` for the default output size and border (what the reference
+    and cv2's own LK pyramid use); any other ``dstsize`` / ``borderType`` is refused, not approximated."""
     src = _image_u8(src, "src", "pyrDown")
     h, w = src.shape
     shape = ((h + 1) // 2, (w + 1) // 2)
+    if dstsize is not None and tuple(dstsize) not in ((0, 0), (shape[1], shape[0])):
+        raise error(-213, f"pyrDown: only the default dstsize {(shape[1], shape[0])} is supported; got {tuple(dstsize)}")
+    if borderType != BORDER_DEFAULT:
+        raise error(-213, f"pyrDown: only BORDER_DEFAULT (BORDER_REFLECT_101) is supported; got {borderType}")
     if dst is None or not (isinstance(dst, np.ndarray) and dst.shape == shape and dst.dtype == np.uint8
                            and dst.flags.c_contiguous):
         dst = np.empty(shape, np.uint8)
@@ -199,7 +214,7 @@ def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts, status=None, err=No
     st = status if _reuse(status, (n, 1), np.uint8) else np.empty((n, 1), np.uint8)
     er = err if _reuse(err, (n, 1), np.float32) else np.empty((n, 1), np.float32)
     if n == 0:
-        return nxt_ret, st, er
+        return None, None, None          # what cv2's binding hands back for an empty point set
     if prevImg.strides[0] != nextImg.strides[0]:
         prevImg, nextImg = np.ascontiguousarray(prevImg), np.ascontiguousarray(nextImg)
     h, w = prevImg.shape

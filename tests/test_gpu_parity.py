@@ -104,6 +104,30 @@ def test_gray_noncontiguous_and_dst_buffer(b2):
     assert out is dst and np.array_equal(out, ogp.bgr2gray(view))
 
 
+@pytest.mark.skipif(not have_cv2(), reason="cv2 wheel not importable on this box")
+def test_cvtcolor_gray_codes_and_pyrdown_arguments_vs_live_cv2(b2):
+    """The other *2GRAY codes and four-channel input (cv2 ignores the fourth channel), pyrDown's optional arguments at
+    their defaults, and the refusals: bit-exact against live cv2 where cv2 succeeds, an error where cv2 raises."""
+    import cv2
+    rng = np.random.default_rng(2)
+    img4 = rng.integers(0, 256, (77, 131, 4), dtype=np.uint8)
+    img3 = np.ascontiguousarray(img4[..., :3])
+    for code in (cv2.COLOR_BGR2GRAY, cv2.COLOR_RGB2GRAY, cv2.COLOR_BGRA2GRAY, cv2.COLOR_RGBA2GRAY):
+        for src in (img3, img4, img4[:, ::2], img3[5:60, 7:100]):
+            assert np.array_equal(b2.cvtColor(src, code), cv2.cvtColor(src, code)), (code, src.shape)
+    with pytest.raises(Exception):
+        b2.cvtColor(np.zeros((0, 0, 3), np.uint8), cv2.COLOR_BGR2GRAY)
+    with pytest.raises(Exception):
+        b2.cvtColor(img3, cv2.COLOR_BGR2HSV)
+    g = rng.integers(0, 256, (75, 131), dtype=np.uint8)
+    assert np.array_equal(b2.pyrDown(g, dstsize=(66, 38)), cv2.pyrDown(g, dstsize=(66, 38)))
+    assert np.array_equal(b2.pyrDown(g, None, (0, 0), cv2.BORDER_DEFAULT), cv2.pyrDown(g))
+    with pytest.raises(Exception):
+        b2.pyrDown(g, dstsize=(65, 38))
+    with pytest.raises(Exception):
+        b2.pyrDown(g, borderType=cv2.BORDER_REPLICATE)
+
+
 def test_pyrdown_batched_device_chain(batch):
     import torch
     from oracle import gray_pyr as ogp

@@ -5,6 +5,7 @@ import sys
 
 import numpy as np
 import pytest
+from conftest import have_cv2
 
 from conftest import ROOT
 from hackathonopticalflow_b200 import cv2compat as b2
@@ -57,10 +58,14 @@ def test_cv2_style_argument_errors():
         b2.cvtColor(g, b2.COLOR_BGR2GRAY)  # not 3-channel
 
 
-def test_empty_point_set_returns_empty_arrays_without_gpu():
+def test_empty_point_set_returns_what_cv2_returns_without_gpu():
     g = np.zeros((40, 50), np.uint8)
-    nxt, st, err = b2.calcOpticalFlowPyrLK(g, g, np.zeros((0, 1, 2), np.float32), None)
-    assert nxt.shape == (0, 1, 2) and st.shape == (0, 1) and err.shape == (0, 1)
+    for shape in ((0, 1, 2), (0, 2)):
+        got = b2.calcOpticalFlowPyrLK(g, g, np.zeros(shape, np.float32), None)
+        assert got == (None, None, None)
+        if have_cv2():
+            import cv2
+            assert cv2.calcOpticalFlowPyrLK(g, g, np.zeros(shape, np.float32), None) == got
 
 
 def test_gather_stats_two_ranks_gloo(tmp_path):
