@@ -245,8 +245,31 @@ def real_1080p_record(batch, dev, pairs):
             rec.update({"cv2_stable_fraction": float(stable.mean()), "epe_max_on_cv2_stable_px": float(d[stable].max()),
                         "fraction_over_0.5px": float((d > 0.5).mean())})
         per_clip.append(rec)
-    del eng, flow, frames
+    # the same sequence with the library's blocked horizontal sums (B2OF_FARNEBACK_BLOCKED_SUMS, include/b2of.h)
+    eng_b = batch.FarnebackEngine(H, W, chunk_pairs=pairs, device=dev, **{**PARAMS, "flags": PARAMS.get("flags", 0) | 0x10000})
+    for _ in range(2):
+        eng_b.flow_sequence(frames, flow)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        eng_b.flow_sequence(frames, flow)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_b = e0.elapsed_time(e1) / n
+    blocked = []
+    for (a, b, want, src, bits), k in zip(clips, first):
+        if k >= pairs or bits is None:
+            continue
+        got = flow[k, ::8, ::8].cpu().numpy().astype(np.float64)
+        d = np.sqrt(((got - want.astype(np.float64)) ** 2).sum(-1))
+        stable = np.unpackbits(bits)[:d.size].reshape(d.shape).astype(bool)
+        blocked.append({"source": src, "epe_mean_vs_cv2": float(d.mean()), "epe_max_on_cv2_stable_px": float(d[stable].max()),
+                        "fraction_over_0.5px": float((d > 0.5).mean())})
+    del eng, eng_b, flow, frames
     return {"pairs_per_s": pairs / (ms * 1e-3), "ms_per_step": ms, "pairs_per_step": pairs,
+            "blocked_sums": {"pairs_per_s": pairs / (ms_b * 1e-3), "clips": blocked,
+                             "note": "flags | B2OF_FARNEBACK_BLOCKED_SUMS: horizontal box sums per block of 15 instead "
+                                     "of sliding (each output sums only its own inputs)"},
             "epe_mean_vs_cv2": max(c["epe_mean_vs_cv2"] for c in per_clip),
             "epe_max_vs_cv2": max(c["epe_max_vs_cv2"] for c in per_clip),
             "flow_mean_px": max(c["flow_mean_px"] for c in per_clip),

@@ -2019,12 +2019,13 @@ static void set_func_attrs() {
   B2OF_ATTR(512, 0, 0, false)
   B2OF_ATTR(512, 0, 0, true)
 #undef B2OF_ATTR
-  cudaFuncSetAttribute(fb_iter_ws<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
-  cudaFuncSetAttribute(fb_iter_ws<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
-  cudaFuncSetAttribute(fb_iter_ws<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
-  cudaFuncSetAttribute(fb_iter_ws<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
-  cudaFuncSetAttribute(fb_iter_ws<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
-  cudaFuncSetAttribute(fb_iter_ws<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM);
+#define B2OF_WS_ATTR(MODE, STATS, HB) \
+  cudaFuncSetAttribute(fb_iter_ws<MODE, STATS, HB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FBW_SMEM)
+  B2OF_WS_ATTR(0, false, false); B2OF_WS_ATTR(1, false, false); B2OF_WS_ATTR(2, false, false);
+  B2OF_WS_ATTR(0, true, false); B2OF_WS_ATTR(1, true, false); B2OF_WS_ATTR(2, true, false);
+  B2OF_WS_ATTR(0, false, true); B2OF_WS_ATTR(1, false, true); B2OF_WS_ATTR(2, false, true);
+  B2OF_WS_ATTR(0, true, true); B2OF_WS_ATTR(1, true, true); B2OF_WS_ATTR(2, true, true);
+#undef B2OF_WS_ATTR
   cudaFuncSetAttribute(fb_polyexp, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   cudaFuncSetAttribute(fb_level_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 }
@@ -2202,15 +2203,16 @@ static int fb_pairs_range(const FbPlan* pl, const FbWorkspace& ws, int pairs_tot
           if (b.mode == 1 && b.in_pitch != L.pitch)     // the kernel indexes flow_in with the level's own pitch
             return fail(B2OF_E_BADARG, "internal: flow_in pitch %d != level pitch %d", b.in_pitch, L.pitch);
           dim3 gs(pairs, nstrips, cdiv(blocks, b.nb));
-          if (b.stats_acc) {
-            if (b.mode == 0) fb_iter_ws<0, true><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
-            else if (b.mode == 1) fb_iter_ws<1, true><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
-            else fb_iter_ws<2, true><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
-          } else {
-            if (b.mode == 0) fb_iter_ws<0, false><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
-            else if (b.mode == 1) fb_iter_ws<1, false><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
-            else fb_iter_ws<2, false><<<gs, FBW_NT, FBW_SMEM, st>>>(b);
-          }
+          // horizontal window sums: sliding (default) or per block of 15 (B2OF_FARNEBACK_BLOCKED_SUMS, fb_ws.cuh)
+          const bool hblock = (call_flags & B2OF_FARNEBACK_BLOCKED_SUMS) != 0;
+#define B2OF_WS_LAUNCH(MODE, STATS, HB) fb_iter_ws<MODE, STATS, HB><<<gs, FBW_NT, FBW_SMEM, st>>>(b)
+#define B2OF_WS_MODE(STATS, HB) \
+  do { if (b.mode == 0) B2OF_WS_LAUNCH(0, STATS, HB); else if (b.mode == 1) B2OF_WS_LAUNCH(1, STATS, HB); \
+       else B2OF_WS_LAUNCH(2, STATS, HB); } while (0)
+          if (b.stats_acc) { if (hblock) B2OF_WS_MODE(true, true); else B2OF_WS_MODE(true, false); }
+          else { if (hblock) B2OF_WS_MODE(false, true); else B2OF_WS_MODE(false, false); }
+#undef B2OF_WS_MODE
+#undef B2OF_WS_LAUNCH
         } else if (gauss) B2OF_ITER_LAUNCH(512, 0, 0, true);
         else B2OF_ITER_LAUNCH(512, 0, 0, false);
 #undef B2OF_ITER_LAUNCH

@@ -206,18 +206,62 @@ __device__ __forceinline__ T hp_sub(T a, T b);
 template <> __device__ __forceinline__ float2 hp_sub<float2>(float2 a, float2 b) { return sub2(a, b); }
 template <> __device__ __forceinline__ float hp_sub<float>(float a, float b) { return a - b; }
 
-// The 15 most recent inputs stay in a register window (circular, statically indexed: the walk is unrolled by the
-// window length), so every element is read from shared memory once and written once.
-template <typename T, bool FULL>
+// Sums are taken per block of 15 positions, not as a sliding sum: output xo = 15 b + j is
+//   (suffix of block b from j) + (prefix of block b + 1 up to j - 1),
+// i.e. exactly its own 15 inputs, added in a fixed order.  A sliding sum (s += new; s -= old) is one add cheaper per
+// output but carries the absolute rounding error of whatever passed through the window: behind bright texture a dark
+// wall's sums keep errors of the texture's magnitude, and on real footage that was the path's largest source of
+// disagreement with cv2 at near-singular pixels (restated in numpy: 102 of 32,400 sampled pixels beyond 0.5 px with a
+// sliding horizontal pass, 10 with direct sums -- cv2 against its own plain build: 12).  Cost: 42 adds per 15 outputs
+// instead of 30; the register window is the same (a slot holds a block's suffix sum until its output is out, then the
+// next block's input), and every element is still read from shared memory once and written once.
+// The sliding walk stays the default (BLOCKED = false: 3 % more pairs/s end to end, and on well-conditioned pixels the
+// two agree to 1e-3 px); the blocked walk is chosen per call with B2OF_FARNEBACK_BLOCKED_SUMS in the flags.
+template <typename T, int DIR>
+__device__ __forceinline__ void hpass_blocked(T* __restrict__ base, int n_out, T (&win)[2 * FBS_M + 1]) {
+  constexpr int WN = 2 * FBS_M + 1;
+  if (n_out <= 0) return;
+#pragma unroll
+  for (int k = 0; k < WN; ++k) win[k] = base[DIR * k];
+  for (int eb = 0; eb < n_out; eb += WN) {
+    // win[] holds block eb / 15 raw: turn it into suffix sums in place
+#pragma unroll
+    for (int k = WN - 2; k >= 0; --k) win[k] = hp_add(win[k], win[k + 1]);
+    T* b = base + DIR * eb;
+    const int left = n_out - eb;                       // outputs from this block on
+    T pre;
+#pragma unroll
+    for (int j = 0; j < WN; ++j) {
+      if (j < left) {
+        b[DIR * j] = j == 0 ? win[0] : hp_add(win[j], pre);
+        if (j + 1 < left) {                            // element e + 15: the last input of output e + 1
+          const T nw = b[DIR * (j + WN)];
+          pre = j == 0 ? nw : hp_add(pre, nw);
+          win[j] = nw;
+        }
+      }
+    }
+  }
+}
+template <typename T, bool FULL, bool BLOCKED>
 __device__ __forceinline__ void hpass_half_row(T* rowp, bool right, int nv) {
   // nv = outputs this strip really has (FULL: the whole strip, compile-time bounds; otherwise the last strip of a
   // row: nothing beyond its outputs is summed)
   constexpr int M = FBS_M, HL = FBS_HL, WN = 2 * M + 1;
   const int TW = FULL ? FBS_TW : nv;
   T win[WN];
+  if constexpr (BLOCKED) {
+    // One walk for both halves: element e of the walk is position e (left half, left -> right, stored at its own
+    // position) or position TW - 1 + 14 - e counted down from the right-most input (right half, right -> left).
+    // Output e sums elements [e, e + 14] and is stored at element e.  The direction is a compile-time constant of each
+    // call, so that the loads and stores of an unrolled block have provably different offsets and the loads can be
+    // issued ahead.
+    if (!right) hpass_blocked<T, 1>(rowp, FULL ? HL : min(HL, nv), win);
+    else hpass_blocked<T, -1>(rowp + (TW - 1 + 2 * M), TW - HL, win);
+    return;
+  }
   if (!right) {
     const int HLv = FULL ? HL : min(HL, nv);
-    // outputs xo = 0 .. HL-1: sum of positions [xo, xo + 14], stored at position xo
     T sm = rowp[0];
     win[0] = sm;
 #pragma unroll
@@ -227,7 +271,6 @@ __device__ __forceinline__ void hpass_half_row(T* rowp, bool right, int nv) {
       for (int j = 0; j < WN; ++j) {
         const int xo = xb + j;
         if (xo < HLv) {
-          // slot (j + 14) % 15 receives position xo + 14; slot j holds position xo (the one leaving the window)
           const T nw = rowp[xo + 2 * M];
           sm = hp_add(sm, nw);
           rowp[xo] = sm;
@@ -237,9 +280,7 @@ __device__ __forceinline__ void hpass_half_row(T* rowp, bool right, int nv) {
       }
     }
   } else if (TW > HL) {
-    // outputs xo = TW-1 .. HL: sum of positions [xo, xo + 14], stored at position xo + 14; walk right to left:
-    // mirrored index u = TW - 1 - xo, position q(u, k) = TW - 1 + 14 - u - k
-    T* top = rowp + (TW - 1 + 2 * M);                   // position of the right-most input
+    T* top = rowp + (TW - 1 + 2 * M);
     T sm = top[0];
     win[0] = sm;
 #pragma unroll
@@ -267,7 +308,7 @@ __device__ __forceinline__ void hpass_half_row(T* rowp, bool right, int nv) {
 #else
 #define FBW_BOUNDS __launch_bounds__(FBW_NT, 1)
 #endif
-template <int MODE, bool STATS>
+template <int MODE, bool STATS, bool HBLOCK>
 __global__ void FBW_BOUNDS fb_iter_ws(IterArgs a) {
   extern __shared__ __align__(16) float smem[];
   constexpr int EW = FBS_EW, TW = FBS_TW, M = FBS_M, RB = FBW_RB, NR = FBW_NR, ES = FBS_ES, HL = FBS_HL;
@@ -590,11 +631,11 @@ __global__ void FBW_BOUNDS fb_iter_ws(IterArgs a) {
           if (pr >= NR) pr -= NR;
           const bool right = q & 1;
           if (nv == TW) {
-            if (wide) hpass_half_row<float2, true>((q & 2 ? Pzw : Pxy) + pr * ES + woff, right, nv);
-            else hpass_half_row<float, true>(Pe + pr * ES + woff, right, nv);
+            if (wide) hpass_half_row<float2, true, HBLOCK>((q & 2 ? Pzw : Pxy) + pr * ES + woff, right, nv);
+            else hpass_half_row<float, true, HBLOCK>(Pe + pr * ES + woff, right, nv);
           } else {
-            if (wide) hpass_half_row<float2, false>((q & 2 ? Pzw : Pxy) + pr * ES + woff, right, nv);
-            else hpass_half_row<float, false>(Pe + pr * ES + woff, right, nv);
+            if (wide) hpass_half_row<float2, false, HBLOCK>((q & 2 ? Pzw : Pxy) + pr * ES + woff, right, nv);
+            else hpass_half_row<float, false, HBLOCK>(Pe + pr * ES + woff, right, nv);
           }
         }
       }

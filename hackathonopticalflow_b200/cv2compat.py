@@ -21,6 +21,7 @@ import numpy as np
 from . import _lib
 from ._lib import error, FarnebackParams, LKParams, GFTTParams
 
+FARNEBACK_BLOCKED_SUMS = 0x10000   # library extension, include/b2of.h: B2OF_FARNEBACK_BLOCKED_SUMS
 COLOR_BGR2GRAY = 6
 COLOR_RGB2GRAY = 7
 COLOR_BGRA2GRAY = 10
