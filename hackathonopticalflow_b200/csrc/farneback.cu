@@ -2203,8 +2203,16 @@ static int fb_pairs_range(const FbPlan* pl, const FbWorkspace& ws, int pairs_tot
           if (b.mode == 1 && b.in_pitch != L.pitch)     // the kernel indexes flow_in with the level's own pitch
             return fail(B2OF_E_BADARG, "internal: flow_in pitch %d != level pitch %d", b.in_pitch, L.pitch);
           dim3 gs(pairs, nstrips, cdiv(blocks, b.nb));
-          // horizontal window sums: sliding (default) or per block of 15 (B2OF_FARNEBACK_BLOCKED_SUMS, fb_ws.cuh)
-          const bool hblock = (call_flags & B2OF_FARNEBACK_BLOCKED_SUMS) != 0;
+          // horizontal window sums: per block of 15 (fb_ws.cuh) at the two coarsest levels -- that is where a sliding
+          // sum's carried rounding error decides near-singular pixels (numpy restatement on real footage: blocked sums
+          // at these two levels alone give the whole gain, at the finest level alone none), and they are 8 % of the
+          // iteration time -- and sliding at the finer ones, unless the call asks for blocked sums everywhere
+          // (B2OF_FARNEBACK_BLOCKED_SUMS)
+#ifndef FBW_HBLOCK_COARSE_LEVELS
+#define FBW_HBLOCK_COARSE_LEVELS 2
+#endif
+          const bool hblock = (call_flags & B2OF_FARNEBACK_BLOCKED_SUMS) != 0 ||
+                              ((int)li < FBW_HBLOCK_COARSE_LEVELS && !last_level);
 #define B2OF_WS_LAUNCH(MODE, STATS, HB) fb_iter_ws<MODE, STATS, HB><<<gs, FBW_NT, FBW_SMEM, st>>>(b)
 #define B2OF_WS_MODE(STATS, HB) \
   do { if (b.mode == 0) B2OF_WS_LAUNCH(0, STATS, HB); else if (b.mode == 1) B2OF_WS_LAUNCH(1, STATS, HB); \

@@ -222,10 +222,12 @@ def test_real_footage_sweep_full_1080p(b2, sweep, i):
 
 
 def test_farneback_blocked_sums_option_on_real_footage(b2, sweep, full1080):
-    """B2OF_FARNEBACK_BLOCKED_SUMS (library extension): the horizontal box sums per block of 15 instead of sliding.  Same
-    conditioning-aware bar as the default on every clip; on the stable pixels it agrees with the default to 0.03 px; on
-    the clip with the most near-singular pixels (the dark corridor) it leaves fewer pixels beyond 0.5 px than the
-    default (measured 46 against 73 of 32,400) -- and the batched entry gives the same bits as the single call."""
+    """Horizontal box sums per block of 15 instead of sliding: the default at the two coarsest pyramid levels (where a
+    sliding sum's carried rounding error decides near-singular pixels), everywhere with B2OF_FARNEBACK_BLOCKED_SUMS
+    (library extension flag).  Same conditioning-aware bar as the default on every clip; on the stable pixels the two
+    agree to 0.03 px; on the clip with the most near-singular pixels (the dark corridor) both leave about 45 of 32,400
+    sampled pixels beyond 0.5 px where sliding sums at every level left 73 (regression guard at 60) -- and the batched
+    entry gives the same bits as the single call."""
     flags = b2.FARNEBACK_BLOCKED_SUMS
     n_def = n_blk = None
     for i in range(4):
@@ -243,7 +245,7 @@ def test_farneback_blocked_sums_option_on_real_footage(b2, sweep, full1080):
             n_def, n_blk = int((d0 > FB_MAX_TOL).sum()), int((d > FB_MAX_TOL).sum())
             seq = b2.calcOpticalFlowFarnebackSequence(np.stack([g0, g1, g0]), flags=flags)
             assert np.array_equal(seq[0], blk)
-    assert n_blk < n_def, (n_blk, n_def)
+    assert n_def <= 60 and n_blk <= 60, (n_def, n_blk)
 
 
 @pytest.mark.parametrize("name", ["ref", "gauss", "p08", "even", "sig0"])
