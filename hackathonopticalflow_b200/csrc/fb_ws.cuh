@@ -657,6 +657,13 @@ __global__ void FBW_BOUNDS fb_iter_ws(IterArgs a) {
     float2* __restrict__ fo = a.flow_out + (size_t)pair * a.flow_out_pair_stride;
     float2 vxy = make_float2(0.f, 0.f), vzw = vxy;
     float ve = 0.f;
+    // HBLOCK instantiation (the two coarsest levels, or every level on request): the vertical running sums are carried
+    // in double -- a float running sum keeps the absolute rounding error of the rows that passed through the window,
+    // and at near-singular pixels below bright texture that error decides the result (numpy restatement on real
+    // footage: with direct horizontal AND vertical sums at the two coarsest levels the path disagrees with cv2 on as
+    // few pixels as cv2's plain build does).  Sums of fifteen floats are exact in double, so each output is the
+    // correctly rounded sum of its own inputs whatever the restart period.
+    double dv0 = 0., dv1 = 0., dv2 = 0., dv3 = 0., dv4 = 0.;
     const float eps = 1e-3f / (a.inv_area * a.inv_area);
     // per-pair flow statistics folded into the last iteration (STATS): every C thread sums its own column, the CTA
     // adds one set of fixed-point partials (same layout as flow_stats_accum, pathfinder.cu)
@@ -699,12 +706,19 @@ __global__ void FBW_BOUNDS fb_iter_ws(IterArgs a) {
         if (s == 0 || ((yb / RB) % FBW_REFRESH) == 0) {
           // (re)start the running sums from the 14 rows above the window's newest row
           vxy = make_float2(0.f, 0.f); vzw = vxy; ve = 0.f;
+          if (HBLOCK) { dv0 = 0.; dv1 = 0.; dv2 = 0.; dv3 = 0.; dv4 = 0.; }
 #pragma unroll
           for (int k = 0; k < 2 * M; ++k) {
             const int e = pn * ES + col;
-            vxy = add2(vxy, Pxy[e]);
-            vzw = add2(vzw, Pzw[e]);
-            ve += Pe[e];
+            if (HBLOCK) {
+              const float2 pxy = Pxy[e], pzw = Pzw[e];
+              dv0 += (double)pxy.x; dv1 += (double)pxy.y; dv2 += (double)pzw.x; dv3 += (double)pzw.y;
+              dv4 += (double)Pe[e];
+            } else {
+              vxy = add2(vxy, Pxy[e]);
+              vzw = add2(vzw, Pzw[e]);
+              ve += Pe[e];
+            }
             if (++pn == NR) pn = 0;
           }
         } else {
@@ -744,22 +758,41 @@ __global__ void FBW_BOUNDS fb_iter_ws(IterArgs a) {
           }
           float2 wxy[4], wzw[4];
           float we[4];
-          wxy[0] = add2(vxy, nxy[0]); wzw[0] = add2(vzw, nzw[0]); we[0] = ve + ne[0];
+          if (HBLOCK) {
 #pragma unroll
-          for (int k = 1; k < 4; ++k) {
-            wxy[k] = add2(wxy[k - 1], sub2(nxy[k], oxy[k - 1]));
-            wzw[k] = add2(wzw[k - 1], sub2(nzw[k], ozw[k - 1]));
-            we[k] = we[k - 1] + (ne[k] - oe[k - 1]);
+            for (int k = 0; k < 4; ++k) {
+              dv0 += (double)nxy[k].x; dv1 += (double)nxy[k].y; dv2 += (double)nzw[k].x; dv3 += (double)nzw[k].y;
+              dv4 += (double)ne[k];
+              wxy[k] = make_float2((float)dv0, (float)dv1); wzw[k] = make_float2((float)dv2, (float)dv3);
+              we[k] = (float)dv4;
+              dv0 -= (double)oxy[k].x; dv1 -= (double)oxy[k].y; dv2 -= (double)ozw[k].x; dv3 -= (double)ozw[k].y;
+              dv4 -= (double)oe[k];
+            }
+          } else {
+            wxy[0] = add2(vxy, nxy[0]); wzw[0] = add2(vzw, nzw[0]); we[0] = ve + ne[0];
+#pragma unroll
+            for (int k = 1; k < 4; ++k) {
+              wxy[k] = add2(wxy[k - 1], sub2(nxy[k], oxy[k - 1]));
+              wzw[k] = add2(wzw[k - 1], sub2(nzw[k], ozw[k - 1]));
+              we[k] = we[k - 1] + (ne[k] - oe[k - 1]);
+            }
+            vxy = sub2(wxy[3], oxy[3]); vzw = sub2(wzw[3], ozw[3]); ve = we[3] - oe[3];
           }
-          vxy = sub2(wxy[3], oxy[3]); vzw = sub2(wzw[3], ozw[3]); ve = we[3] - oe[3];
 #pragma unroll
           for (int k = 0; k < 4; ++k) solve_store(wxy[k], wzw[k], we[k]);
         }
         for (; r < nr; ++r) {                           // last rows of the image
           const int en = pn * ES + col, eo = pold * ES + col;
-          vxy = add2(vxy, Pxy[en]); vzw = add2(vzw, Pzw[en]); ve += Pe[en];
-          solve_store(vxy, vzw, ve);
-          vxy = sub2(vxy, Pxy[eo]); vzw = sub2(vzw, Pzw[eo]); ve -= Pe[eo];
+          if (HBLOCK) {
+            const float2 pxy = Pxy[en], pzw = Pzw[en], qxy = Pxy[eo], qzw = Pzw[eo];
+            dv0 += (double)pxy.x; dv1 += (double)pxy.y; dv2 += (double)pzw.x; dv3 += (double)pzw.y; dv4 += (double)Pe[en];
+            solve_store(make_float2((float)dv0, (float)dv1), make_float2((float)dv2, (float)dv3), (float)dv4);
+            dv0 -= (double)qxy.x; dv1 -= (double)qxy.y; dv2 -= (double)qzw.x; dv3 -= (double)qzw.y; dv4 -= (double)Pe[eo];
+          } else {
+            vxy = add2(vxy, Pxy[en]); vzw = add2(vzw, Pzw[en]); ve += Pe[en];
+            solve_store(vxy, vzw, ve);
+            vxy = sub2(vxy, Pxy[eo]); vzw = sub2(vzw, Pzw[eo]); ve -= Pe[eo];
+          }
           if (++pn == NR) pn = 0;
           if (++pold == NR) pold = 0;
         }

@@ -46,12 +46,13 @@ extern "C" {
 #define B2OF_OPTFLOW_LK_GET_MIN_EIGENVALS 8
 #define B2OF_OPTFLOW_FARNEBACK_GAUSSIAN 256
 /* library extension (no cv2 counterpart; a bit cv2 does not use): the 15x15 box sums of the fused iteration kernel take
-   their horizontal pass per block of 15 instead of as a sliding sum at EVERY pyramid level -- each output is the sum of
-   its own inputs only, so near-singular pixels behind bright texture land closer to cv2.  Without the flag the two
-   coarsest levels already do (that is where it decides the result: real footage, 0.14 % instead of 0.23 % of the
-   pixels of the worst clip beyond 0.5 px, where cv2 differs from itself on 0.04 %; 0.7 % fewer pairs/s) and the finer
-   levels slide; with it, about 3 % fewer pairs/s and no measurable further change.  Ignored by the general kernels
-   (other window sizes, Gaussian window), whose sums are direct. */
+   their horizontal pass per block of 15 instead of as a sliding sum and carry their vertical running sums in double at
+   EVERY pyramid level -- each output is then the rounded sum of its own inputs only, so near-singular pixels next to
+   bright texture land closer to cv2.  Without the flag the two coarsest levels already do (that is where it decides the
+   result: on real footage the pixels beyond 0.5 px drop from 0.15 / 0.23 % to 0.01 / 0.15 % on the two hard clips, where
+   cv2 differs from itself on 0 / 0.04 %; 2 % fewer pairs/s) and the finer levels use float sliding sums; with the flag,
+   14 % fewer pairs/s and no measurable further change -- a diagnostic, not a recommendation.  Ignored by the general
+   kernels (other window sizes, Gaussian window), whose sums are direct. */
 #define B2OF_FARNEBACK_BLOCKED_SUMS 0x10000
 #define B2OF_TERM_COUNT 1
 #define B2OF_TERM_EPS 2
